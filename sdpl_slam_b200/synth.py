@@ -1,0 +1,63 @@
+"""Deterministic synthetic frames shared by the oracle, the CPU baseline and the GPU path
+(SURVEY.md section 8d).  Pure numpy integer arithmetic, seeded with PCG64, so the same seed gives the
+same bytes on every machine.
+
+frame(seed) = low-resolution uniform noise (1/4 resolution) bilinearly upsampled with integer weights
+(gives FAST corners everywhere) + 40 filled random rectangles (gives LSD line segments) + +-2 grey
+levels of pixel noise.  partner(seed) = the same frame shifted by a few integer pixels with a
+brightness offset (for frame-to-frame matching).
+"""
+import numpy as np
+
+
+def frame(seed: int, h: int = 375, w: int = 1242, n_rect: int = 40) -> np.ndarray:
+    rng = np.random.default_rng(int(seed))
+    gh, gw = (h + 3) // 4 + 2, (w + 3) // 4 + 2
+    lat = rng.integers(0, 256, size=(gh, gw), dtype=np.int64)
+    ys, xs = np.arange(h), np.arange(w)
+    y0, fy = ys // 4, ys % 4
+    x0, fx = xs // 4, xs % 4
+    a = lat[y0][:, x0] * (4 - fx)[None, :] + lat[y0][:, x0 + 1] * fx[None, :]
+    b = lat[y0 + 1][:, x0] * (4 - fx)[None, :] + lat[y0 + 1][:, x0 + 1] * fx[None, :]
+    img = (a * (4 - fy)[:, None] + b * fy[:, None] + 8) // 16
+    # compress the texture contrast a little and paint rectangles
+    img = 64 + img // 2
+    for _ in range(n_rect):
+        rw = int(rng.integers(20, max(21, w // 4)))
+        rh = int(rng.integers(20, max(21, h // 2)))
+        rx = int(rng.integers(0, max(1, w - rw)))
+        ry = int(rng.integers(0, max(1, h - rh)))
+        g = int(rng.integers(0, 256))
+        tex = int(rng.integers(0, 3))   # 0: flat, 1/2: keep some texture inside
+        if tex == 0:
+            img[ry:ry + rh, rx:rx + rw] = g
+        else:
+            img[ry:ry + rh, rx:rx + rw] = (img[ry:ry + rh, rx:rx + rw] + 3 * g) // 4
+    img = img + rng.integers(-2, 3, size=(h, w))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def partner(seed: int, h: int = 375, w: int = 1242, dx: int = 3, dy: int = 1, gain: int = 6) -> np.ndarray:
+    """Integer-shifted, brightness-offset copy of frame(seed) (edge pixels replicated)."""
+    f = frame(seed, h, w).astype(np.int64)
+    ys = np.clip(np.arange(h) - dy, 0, h - 1)
+    xs = np.clip(np.arange(w) - dx, 0, w - 1)
+    return np.clip(f[ys][:, xs] + gain, 0, 255).astype(np.uint8)
+
+
+def frames(seeds, h: int = 375, w: int = 1242) -> np.ndarray:
+    return np.stack([frame(s, h, w) for s in seeds])
+
+
+def map_descriptors(desc: np.ndarray, n_map: int, seed: int, flips: int = 12) -> np.ndarray:
+    """Config-3 style map: the frame's own descriptors with `flips` random bits flipped, padded with
+    uniform random 256-bit strings up to n_map rows, then shuffled."""
+    rng = np.random.default_rng(int(seed))
+    own = desc.copy()
+    for i in range(own.shape[0]):
+        bits = rng.choice(256, size=flips, replace=False)
+        for b in bits:
+            own[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    rest = rng.integers(0, 256, size=(max(0, n_map - own.shape[0]), 32), dtype=np.uint8)
+    allm = np.concatenate([own, rest])[:n_map]
+    return allm[rng.permutation(allm.shape[0])].copy()
