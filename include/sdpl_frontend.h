@@ -1,0 +1,147 @@
+/*
+ * sdpl_frontend.h -- C ABI of the B200-native (sm_100a CUDA) SDPL-SLAM feature front-end.
+ *
+ * This is the drop-in boundary for the per-frame front-end of argyrissm/SDPL-SLAM: every entry point
+ * below replaces one C++ interface of the reference (cited as file:line, relative to the reference
+ * root).  Plain pointers and sizes only; int status codes; no exceptions cross the boundary.
+ * One handle = one CUDA device + one stream + one pre-allocated device arena.  A handle is not
+ * thread-safe; different handles are independent.  There is NO CPU fallback: every call needs a
+ * CUDA device and returns SDPL_ERR_CUDA otherwise.
+ *
+ * Host <-> device: the *_extract / *_match entry points take HOST buffers (they are what
+ * Frame::ExtractORB / Frame::ExtractLines would call, src/Frame.cc:927-949).  The *_dev entry points
+ * take DEVICE pointers and leave results on the device (throughput path, batch of frames resident in HBM).
+ */
+#ifndef SDPL_FRONTEND_H
+#define SDPL_FRONTEND_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* == cv::KeyPoint (28 B POD): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } sdpl_keypoint;
+/* == cv::line_descriptor::KeyLine (68 B POD), 3rdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp */
+typedef struct {
+  float angle; int32_t class_id, octave; float pt_x, pt_y, response, size;
+  float sx, sy, ex, ey, sx_oct, sy_oct, ex_oct, ey_oct, length; int32_t num_pixels;
+} sdpl_keyline;
+/* == cv::DMatch (16 B POD): queryIdx, trainIdx, imgIdx, distance */
+typedef struct { int32_t query, train, img; float distance; } sdpl_dmatch;
+
+enum {
+  SDPL_OK = 0,
+  SDPL_ERR_ARG = 1,        /* bad argument (null pointer, non-positive size, unsupported parameter) */
+  SDPL_ERR_CUDA = 2,       /* CUDA runtime failure / no device (there is no CPU fallback) */
+  SDPL_ERR_CAPACITY = 3,   /* caller-provided output capacity too small (n_out holds the needed count) */
+  SDPL_ERR_OVERFLOW = 4,   /* an internal device buffer overflowed (reported, never silently truncated) */
+  SDPL_ERR_UNSUPPORTED = 5 /* configuration outside what the kernels implement (e.g. extractor==1 / EDLines) */
+};
+const char* sdpl_strerror(int code);
+/* last CUDA / internal error text of the calling thread (empty string if none) */
+const char* sdpl_last_error(void);
+int sdpl_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB extractor -- replaces SDPL_SLAM::ORBextractor (include/ORBextractor.h:33-99, src/ORBextractor.cc)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sdpl_orb sdpl_orb;
+/* ORBextractor::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST), src/ORBextractor.cc:399-459 */
+int sdpl_orb_create(sdpl_orb** h, int nfeatures, float scale, int nlevels, int ini_th, int min_th, int device);
+void sdpl_orb_destroy(sdpl_orb* h);
+/* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:49-69); each array has nlevels entries; any pointer may be NULL */
+int sdpl_orb_levels(const sdpl_orb* h);
+int sdpl_orb_tables(const sdpl_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2);
+/* mnFeaturesPerLevel (src/ORBextractor.cc:424-435) and umax[16] (:443-458), for parity tests */
+int sdpl_orb_quota(const sdpl_orb* h, int* per_level, int* umax16);
+/* upper bound of keypoints one frame can produce (sum over levels of quota+3) */
+int sdpl_orb_max_keypoints(const sdpl_orb* h);
+/* ORBextractor::operator()(image, mask (ignored), keypoints, descriptors), src/ORBextractor.cc:1035-1110.
+ * img: HOST u8 grayscale, row stride in bytes.  kps/desc: HOST outputs, capacity rows (desc is capacity x 32).
+ * Empty image (w<=0 or h<=0 or img==NULL) -> *n_out = 0, SDPL_OK (the reference returns silently, :1038). */
+int sdpl_orb_extract(sdpl_orb* h, const uint8_t* img, int w, int h_, int stride,
+                     sdpl_keypoint* kps, uint8_t* desc, int capacity, int* n_out);
+/* Batch of nframes same-size frames.  imgs: HOST pointer to frame 0, frames frame_stride bytes apart.
+ * Outputs: frame f writes kps[f*capacity ...], desc[(f*capacity)*32 ...], n_out[f]. */
+int sdpl_orb_extract_batch(sdpl_orb* h, const uint8_t* imgs, int nframes, int w, int h_, int stride, size_t frame_stride,
+                           sdpl_keypoint* kps, uint8_t* desc, int capacity, int* n_out);
+/* Same with DEVICE pointers for input and outputs; asynchronous on the handle's stream unless sync != 0.
+ * n_out is a DEVICE int array [nframes]. */
+int sdpl_orb_extract_batch_dev(sdpl_orb* h, const uint8_t* d_imgs, int nframes, int w, int h_, int stride,
+                               size_t frame_stride, sdpl_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n_out,
+                               int sync);
+/* mvImagePyramid (include/ORBextractor.h:71): copies the padded (w+38)x(h+38) plane of `level` of frame `frame` of
+ * the last call to a HOST buffer with row stride out_stride; w_out/h_out receive the interior size. out may be NULL. */
+int sdpl_orb_pyramid_level(sdpl_orb* h, int frame, int level, uint8_t* out, int out_stride, int* w_out, int* h_out);
+/* stage introspection for parity tests: blurred level (w x h), FAST/NMS candidates given to DistributeOctTree */
+int sdpl_orb_blurred_level(sdpl_orb* h, int frame, int level, uint8_t* out, int out_stride);
+int sdpl_orb_candidates(sdpl_orb* h, int frame, int level, int* xs, int* ys, int* resp, int capacity, int* n_out);
+int sdpl_orb_level_counts(sdpl_orb* h, int frame, int* per_level);
+/* number of kernels the last extract call launched (for bench.py's gpu_launches) */
+int sdpl_orb_last_launches(const sdpl_orb* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Line extractor -- replaces SDPL_SLAM::Lineextractor (include/Lineextractor.h:51-87, src/Lineextractor.cc:42-99)
+ * = LSDDetectorC::detect (3rdparty/line_descriptor/src/LSDDetector_custom.cpp:254-369, cv::LineSegmentDetector inside)
+ * + BinaryDescriptor::compute (binary_descriptor_custom.cpp:524-687, computeLBD :1026-1372)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sdpl_line sdpl_line;
+/* Lineextractor(lsd_nfeatures, lsd_refine, lsd_scale, nlevels, scale, extractor), src/Lineextractor.cc:36-40.
+ * extractor must be 0 (LSD); 1 (EDLines) returns SDPL_ERR_UNSUPPORTED. */
+int sdpl_line_create(sdpl_line** h, int nfeatures, int refine, float lsd_scale, int nlevels, float scale, int extractor,
+                     int device);
+void sdpl_line_destroy(sdpl_line* h);
+/* mvScaleFactor_l / mvInvScaleFactor_l / mvLevelSigma2_l / mvInvLevelSigma2_l (include/Lineextractor.h:66-75) */
+int sdpl_line_levels(const sdpl_line* h);
+int sdpl_line_tables(const sdpl_line* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2);
+/* Lineextractor::operator()(image, mask (ignored), keylines, descriptors_line) */
+int sdpl_line_extract(sdpl_line* h, const uint8_t* img, int w, int h_, int stride,
+                      sdpl_keyline* kls, uint8_t* desc, int capacity, int* n_out);
+int sdpl_line_extract_batch(sdpl_line* h, const uint8_t* imgs, int nframes, int w, int h_, int stride, size_t frame_stride,
+                            sdpl_keyline* kls, uint8_t* desc, int capacity, int* n_out);
+int sdpl_line_extract_batch_dev(sdpl_line* h, const uint8_t* d_imgs, int nframes, int w, int h_, int stride,
+                                size_t frame_stride, sdpl_keyline* d_kls, uint8_t* d_desc, int capacity, int* d_n_out,
+                                int sync);
+/* BinaryDescriptor::compute(image, keylines, descriptors) alone, on caller-provided keylines (HOST buffers) */
+int sdpl_line_lbd_compute(sdpl_line* h, const uint8_t* img, int w, int h_, int stride,
+                          const sdpl_keyline* kls, int n, uint8_t* desc);
+/* raw cv::LineSegmentDetector::detect output (x1,y1,x2,y2 per line) of pyramid level `octave` of the last
+ * single-frame call, for parity tests */
+int sdpl_line_lsd_segments(sdpl_line* h, int frame, int octave, float* xyxy, int capacity, int* n_out);
+int sdpl_line_last_launches(const sdpl_line* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Descriptor matcher -- 256-bit Hamming (cv::line_descriptor::match, bitops_custom.hpp:86-99) brute force;
+ * surface of BinaryDescriptorMatcher::match / knnMatch / radiusMatch (binary_descriptor_matcher.cpp:197-504).
+ * best/second by strict '<' over ascending train index (ties -> lowest train index). distance = (float)hamming.
+ * Missing neighbour (nt < 2): train = -1, distance = 257.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sdpl_matcher sdpl_matcher;
+int sdpl_matcher_create(sdpl_matcher** h, int device);
+void sdpl_matcher_destroy(sdpl_matcher* h);
+int sdpl_match_knn2(sdpl_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                    sdpl_dmatch* best, sdpl_dmatch* second);
+/* knn2 + ratio test d1 < ratio*d2 and d1 <= max_dist: rejected rows get train = -1; *n_acc = accepted count */
+int sdpl_match_ratio(sdpl_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt, float ratio, int max_dist,
+                     sdpl_dmatch* out, int* n_acc);
+/* radius search: counts[i] = #train within radius; out[i*k ..] = k nearest within radius (ascending distance, index) */
+int sdpl_match_radius(sdpl_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt, int radius, int k,
+                      int* counts, sdpl_dmatch* out);
+/* Batched DEVICE variant: npairs problems; problem p matches d_q + p*q_stride (nq[p] rows) against
+ * d_t + p*t_stride (nt[p] rows); d_nq/d_nt are DEVICE int arrays; outputs [p*max_q + i]. */
+int sdpl_match_knn2_batch_dev(sdpl_matcher* h, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t,
+                              const int* d_nt, size_t t_stride, int npairs, int max_q, int max_t, sdpl_dmatch* d_best,
+                              sdpl_dmatch* d_second, int sync);
+int sdpl_matcher_last_launches(const sdpl_matcher* h);
+
+/* Bind a handle's work to a caller stream (cudaStream_t as void*; NULL = the handle's own stream). */
+int sdpl_orb_set_stream(sdpl_orb* h, void* cuda_stream);
+int sdpl_line_set_stream(sdpl_line* h, void* cuda_stream);
+int sdpl_matcher_set_stream(sdpl_matcher* h, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

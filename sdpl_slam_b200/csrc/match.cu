@@ -1,0 +1,319 @@
+// match.cu -- brute-force 256-bit Hamming matching on sm_100a.
+// Metric: cv::line_descriptor::match(P,Q,32), 3rdparty/line_descriptor/src/bitops_custom.hpp:86-99.
+// Surface: BinaryDescriptorMatcher::match / knnMatch / radiusMatch (binary_descriptor_matcher.cpp:197-504).
+//
+// K10: one warp owns QW query descriptors (8 x u32 each, in registers of every lane); the 32 lanes stride
+// over the train rows with two 128-bit loads per row, popc the XOR, and keep a private top-2 per query;
+// the lanes' top-2 are merged with warp shuffles under the total order (distance, train index), which is
+// exactly "strict '<' while scanning ascending train index" (ties -> lowest index).  The train set is split
+// across blockIdx.y to fill the 148 SMs; partial top-2 are merged by a second tiny kernel.
+// This kernel is popc-issue bound, not HBM bound (Q*T*8 popc vs (Q+T)*32 bytes).
+#include "common.cuh"
+#include <algorithm>
+
+namespace sdpl {
+
+constexpr int kQW = 4;           // queries per warp
+constexpr int kWarps = 8;        // warps per block
+constexpr uint32_t kNoDist = 257;
+
+struct Top2 { uint32_t d1, i1, d2, i2; };
+
+__device__ __forceinline__ void top2_insert(Top2& t, uint32_t d, uint32_t i) {
+  // (d,i) lexicographic; callers feed ascending i per lane so '<' on d alone would do inside a lane,
+  // but the merge needs the full order.
+  if (d < t.d1 || (d == t.d1 && i < t.i1)) { t.d2 = t.d1; t.i2 = t.i1; t.d1 = d; t.i1 = i; }
+  else if (d < t.d2 || (d == t.d2 && i < t.i2)) { t.d2 = d; t.i2 = i; }
+}
+
+__device__ __forceinline__ Top2 top2_warp_merge(Top2 t) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    Top2 u;
+    u.d1 = __shfl_xor_sync(0xffffffffu, t.d1, o); u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+    u.d2 = __shfl_xor_sync(0xffffffffu, t.d2, o); u.i2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+    top2_insert(t, u.d1, u.i1);
+    top2_insert(t, u.d2, u.i2);
+  }
+  return t;
+}
+
+// partial[(p*max_q + q)*nsplit + s]
+__global__ void __launch_bounds__(kWarps * 32) k_match_partial(const uint8_t* __restrict__ q, const int* __restrict__ nq_arr,
+                                                               size_t q_stride, const uint8_t* __restrict__ t,
+                                                               const int* __restrict__ nt_arr, size_t t_stride, int max_q,
+                                                               int nsplit, Top2* __restrict__ partial) {
+  const int p = blockIdx.z, s = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nq = nq_arr[p], nt = nt_arr[p];
+  const int q0 = (blockIdx.x * kWarps + warp) * kQW;
+  if (q0 >= nq) return;
+  const uint8_t* qp = q + (size_t)p * q_stride;
+  const uint8_t* tp = t + (size_t)p * t_stride;
+  uint32_t qw[kQW][8];
+#pragma unroll
+  for (int k = 0; k < kQW; k++) {
+    int qi = min(q0 + k, nq - 1);
+    const uint4* src = (const uint4*)(qp + (size_t)qi * 32);
+    uint4 a = __ldg(src), b = __ldg(src + 1);
+    qw[k][0] = a.x; qw[k][1] = a.y; qw[k][2] = a.z; qw[k][3] = a.w;
+    qw[k][4] = b.x; qw[k][5] = b.y; qw[k][6] = b.z; qw[k][7] = b.w;
+  }
+  Top2 best[kQW];
+#pragma unroll
+  for (int k = 0; k < kQW; k++) best[k] = Top2{kNoDist, 0xFFFFFFFFu, kNoDist, 0xFFFFFFFFu};
+  // this split's train range
+  const int per = (nt + nsplit - 1) / nsplit;
+  const int tb = s * per, te = min(nt, tb + per);
+  for (int j = tb + lane; j < te; j += 32) {
+    const uint4* src = (const uint4*)(tp + (size_t)j * 32);
+    uint4 a = __ldg(src), b = __ldg(src + 1);
+#pragma unroll
+    for (int k = 0; k < kQW; k++) {
+      uint32_t d = __popc(qw[k][0] ^ a.x) + __popc(qw[k][1] ^ a.y) + __popc(qw[k][2] ^ a.z) + __popc(qw[k][3] ^ a.w) +
+                   __popc(qw[k][4] ^ b.x) + __popc(qw[k][5] ^ b.y) + __popc(qw[k][6] ^ b.z) + __popc(qw[k][7] ^ b.w);
+      // ascending j inside a lane: strict '<' keeps the lowest index on ties
+      if (d < best[k].d1) { best[k].d2 = best[k].d1; best[k].i2 = best[k].i1; best[k].d1 = d; best[k].i1 = j; }
+      else if (d < best[k].d2) { best[k].d2 = d; best[k].i2 = j; }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kQW; k++) {
+    Top2 m = top2_warp_merge(best[k]);
+    if (lane == 0 && q0 + k < nq) partial[((size_t)p * max_q + q0 + k) * nsplit + s] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_match_merge(const Top2* __restrict__ partial, const int* __restrict__ nq_arr, int max_q,
+                                                     int nsplit, sdpl_dmatch* __restrict__ best, sdpl_dmatch* __restrict__ second) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq_arr[p]) return;
+  Top2 t{kNoDist, 0xFFFFFFFFu, kNoDist, 0xFFFFFFFFu};
+  const Top2* src = partial + ((size_t)p * max_q + i) * nsplit;
+  for (int s = 0; s < nsplit; s++) { Top2 u = src[s]; top2_insert(t, u.d1, u.i1); top2_insert(t, u.d2, u.i2); }
+  sdpl_dmatch b, c;
+  b.query = i; b.train = t.d1 == kNoDist ? -1 : (int)t.i1; b.img = 0; b.distance = (float)t.d1;
+  c.query = i; c.train = t.d2 == kNoDist ? -1 : (int)t.i2; c.img = 0; c.distance = (float)t.d2;
+  best[(size_t)p * max_q + i] = b;
+  second[(size_t)p * max_q + i] = c;
+}
+
+// ratio + max-distance filter; counts accepted matches per problem
+__global__ void __launch_bounds__(256) k_match_ratio(const sdpl_dmatch* __restrict__ best, const sdpl_dmatch* __restrict__ second, int nq,
+                                                     float ratio, float max_dist, sdpl_dmatch* __restrict__ out, int* __restrict__ n_acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i < nq) {
+    sdpl_dmatch b = best[i], s = second[i];
+    ok = b.train >= 0 && b.distance <= max_dist && b.distance < __fmul_rn(ratio, s.distance);
+    if (!ok) b.train = -1;
+    out[i] = b;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_acc, __popc(m));
+}
+
+// radius search: one warp per query; counts all train rows within radius and keeps the k nearest
+// (ascending (distance, index)) by k rounds of warp-wide arg-min selection over a per-lane scan.
+__global__ void __launch_bounds__(256) k_match_radius(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
+                                                      int radius, int k, int* __restrict__ counts, sdpl_dmatch* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (qi >= nq) return;
+  uint32_t qw[8];
+  {
+    const uint4* src = (const uint4*)(q + (size_t)qi * 32);
+    uint4 a = __ldg(src), b = __ldg(src + 1);
+    qw[0] = a.x; qw[1] = a.y; qw[2] = a.z; qw[3] = a.w; qw[4] = b.x; qw[5] = b.y; qw[6] = b.z; qw[7] = b.w;
+  }
+  int cnt = 0;
+  uint32_t last_d = 0, last_i = 0;   // last emitted (distance, index); next must be strictly greater
+  bool first = true;
+  for (int r = 0; r <= k; r++) {
+    // pass r: find the smallest (d,i) > (last_d,last_i) with d <= radius; pass 0 also counts
+    uint32_t bd = kNoDist, bi = 0xFFFFFFFFu;
+    for (int j = lane; j < nt; j += 32) {
+      const uint4* src = (const uint4*)(t + (size_t)j * 32);
+      uint4 a = __ldg(src), b = __ldg(src + 1);
+      uint32_t d = __popc(qw[0] ^ a.x) + __popc(qw[1] ^ a.y) + __popc(qw[2] ^ a.z) + __popc(qw[3] ^ a.w) +
+                   __popc(qw[4] ^ b.x) + __popc(qw[5] ^ b.y) + __popc(qw[6] ^ b.z) + __popc(qw[7] ^ b.w);
+      if ((int)d > radius) continue;
+      if (r == 0) cnt++;
+      bool after = first || d > last_d || (d == last_d && (uint32_t)j > last_i);
+      if (after && (d < bd || (d == bd && (uint32_t)j < bi))) { bd = d; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      uint32_t od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (r == 0) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (lane == 0) counts[qi] = cnt;
+    }
+    if (r == k) break;
+    if (lane == 0) {
+      sdpl_dmatch m;
+      m.query = qi; m.img = 0;
+      if (bd == kNoDist) { m.train = -1; m.distance = 257.f; } else { m.train = (int)bi; m.distance = (float)bd; }
+      out[(size_t)qi * k + r] = m;
+    }
+    if (bd == kNoDist) {
+      // nothing left: fill the remaining slots
+      if (lane == 0) for (int rr = r + 1; rr < k; rr++) { sdpl_dmatch m{qi, -1, 0, 257.f}; out[(size_t)qi * k + rr] = m; }
+      break;
+    }
+    last_d = bd; last_i = bi; first = false;
+  }
+}
+
+}  // namespace sdpl
+
+using namespace sdpl;
+
+struct sdpl_matcher {
+  int device;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  DevBuf q, t, best, second, out, partial, scal, counts;
+  int launches = 0;
+  int sm_count = 148;
+};
+
+static int match_run_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t, const int* d_nt,
+                         size_t t_stride, int npairs, int max_q, int max_t, sdpl_dmatch* d_best, sdpl_dmatch* d_second) {
+  // choose the train split so that the grid covers the SMs a few times
+  int qblocks = div_up(max_q, kWarps * kQW);
+  int nsplit = std::max(1, std::min(div_up(4 * m->sm_count, std::max(1, qblocks * npairs)), div_up(max_t, 64)));
+  nsplit = std::min(nsplit, 64);
+  int rc = m->partial.reserve(sizeof(Top2) * (size_t)npairs * max_q * nsplit);
+  if (rc) return rc;
+  k_match_partial<<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q, nsplit,
+                                                                                 m->partial.as<Top2>());
+  SDPL_LAUNCH_CHECK();
+  k_match_merge<<<dim3(div_up(max_q, 256), npairs), 256, 0, m->stream>>>(m->partial.as<Top2>(), d_nq, max_q, nsplit, d_best, d_second);
+  SDPL_LAUNCH_CHECK();
+  return SDPL_OK;
+}
+
+extern "C" {
+
+int sdpl_matcher_create(sdpl_matcher** out, int device) {
+  if (!out) return SDPL_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    set_last_error("sdpl_matcher_create: no such CUDA device (this library has no CPU fallback)");
+    return SDPL_ERR_CUDA;
+  }
+  SDPL_CUDA(cudaSetDevice(device));
+  sdpl_matcher* m = new sdpl_matcher;
+  m->device = device;
+  cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+  SDPL_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  m->stream = m->own_stream;
+  *out = m;
+  return SDPL_OK;
+}
+
+void sdpl_matcher_destroy(sdpl_matcher* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  for (DevBuf* b : {&m->q, &m->t, &m->best, &m->second, &m->out, &m->partial, &m->scal, &m->counts}) b->release();
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  delete m;
+}
+int sdpl_matcher_set_stream(sdpl_matcher* m, void* s) { if (!m) return SDPL_ERR_ARG; m->stream = s ? (cudaStream_t)s : m->own_stream; return SDPL_OK; }
+int sdpl_matcher_last_launches(const sdpl_matcher* m) { return m ? m->launches : 0; }
+
+int sdpl_match_knn2_batch_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t, const int* d_nt,
+                              size_t t_stride, int npairs, int max_q, int max_t, sdpl_dmatch* d_best, sdpl_dmatch* d_second, int sync) {
+  if (!m || !d_q || !d_nq || !d_t || !d_nt || npairs < 1 || max_q < 1 || max_t < 1 || !d_best || !d_second) {
+    set_last_error("sdpl_match_knn2_batch_dev: bad argument");
+    return SDPL_ERR_ARG;
+  }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  g_launches = 0;
+  int rc = match_run_dev(m, d_q, d_nq, q_stride, d_t, d_nt, t_stride, npairs, max_q, max_t, d_best, d_second);
+  m->launches = g_launches;
+  if (rc) return rc;
+  if (sync) SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  return SDPL_OK;
+}
+
+static int match_host_common(sdpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt) {
+  int rc;
+  if ((rc = m->q.reserve((size_t)nq * 32))) return rc;
+  if ((rc = m->t.reserve((size_t)std::max(nt, 1) * 32))) return rc;
+  if ((rc = m->best.reserve(sizeof(sdpl_dmatch) * nq))) return rc;
+  if ((rc = m->second.reserve(sizeof(sdpl_dmatch) * nq))) return rc;
+  if ((rc = m->out.reserve(sizeof(sdpl_dmatch) * nq))) return rc;
+  if ((rc = m->scal.reserve(sizeof(int) * 4))) return rc;
+  SDPL_CUDA(cudaMemcpyAsync(m->q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+  if (nt > 0) SDPL_CUDA(cudaMemcpyAsync(m->t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+  int scal[4] = {nq, nt, 0, 0};
+  SDPL_CUDA(cudaMemcpyAsync(m->scal.p, scal, sizeof(scal), cudaMemcpyHostToDevice, m->stream));
+  return match_run_dev(m, m->q.as<uint8_t>(), m->scal.as<int>(), 0, m->t.as<uint8_t>(), m->scal.as<int>() + 1, 0, 1, nq, std::max(nt, 1),
+                       m->best.as<sdpl_dmatch>(), m->second.as<sdpl_dmatch>());
+}
+
+int sdpl_match_knn2(sdpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, sdpl_dmatch* best, sdpl_dmatch* second) {
+  if (!m || nq < 0 || nt < 0) { set_last_error("sdpl_match_knn2: bad argument"); return SDPL_ERR_ARG; }
+  if (nq == 0) return SDPL_OK;   // the reference matcher prints and returns on empty inputs (binary_descriptor_matcher.cpp:201-205)
+  if (!q || (nt > 0 && !t) || !best || !second) { set_last_error("sdpl_match_knn2: null pointer"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  g_launches = 0;
+  int rc = match_host_common(m, q, nq, t, nt);
+  m->launches = g_launches;
+  if (rc) return rc;
+  SDPL_CUDA(cudaMemcpyAsync(best, m->best.p, sizeof(sdpl_dmatch) * nq, cudaMemcpyDeviceToHost, m->stream));
+  SDPL_CUDA(cudaMemcpyAsync(second, m->second.p, sizeof(sdpl_dmatch) * nq, cudaMemcpyDeviceToHost, m->stream));
+  SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  return SDPL_OK;
+}
+
+int sdpl_match_ratio(sdpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, float ratio, int max_dist, sdpl_dmatch* out,
+                     int* n_acc) {
+  if (!m || nq < 0 || nt < 0 || !n_acc) { set_last_error("sdpl_match_ratio: bad argument"); return SDPL_ERR_ARG; }
+  *n_acc = 0;
+  if (nq == 0) return SDPL_OK;
+  if (!q || (nt > 0 && !t) || !out) { set_last_error("sdpl_match_ratio: null pointer"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  g_launches = 0;
+  int rc = match_host_common(m, q, nq, t, nt);
+  if (rc) { m->launches = g_launches; return rc; }
+  k_match_ratio<<<div_up(nq, 256), 256, 0, m->stream>>>(m->best.as<sdpl_dmatch>(), m->second.as<sdpl_dmatch>(), nq, ratio, (float)max_dist,
+                                                        m->out.as<sdpl_dmatch>(), m->scal.as<int>() + 2);
+  SDPL_LAUNCH_CHECK();
+  m->launches = g_launches;
+  SDPL_CUDA(cudaMemcpyAsync(out, m->out.p, sizeof(sdpl_dmatch) * nq, cudaMemcpyDeviceToHost, m->stream));
+  SDPL_CUDA(cudaMemcpyAsync(n_acc, m->scal.as<int>() + 2, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  return SDPL_OK;
+}
+
+int sdpl_match_radius(sdpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int radius, int k, int* counts, sdpl_dmatch* out) {
+  if (!m || nq < 0 || nt < 0 || k < 0 || radius < 0) { set_last_error("sdpl_match_radius: bad argument"); return SDPL_ERR_ARG; }
+  if (nq == 0) return SDPL_OK;
+  if (!q || (nt > 0 && !t) || !counts || (k > 0 && !out)) { set_last_error("sdpl_match_radius: null pointer"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = m->q.reserve((size_t)nq * 32))) return rc;
+  if ((rc = m->t.reserve((size_t)std::max(nt, 1) * 32))) return rc;
+  if ((rc = m->counts.reserve(sizeof(int) * nq))) return rc;
+  if ((rc = m->out.reserve(sizeof(sdpl_dmatch) * (size_t)nq * std::max(k, 1)))) return rc;
+  SDPL_CUDA(cudaMemcpyAsync(m->q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+  if (nt > 0) SDPL_CUDA(cudaMemcpyAsync(m->t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+  g_launches = 0;
+  k_match_radius<<<div_up(nq, 8), 256, 0, m->stream>>>(m->q.as<uint8_t>(), nq, m->t.as<uint8_t>(), nt, radius, k, m->counts.as<int>(),
+                                                       m->out.as<sdpl_dmatch>());
+  SDPL_LAUNCH_CHECK();
+  m->launches = g_launches;
+  SDPL_CUDA(cudaMemcpyAsync(counts, m->counts.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
+  if (k > 0) SDPL_CUDA(cudaMemcpyAsync(out, m->out.p, sizeof(sdpl_dmatch) * (size_t)nq * k, cudaMemcpyDeviceToHost, m->stream));
+  SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  return SDPL_OK;
+}
+
+}  // extern "C"

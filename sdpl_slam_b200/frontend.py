@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference front-end interface over the C ABI (include/sdpl_frontend.h).
+
+Class and method names follow the reference (argyrissm/SDPL-SLAM):
+  ORBextractor            include/ORBextractor.h:33-99    (operator() -> __call__)
+  Lineextractor           include/Lineextractor.h:51-87   (operator() -> __call__)
+  BinaryDescriptorMatcher 3rdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp:1015-1126
+All compute happens in the sm_100a CUDA library `lib/libsdpl_frontend.so`; there is no CPU fallback and the
+import of this module fails loudly when the library is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsdpl_frontend.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+KL_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt_x", "<f4"), ("pt_y", "<f4"),
+                     ("response", "<f4"), ("size", "<f4"), ("sx", "<f4"), ("sy", "<f4"), ("ex", "<f4"), ("ey", "<f4"),
+                     ("sx_oct", "<f4"), ("sy_oct", "<f4"), ("ex_oct", "<f4"), ("ey_oct", "<f4"), ("length", "<f4"),
+                     ("num_pixels", "<i4")])
+DM_DTYPE = np.dtype([("query", "<i4"), ("train", "<i4"), ("img", "<i4"), ("distance", "<f4")])
+
+SDPL_OK, SDPL_ERR_ARG, SDPL_ERR_CUDA, SDPL_ERR_CAPACITY, SDPL_ERR_OVERFLOW, SDPL_ERR_UNSUPPORTED = range(6)
+
+
+class SdplError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sdpl_frontend error %d (%s): %s" % (code, _strerror(code), msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the CUDA front-end.  Raises (never falls back) when the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError("sdpl_slam_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(sdpl_slam_b200/csrc/build.sh).  There is no CPU fallback." % p)
+    L = C.CDLL(p)
+    vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    ip = C.POINTER(C.c_int)
+    L.sdpl_strerror.restype = C.c_char_p; L.sdpl_strerror.argtypes = [i]
+    L.sdpl_last_error.restype = C.c_char_p
+    L.sdpl_device_count.restype = i
+    # ORB
+    L.sdpl_orb_create.argtypes = [C.POINTER(vp), i, f, i, i, i, i]
+    L.sdpl_orb_destroy.argtypes = [vp]; L.sdpl_orb_destroy.restype = None
+    L.sdpl_orb_levels.argtypes = [vp]
+    L.sdpl_orb_tables.argtypes = [vp, vp, vp, vp, vp]
+    L.sdpl_orb_quota.argtypes = [vp, vp, vp]
+    L.sdpl_orb_max_keypoints.argtypes = [vp]
+    L.sdpl_orb_extract.argtypes = [vp, vp, i, i, i, vp, vp, i, ip]
+    L.sdpl_orb_extract_batch.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp]
+    L.sdpl_orb_extract_batch_dev.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp, i]
+    L.sdpl_orb_pyramid_level.argtypes = [vp, i, i, vp, i, ip, ip]
+    L.sdpl_orb_blurred_level.argtypes = [vp, i, i, vp, i]
+    L.sdpl_orb_candidates.argtypes = [vp, i, i, vp, vp, vp, i, ip]
+    L.sdpl_orb_level_counts.argtypes = [vp, i, vp]
+    L.sdpl_orb_last_launches.argtypes = [vp]
+    L.sdpl_orb_set_stream.argtypes = [vp, vp]
+    # lines
+    L.sdpl_line_create.argtypes = [C.POINTER(vp), i, i, f, i, f, i, i]
+    L.sdpl_line_destroy.argtypes = [vp]; L.sdpl_line_destroy.restype = None
+    L.sdpl_line_levels.argtypes = [vp]
+    L.sdpl_line_tables.argtypes = [vp, vp, vp, vp, vp]
+    L.sdpl_line_extract.argtypes = [vp, vp, i, i, i, vp, vp, i, ip]
+    L.sdpl_line_extract_batch.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp]
+    L.sdpl_line_extract_batch_dev.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, i, vp, i]
+    L.sdpl_line_lbd_compute.argtypes = [vp, vp, i, i, i, vp, i, vp]
+    L.sdpl_line_lsd_segments.argtypes = [vp, i, i, vp, i, ip]
+    L.sdpl_line_last_launches.argtypes = [vp]
+    L.sdpl_line_set_stream.argtypes = [vp, vp]
+    # matcher
+    L.sdpl_matcher_create.argtypes = [C.POINTER(vp), i]
+    L.sdpl_matcher_destroy.argtypes = [vp]; L.sdpl_matcher_destroy.restype = None
+    L.sdpl_match_knn2.argtypes = [vp, vp, i, vp, i, vp, vp]
+    L.sdpl_match_ratio.argtypes = [vp, vp, i, vp, i, f, i, vp, ip]
+    L.sdpl_match_radius.argtypes = [vp, vp, i, vp, i, i, i, vp, vp]
+    L.sdpl_match_knn2_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i, i, i, vp, vp, i]
+    L.sdpl_matcher_last_launches.argtypes = [vp]
+    L.sdpl_matcher_set_stream.argtypes = [vp, vp]
+    if path is None:
+        _lib = L
+    return L
+
+
+def _strerror(code):
+    try:
+        return load_library().sdpl_strerror(code).decode()
+    except Exception:  # pragma: no cover
+        return "?"
+
+
+def _check(rc):
+    if rc != SDPL_OK:
+        raise SdplError(rc, load_library().sdpl_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _gray(image):
+    img = np.asarray(image)
+    if img.dtype != np.uint8 or img.ndim != 2:
+        # the reference asserts CV_8UC1 (src/ORBextractor.cc:1042)
+        raise TypeError("image must be a 2-D uint8 (CV_8UC1) array")
+    if img.strides[1] != 1:
+        img = np.ascontiguousarray(img)
+    return img
+
+
+class ORBextractor:
+    """SDPL_SLAM::ORBextractor.  `extractor(image, mask) -> (keypoints, descriptors)`; keypoints is a structured
+    array with cv::KeyPoint's fields, descriptors an (N, 32) uint8 array."""
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        _check(self._L.sdpl_orb_create(C.byref(self._h), int(nfeatures), float(scaleFactor), int(nlevels), int(iniThFAST),
+                                       int(minThFAST), int(device)))
+        self.nfeatures, self.nlevels, self.device = int(nfeatures), int(nlevels), int(device)
+        self._scale = float(np.float32(scaleFactor))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.sdpl_orb_destroy(h)
+            self._h = None
+
+    # --- getters, include/ORBextractor.h:49-69 ---
+    def GetLevels(self):
+        return self._L.sdpl_orb_levels(self._h)
+
+    def GetScaleFactor(self):
+        return self._scale
+
+    def _tables(self):
+        n = self.nlevels
+        a = [np.empty(n, np.float32) for _ in range(4)]
+        _check(self._L.sdpl_orb_tables(self._h, *[_p(x) for x in a]))
+        return a
+
+    def GetScaleFactors(self):
+        return self._tables()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3]
+
+    def features_per_level(self):
+        q = np.empty(self.nlevels, np.int32); u = np.empty(16, np.int32)
+        _check(self._L.sdpl_orb_quota(self._h, _p(q), _p(u)))
+        return q, u
+
+    def max_keypoints(self):
+        return self._L.sdpl_orb_max_keypoints(self._h)
+
+    # --- operator() ---
+    def __call__(self, image, mask=None):
+        if image is None or np.asarray(image).size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)   # silent return, src/ORBextractor.cc:1038
+        img = _gray(image)
+        cap = self.max_keypoints()
+        kps = np.empty(cap, KP_DTYPE); desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int(0)
+        _check(self._L.sdpl_orb_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap,
+                                        C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images):
+        """images: (B, H, W) uint8 host array -> list of (keypoints, descriptors)."""
+        imgs = np.ascontiguousarray(images, dtype=np.uint8)
+        assert imgs.ndim == 3
+        B, H, W = imgs.shape
+        cap = self.max_keypoints()
+        kps = np.empty((B, cap), KP_DTYPE); desc = np.empty((B, cap, 32), np.uint8); n = np.zeros(B, np.int32)
+        _check(self._L.sdpl_orb_extract_batch(self._h, _p(imgs), B, W, H, W, W * H, _p(kps), _p(desc), cap, _p(n)))
+        return [(kps[f, :n[f]].copy(), desc[f, :n[f]].copy()) for f in range(B)]
+
+    def extract_batch_dev(self, d_imgs, nframes, w, h, d_kps, d_desc, capacity, d_n, stride=None, frame_stride=None, sync=False):
+        """Device-pointer throughput path (ints are raw device addresses, e.g. torch tensor.data_ptr())."""
+        stride = w if stride is None else stride
+        frame_stride = stride * h if frame_stride is None else frame_stride
+        _check(self._L.sdpl_orb_extract_batch_dev(self._h, C.c_void_p(d_imgs), nframes, w, h, stride, frame_stride,
+                                                  C.c_void_p(d_kps), C.c_void_p(d_desc), capacity, C.c_void_p(d_n), int(sync)))
+
+    def set_stream(self, cuda_stream):
+        _check(self._L.sdpl_orb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # --- mvImagePyramid and stage introspection (parity tests) ---
+    def pyramid_level(self, level, frame=0):
+        w = C.c_int(); h = C.c_int()
+        _check(self._L.sdpl_orb_pyramid_level(self._h, frame, level, None, 0, C.byref(w), C.byref(h)))
+        out = np.empty((h.value + 38, w.value + 38), np.uint8)
+        _check(self._L.sdpl_orb_pyramid_level(self._h, frame, level, _p(out), out.strides[0], C.byref(w), C.byref(h)))
+        return out
+
+    def blurred_level(self, level, frame=0):
+        w = C.c_int(); h = C.c_int()
+        _check(self._L.sdpl_orb_pyramid_level(self._h, frame, level, None, 0, C.byref(w), C.byref(h)))
+        out = np.empty((h.value, w.value), np.uint8)
+        _check(self._L.sdpl_orb_blurred_level(self._h, frame, level, _p(out), out.strides[0]))
+        return out
+
+    def candidates(self, level, frame=0):
+        n = C.c_int()
+        _check(self._L.sdpl_orb_candidates(self._h, frame, level, None, None, None, 0, C.byref(n)))
+        xs = np.empty(n.value, np.int32); ys = np.empty(n.value, np.int32); rs = np.empty(n.value, np.int32)
+        if n.value:
+            _check(self._L.sdpl_orb_candidates(self._h, frame, level, _p(xs), _p(ys), _p(rs), n.value, C.byref(n)))
+        return xs, ys, rs
+
+    def level_counts(self, frame=0):
+        c = np.empty(self.nlevels, np.int32)
+        _check(self._L.sdpl_orb_level_counts(self._h, frame, _p(c)))
+        return c
+
+    def last_launches(self):
+        return self._L.sdpl_orb_last_launches(self._h)
+
+
+class Lineextractor:
+    """SDPL_SLAM::Lineextractor.  `extractor(image, mask) -> (keylines, descriptors_line)`."""
+
+    def __init__(self, lsd_nfeatures=0, lsd_refine=2, lsd_scale=0.8, nlevels=2, scale=2.0, extractor=0, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        _check(self._L.sdpl_line_create(C.byref(self._h), int(lsd_nfeatures), int(lsd_refine), float(lsd_scale), int(nlevels),
+                                        float(scale), int(extractor), int(device)))
+        self.nlevels_l = int(nlevels)
+        self.device = int(device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.sdpl_line_destroy(h)
+            self._h = None
+
+    def _tables(self):
+        a = [np.empty(self.nlevels_l, np.float32) for _ in range(4)]
+        _check(self._L.sdpl_line_tables(self._h, *[_p(x) for x in a]))
+        return a
+
+    # public members of the reference class (include/Lineextractor.h:66-75), as fixed tables
+    @property
+    def mvScaleFactor_l(self):
+        return self._tables()[0]
+
+    @property
+    def mvInvScaleFactor_l(self):
+        return self._tables()[1]
+
+    @property
+    def mvLevelSigma2_l(self):
+        return self._tables()[2]
+
+    @property
+    def mvInvLevelSigma2_l(self):
+        return self._tables()[3]
+
+    def __call__(self, image, mask=None, capacity=16384):
+        img = _gray(image)
+        kls = np.empty(capacity, KL_DTYPE); desc = np.empty((capacity, 32), np.uint8)
+        n = C.c_int(0)
+        _check(self._L.sdpl_line_extract(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kls), _p(desc),
+                                         capacity, C.byref(n)))
+        return kls[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, capacity=16384):
+        imgs = np.ascontiguousarray(images, dtype=np.uint8)
+        B, H, W = imgs.shape
+        kls = np.empty((B, capacity), KL_DTYPE); desc = np.empty((B, capacity, 32), np.uint8); n = np.zeros(B, np.int32)
+        _check(self._L.sdpl_line_extract_batch(self._h, _p(imgs), B, W, H, W, W * H, _p(kls), _p(desc), capacity, _p(n)))
+        return [(kls[f, :n[f]].copy(), desc[f, :n[f]].copy()) for f in range(B)]
+
+    def extract_batch_dev(self, d_imgs, nframes, w, h, d_kls, d_desc, capacity, d_n, stride=None, frame_stride=None, sync=False):
+        stride = w if stride is None else stride
+        frame_stride = stride * h if frame_stride is None else frame_stride
+        _check(self._L.sdpl_line_extract_batch_dev(self._h, C.c_void_p(d_imgs), nframes, w, h, stride, frame_stride,
+                                                   C.c_void_p(d_kls), C.c_void_p(d_desc), capacity, C.c_void_p(d_n), int(sync)))
+
+    def compute(self, image, keylines):
+        """BinaryDescriptor::compute on caller-provided keylines."""
+        img = _gray(image)
+        kls = np.ascontiguousarray(keylines, dtype=KL_DTYPE)
+        desc = np.empty((kls.shape[0], 32), np.uint8)
+        _check(self._L.sdpl_line_lbd_compute(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kls), kls.shape[0],
+                                             _p(desc)))
+        return desc
+
+    def lsd_segments(self, octave, frame=0, capacity=65536):
+        out = np.empty((capacity, 4), np.float32); n = C.c_int()
+        _check(self._L.sdpl_line_lsd_segments(self._h, frame, octave, _p(out), capacity, C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_stream(self, cuda_stream):
+        _check(self._L.sdpl_line_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def last_launches(self):
+        return self._L.sdpl_line_last_launches(self._h)
+
+
+class BinaryDescriptorMatcher:
+    """Brute-force 256-bit Hamming matcher with the surface of cv::line_descriptor::BinaryDescriptorMatcher
+    (match / knnMatch / radiusMatch).  Results are structured arrays with cv::DMatch's fields."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        _check(self._L.sdpl_matcher_create(C.byref(self._h), int(device)))
+        self.device = int(device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.sdpl_matcher_destroy(h)
+            self._h = None
+
+    @staticmethod
+    def _desc(d):
+        d = np.ascontiguousarray(d, dtype=np.uint8)
+        if d.ndim != 2 or d.shape[1] != 32:
+            raise TypeError("descriptors must be (N, 32) uint8")
+        return d
+
+    def knnMatch(self, queryDescriptors, trainDescriptors, k=2):
+        if k != 2:
+            raise ValueError("only k=2 is implemented (best / second best)")
+        q, t = self._desc(queryDescriptors), self._desc(trainDescriptors)
+        best = np.zeros(q.shape[0], DM_DTYPE); second = np.zeros(q.shape[0], DM_DTYPE)
+        _check(self._L.sdpl_match_knn2(self._h, _p(q), q.shape[0], _p(t), t.shape[0], _p(best), _p(second)))
+        return best, second
+
+    def match(self, queryDescriptors, trainDescriptors):
+        return self.knnMatch(queryDescriptors, trainDescriptors, 2)[0]
+
+    def ratioMatch(self, queryDescriptors, trainDescriptors, ratio=0.8, max_dist=100):
+        q, t = self._desc(queryDescriptors), self._desc(trainDescriptors)
+        out = np.zeros(q.shape[0], DM_DTYPE); n = C.c_int(0)
+        _check(self._L.sdpl_match_ratio(self._h, _p(q), q.shape[0], _p(t), t.shape[0], float(ratio), int(max_dist), _p(out),
+                                        C.byref(n)))
+        return out, n.value
+
+    def radiusMatch(self, queryDescriptors, trainDescriptors, maxDistance, k=8):
+        q, t = self._desc(queryDescriptors), self._desc(trainDescriptors)
+        counts = np.zeros(q.shape[0], np.int32); out = np.zeros((q.shape[0], k), DM_DTYPE)
+        _check(self._L.sdpl_match_radius(self._h, _p(q), q.shape[0], _p(t), t.shape[0], int(maxDistance), int(k), _p(counts),
+                                         _p(out)))
+        return counts, out
+
+    def knn2_batch_dev(self, d_q, d_nq, q_stride, d_t, d_nt, t_stride, npairs, max_q, max_t, d_best, d_second, sync=False):
+        _check(self._L.sdpl_match_knn2_batch_dev(self._h, C.c_void_p(d_q), C.c_void_p(d_nq), q_stride, C.c_void_p(d_t),
+                                                 C.c_void_p(d_nt), t_stride, npairs, max_q, max_t, C.c_void_p(d_best),
+                                                 C.c_void_p(d_second), int(sync)))
+
+    def set_stream(self, cuda_stream):
+        _check(self._L.sdpl_matcher_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def last_launches(self):
+        return self._L.sdpl_matcher_last_launches(self._h)
+
+
+def device_count():
+    return load_library().sdpl_device_count()
