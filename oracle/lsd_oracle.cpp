@@ -9,8 +9,11 @@
 //  (vi) seed order: descending gradient bin; tie_mode 0 = row-major (stable) inside a bin -- what the GPU path
 //       implements; tie_mode 1 = the order libstdc++'s std::sort leaves (what an OpenCV binary built with libstdc++
 //       produces), kept only to quantify the difference against cv2.
-//  trig in region growing: cos/sin evaluated in double on the float-rounded angle, accumulated in float
-//       (set by orc_lsd_set_trig_mode for experiments).
+//  trig in region growing: OpenCV calls sincosf; the oracle evaluates cos/sin in double on the float-rounded angle,
+//       rounds to float and accumulates in float (identical except where glibc's sincosf is not correctly rounded).
+//  rect_nfa: follows the OpenCV 4.x implementation (double vertices, ceil/int column limits), recovered from the
+//       cv2 4.13 binary and verified bit-exact against it; the OpenCV 3.4-era integer-division scan is kept behind
+//       orc_lsd_set_nfa_variant(4) only to document the difference (the reference README pins "OpenCV 3.4").
 #include "oracle_internal.h"
 #include <cmath>
 #include <cfloat>
@@ -28,6 +31,9 @@ const double k2PI = 2 * kPI;
 const double kLn10 = 2.30258509299404568402;
 
 int g_trig_mode = 0;
+int g_nfa_variant = 16 + 4;  // bit 16: OpenCV 4.x rect scan (else the 3.4-era integer scan); bit 4: log_gamma(n+1)
+std::vector<double> g_dbg;  // per output line: width, p, log_nfa, n, k
+int g_last_n = 0, g_last_k = 0;
 std::vector<uint8_t> g_last_scaled;
 int g_last_w = 0, g_last_h = 0;
 
@@ -243,7 +249,7 @@ struct Lsd {
     if (n == 0 || k == 0) return -log_nt;
     if (n == k) return -log_nt - double(n) * std::log10(p);
     double p_term = p / (1 - p);
-    double log1term = log_gamma(double(n) + 1) - log_gamma(double(k) + 1) - log_gamma(double(n - k) + 1) + double(k) * std::log(p) +
+    double log1term = ((g_nfa_variant & 4) ? log_gamma(double(n) + 1) : (double(n) + 1)) - log_gamma(double(k) + 1) - log_gamma(double(n - k) + 1) + double(k) * std::log(p) +
                       double(n - k) * std::log(1.0 - p);
     double term = std::exp(log1term);
     if (double_equal(term, 0)) {
@@ -264,8 +270,36 @@ struct Lsd {
     return -std::log10(bin_tail) - log_nt;
   }
 
+  static double dyhw0(const Rect& r) { return r.dy * (r.width / 2.0); }
+  static double dxhw0(const Rect& r) { return r.dx * (r.width / 2.0); }
   double rect_nfa(const Rect& rec) const {
     int total_pts = 0, alg_pts = 0;
+    if (g_nfa_variant & 16) {  // default
+      // OpenCV >= 4.5.x rect_nfa: double vertices rotated to start at the min-y (then min-x) vertex, counter-clockwise;
+      // rows ceil(top) .. ceil(bottom); columns ceil(left limit) .. int(right limit).
+      double vx[4] = {rec.x1 - dyhw0(rec), rec.x2 - dyhw0(rec), rec.x2 + dyhw0(rec), rec.x1 + dyhw0(rec)};
+      double vy[4] = {rec.y1 + dxhw0(rec), rec.y2 + dxhw0(rec), rec.y2 - dxhw0(rec), rec.y1 - dxhw0(rec)};
+      int off = 0;
+      for (int i = 1; i < 4; ++i)
+        if (vy[i] < vy[off] || (vy[i] == vy[off] && vx[i] < vx[off])) off = i;
+      double px[4], py[4];
+      for (int i = 0; i < 4; ++i) { px[i] = vx[(i + off) % 4]; py[i] = vy[(i + off) % 4]; }
+      auto slope = [&](int a, int b) { return ((int)std::ceil(py[b]) != (int)std::ceil(py[a])) ? (px[b] - px[a]) / (py[b] - py[a]) : 0.0; };
+      const double flstep = slope(0, 1), slstep = slope(1, 2), frstep = slope(0, 3), srstep = slope(3, 2);
+      const int y_end = (int)std::ceil(py[2]), c1 = (int)std::ceil(py[1]), c3 = (int)std::ceil(py[3]);
+      for (int y = (int)std::ceil(py[0]); y <= y_end; ++y) {
+        if (y < 0 || y >= h) continue;
+        double left = (y <= c1) ? px[0] + (y - py[0]) * flstep : px[1] + (y - py[1]) * slstep;
+        double right = (y < c3) ? px[0] + (y - py[0]) * frstep : px[3] + (y - py[3]) * srstep;
+        for (int x = (int)std::ceil(left); x <= (int)right; ++x) {
+          if (x < 0 || x >= w) continue;
+          ++total_pts;
+          if (aligned(x, y, rec.theta, rec.prec)) ++alg_pts;
+        }
+      }
+      g_last_n = total_pts; g_last_k = alg_pts;
+      return nfa(total_pts, alg_pts, rec.p);
+    }
     double half_width = rec.width / 2.0;
     double dyhw = rec.dy * half_width, dxhw = rec.dx * half_width;
     struct Edge { int x, y; bool taken; } e[4];
@@ -293,10 +327,16 @@ struct Lsd {
       if (!e[i].taken) { if (!tailp) tailp = &e[i]; else if (tailp->x > e[i].x) tailp = &e[i]; }
     tailp->taken = true;
     // integer divisions and the p.x/p.y mix-up below are those of the OpenCV source
-    double flstep = (min_y->y != leftmost->y) ? (min_y->x - leftmost->x) / (min_y->y - leftmost->y) : 0;
-    double slstep = (leftmost->y != tailp->x) ? (leftmost->x - tailp->x) / (leftmost->y - tailp->x) : 0;
-    double frstep = (min_y->y != rightmost->y) ? (min_y->x - rightmost->x) / (min_y->y - rightmost->y) : 0;
-    double srstep = (rightmost->y != tailp->x) ? (rightmost->x - tailp->x) / (rightmost->y - tailp->x) : 0;
+    double flstep, slstep, frstep, srstep;
+    {
+      const bool dd = g_nfa_variant & 1;   // double division instead of integer division
+      const int ty = (g_nfa_variant & 2) ? tailp->y : tailp->x;
+      auto dv = [&](int a, int b) { return dd ? (double)a / (double)b : (double)(a / b); };
+      flstep = (min_y->y != leftmost->y) ? dv(min_y->x - leftmost->x, min_y->y - leftmost->y) : 0;
+      slstep = (leftmost->y != ty) ? dv(leftmost->x - tailp->x, leftmost->y - ty) : 0;
+      frstep = (min_y->y != rightmost->y) ? dv(min_y->x - rightmost->x, min_y->y - rightmost->y) : 0;
+      srstep = (rightmost->y != ty) ? dv(rightmost->x - tailp->x, rightmost->y - ty) : 0;
+    }
     double lstep = flstep, rstep = frstep;
     double left_x = min_y->x, right_x = min_y->x;
     int min_iter = min_y->y, max_iter = max_y->y;
@@ -312,6 +352,7 @@ struct Lsd {
       left_x += lstep;
       right_x += rstep;
     }
+    g_last_n = total_pts; g_last_k = alg_pts;
     return nfa(total_pts, alg_pts, rec.p);
   }
 
@@ -372,13 +413,14 @@ struct Lsd {
 int lsd_detect(const uint8_t* src, int sw, int sh, int sstride, int refine_mode, double scale, double sigma_scale, double quant,
                double ang_th, double log_eps, double density_th, int n_bins, int tie_mode, std::vector<float>& lines) {
   lines.clear();
+  g_dbg.clear();
   Lsd L;
   const double prec = kPI * ang_th / 180, p = ang_th / 180;
   const double rho = quant / std::sin(prec);
   if (scale != 1) {
     const double sigma = (scale < 1) ? (sigma_scale / scale) : sigma_scale;
     const unsigned int hk = (unsigned int)std::ceil(sigma * std::sqrt(2 * 3.0 * std::log(10.0)));
-    if (!(hk == 3 && std::fabs(sigma - 0.75) < 1e-9)) return -1;  // only the reference's 0.6/0.8 kernel is restated
+    if (!(hk == 3 && std::fabs(sigma - 0.75) < 1e-6)) return -1;  // only the reference's 0.6/0.8 kernel is restated
     std::vector<uint8_t> blurred((size_t)sw * sh);
     gaussian_blur_u8(src, sw, sh, sstride, blurred.data(), sw, 2);
     L.w = cv_round(sw * scale); L.h = cv_round(sh * scale);
@@ -411,8 +453,10 @@ int lsd_detect(const uint8_t* src, int sw, int sh, int sstride, int refine_mode,
           if (log_nfa <= log_eps) continue;
         }
       }
+      Rect rec0 = rec;
       rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
       if (scale != 1) { rec.x1 /= scale; rec.y1 /= scale; rec.x2 /= scale; rec.y2 /= scale; rec.width /= scale; }
+      { double v = L.rect_nfa(rec0); g_dbg.push_back(rec.width); g_dbg.push_back(rec.p); g_dbg.push_back(log_nfa); g_dbg.push_back(g_last_n); g_dbg.push_back(g_last_k); g_dbg.push_back(rec0.x1); g_dbg.push_back(rec0.y1); g_dbg.push_back(rec0.x2); g_dbg.push_back(rec0.y2); g_dbg.push_back(rec0.width); g_dbg.push_back(rec0.dx); g_dbg.push_back(rec0.dy); g_dbg.push_back(rec0.theta); (void)v; }
       lines.push_back(float(rec.x1)); lines.push_back(float(rec.y1)); lines.push_back(float(rec.x2)); lines.push_back(float(rec.y2));
     }
   }
@@ -423,6 +467,8 @@ int lsd_detect(const uint8_t* src, int sw, int sh, int sstride, int refine_mode,
 
 extern "C" {
 void orc_lsd_set_trig_mode(int m) { orc::g_trig_mode = m; }
+void orc_lsd_set_nfa_variant(int m) { orc::g_nfa_variant = m; }
+int orc_lsd_debug(double* out, int cap) { int n = (int)orc::g_dbg.size(); for (int i = 0; i < n && i < cap; i++) out[i] = orc::g_dbg[i]; return n; }
 int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int refine, double scale, double sigma_scale, double quant,
                    double ang_th, double log_eps, double density_th, int n_bins, int tie_mode, float* lines, int cap) {
   std::vector<float> v;

@@ -68,9 +68,11 @@ def lib(path=None):
         L.orc_line_destroy.argtypes = [C.c_void_p]
         L.orc_line_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_line_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+    if hasattr(L, "orc_lsd_detect"):
         L.orc_lsd_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.orc_lsd_last_scaled.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
+    if hasattr(L, "orc_lbd_compute"):
         L.orc_lbd_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     if path is None:
         _lib = L
