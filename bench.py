@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- front-end frames/sec (ORB + LSD/LBD + Hamming match) at 1242x375 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+One "step" = one pass of the front-end over a batch of F frames per GPU (frames come as (frame, partner) pairs;
+every frame's ORB and LBD descriptors are matched against its pair partner's).  `value` is timed with the frames
+already resident in HBM; `e2e` goes through the host-buffer C ABI (H2D and D2H copies inside the timed region).
+Prints ONE JSON line on rank 0.  The oracle under oracle/ is used here only for the cpu_baseline / --impl reference
+legs (it is the CPU restatement of the reference; the reference itself needs OpenCV 3.4 C++ and cannot be built here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 375, 1242
+ORB_CFG = dict(nfeatures=2000, scale=1.2, nlevels=8, ini=20, mn=7)
+LINE_CFG = dict(nfeatures=0, refine=2, lsd_scale=0.8, nlevels=2, scale=2.0, extractor=0)
+RATIO, MAX_DIST = 0.8, 64
+LINE_CAP = 2048
+METRIC = "front-end frames/sec (ORB+LSD/LBD+match) at 1242x375"
+UNIT = "frames/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _level_sizes(w, h, scale, nlevels):
+    sf = np.float32(1.0); out = []
+    for l in range(nlevels):
+        if l:
+            sf = np.float32(sf * np.float32(scale))
+        inv = np.float32(1.0) / sf
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
+    return out
+
+
+def algorithmic_bytes(w=W, h=H):
+    """Minimal per-frame traffic of each stage: compulsory reads + writes only."""
+    lv = _level_sizes(w, h, ORB_CFG["scale"], ORB_CFG["nlevels"])
+    px = [a * b for a, b in lv]
+    padded = [(a + 38) * (b + 38) for a, b in lv]
+    nk = ORB_CFG["nfeatures"]
+    b = {}
+    b["pyramid"] = w * h + sum(px[:-1]) + sum(padded)
+    b["fast_score"] = sum(padded) + sum(px)
+    b["cell_nms"] = 2 * sum(px) + 5 * 15000
+    b["quadtree"] = 15000 * 7 + nk * 5
+    b["blur7"] = 2 * sum(px)
+    b["orient_describe"] = nk * (749 + 512 + 5) + nk * (28 + 32)
+    b["match_partial"] = 2 * nk * 32 + nk * 16
+    b["match_merge"] = nk * 16 + nk * 32
+    # lines: level 0 = w x h, level 1 = round(w/2) x round(h/2); LSD works on the 0.8x blurred level
+    l1 = (int(np.rint(w / 2)), int(np.rint(h / 2)))
+    lsd_px = sum(int(np.rint(a * 0.8)) * int(np.rint(c * 0.8)) for a, c in [(w, h), l1])
+    src_px = w * h + l1[0] * l1[1]
+    b["lsd_pyramid"] = w * h + l1[0] * l1[1]
+    b["lsd_scale"] = src_px + lsd_px
+    b["lsd_gradient"] = lsd_px + lsd_px * (8 + 8 + 4)            # angle f64, cos/sin f32x2, grad u32
+    b["lsd_sort"] = lsd_px * (2 + 4) * 2
+    b["lsd_grow"] = lsd_px * (8 + 8 + 4 + 1 + 4)                  # every pixel's angle/trig/grad/used touched once + region list
+    b["lsd_nfa"] = lsd_px * 8
+    lbd_px = w * h + (w // 2) * (h // 2)
+    b["lbd_sobel"] = w * h * 2 + lbd_px * (1 + 4)
+    b["lbd_bands"] = 600 * (63 * 40 * 4 + 32)
+    b["keylines"] = 600 * (16 + 68)
+    return b
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index; self.lines = []; self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm on host cores
+# ------------------------------------------------------------------------------------------------------------------
+def _cpu_pair(args):
+    """One (frame, partner) pair through the oracle: ORB, lines, and descriptor matching both ways."""
+    seed, stages = args
+    from oracle import oracle as orc
+    from sdpl_slam_b200 import synth
+    a, b = synth.frame(seed, H, W), synth.partner(seed, H, W)
+    t0 = time.perf_counter()
+    res = []
+    orb = orc.OrbOracle(ORB_CFG["nfeatures"], ORB_CFG["scale"], ORB_CFG["nlevels"], ORB_CFG["ini"], ORB_CFG["mn"])
+    for img in (a, b):
+        k, d = orb(img)
+        r = [k, d, None, None]
+        if "line" in stages:
+            ln = orc.LineOracle(LINE_CFG["nfeatures"], LINE_CFG["refine"], LINE_CFG["lsd_scale"], LINE_CFG["nlevels"],
+                                LINE_CFG["scale"], LINE_CFG["extractor"])
+            r[2], r[3] = ln(img)
+        res.append(r)
+    if "match" in stages:
+        for q, t in ((0, 1), (1, 0)):
+            orc.match_ratio(res[q][1], res[t][1], RATIO, MAX_DIST)
+            if "line" in stages and len(res[q][3]) and len(res[t][3]):
+                orc.match_ratio(res[q][3], res[t][3], RATIO, MAX_DIST)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(stages, n_pairs=12):
+    """Single host core, bounded sample (n_pairs pairs = 2*n_pairs frames)."""
+    _cpu_pair((10_000, stages))  # warm-up (page-in, oracle build)
+    t = sum(_cpu_pair((10_001 + i, stages)) for i in range(n_pairs))
+    return {"value": 2 * n_pairs / t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d frames (%d seeded pairs) of the same workload through oracle/liboracle.so, one thread; "
+                      "frame synthesis excluded" % (2 * n_pairs, n_pairs)}
+
+
+def run_reference(args, stages):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    pairs_per_step = max(cores, 2 * ((cores + 1) // 2))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_pair, [(20_000 + i, stages) for i in range(cores)])          # warm-up of every worker
+        for w in range(args.warmup):
+            pool.map(_cpu_pair, [(30_000 + w * pairs_per_step + i, stages) for i in range(pairs_per_step)], chunksize=1)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pool.map(_cpu_pair, [(40_000 + s * pairs_per_step + i, stages) for i in range(pairs_per_step)], chunksize=1)
+        dt = time.perf_counter() - t0
+    frames = 2 * pairs_per_step * args.steps
+    val = frames / dt
+    sample = ("each step = %d frames (%d pairs) of the workload, one pair per worker process, %d processes; wall clock "
+              "includes per-pair frame synthesis in the workers" % (2 * pairs_per_step, pairs_per_step, cores))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": _config(stages, 2 * pairs_per_step),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def _config(stages, frames_per_gpu):
+    return {"workload": "KITTI-size 1242x375 point+line front-end: ORB 2000 (8 levels, x1.2, FAST 20/7) + LSD/LBD lines "
+                        "(refine ADV, 0.8, 2 octaves) + frame-to-partner Hamming knn-2 ratio matching of ORB and LBD descriptors "
+                        "[BASELINE.json configs[1]]",
+            "stages": "+".join(stages), "frames_per_gpu_per_step": frames_per_gpu, "width": W, "height": H,
+            "l2": "per-step working set (pyramids, score/blur planes, gradient maps) exceeds the 126 MB L2 many times; "
+                  "inputs are re-read from HBM every step"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu(args, stages):
+    import torch
+    import torch.distributed as dist
+    from sdpl_slam_b200 import frontend as fe, synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (the front-end has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    F = args.frames - args.frames % 2
+    P = F // 2
+    use_line, use_match = "line" in stages, "match" in stages
+    # ---- synthetic frames: rank r owns pairs [r*P, (r+1)*P) (weak scaling: per-GPU work is fixed).
+    #      layout: frames [0,P) = frame(seed), frames [P,2P) = partner(seed); frame p is matched against frame P+p and back
+    host = np.empty((F, H, W), np.uint8)
+    for p in range(P):
+        seed = rank * P + p
+        host[p] = synth.frame(seed, H, W); host[P + p] = synth.partner(seed, H, W)
+    pinned = torch.from_numpy(host).pin_memory()
+    d_imgs = pinned.to(dev)
+
+    orb = fe.ORBextractor(ORB_CFG["nfeatures"], ORB_CFG["scale"], ORB_CFG["nlevels"], ORB_CFG["ini"], ORB_CFG["mn"], device=local)
+    mat = fe.BinaryDescriptorMatcher(device=local)
+    line = lmat = None
+    if use_line:
+        line = fe.Lineextractor(LINE_CFG["nfeatures"], LINE_CFG["refine"], LINE_CFG["lsd_scale"], LINE_CFG["nlevels"], LINE_CFG["scale"],
+                                LINE_CFG["extractor"], device=local)
+        lmat = fe.BinaryDescriptorMatcher(device=local)
+    cap = orb.max_keypoints()
+    u8, i32 = torch.uint8, torch.int32
+    d_kps = torch.empty((F, cap, 28), dtype=u8, device=dev); d_desc = torch.zeros((F, cap, 32), dtype=u8, device=dev)
+    d_nkp = torch.zeros(F, dtype=i32, device=dev)
+    d_best = torch.empty((F, cap, 16), dtype=u8, device=dev); d_second = torch.empty((F, cap, 16), dtype=u8, device=dev)
+    d_nacc = torch.zeros(F, dtype=i32, device=dev)
+    d_kls = d_ldesc = d_nkl = d_lbest = d_lsecond = d_lnacc = None
+    if use_line:
+        d_kls = torch.empty((F, LINE_CAP, 68), dtype=u8, device=dev); d_ldesc = torch.zeros((F, LINE_CAP, 32), dtype=u8, device=dev)
+        d_nkl = torch.zeros(F, dtype=i32, device=dev)
+        d_lbest = torch.empty((F, LINE_CAP, 16), dtype=u8, device=dev); d_lsecond = torch.empty((F, LINE_CAP, 16), dtype=u8, device=dev)
+        d_lnacc = torch.zeros(F, dtype=i32, device=dev)
+    stats = torch.zeros((F, 4), dtype=i32, device=dev)
+    gathered = torch.zeros((world * F, 4), dtype=i32, device=dev) if world > 1 else None
+
+    s_orb, s_line, s_match, s_lmatch = (torch.cuda.Stream(device=dev) for _ in range(4))
+    orb.set_stream(s_orb.cuda_stream); mat.set_stream(s_match.cuda_stream)
+    if use_line:
+        line.set_stream(s_line.cuda_stream); lmat.set_stream(s_lmatch.cuda_stream)
+    for hdl in (orb, mat, line, lmat):
+        if hdl is not None:
+            hdl.set_profiling(True)
+    launches = [0]
+
+    def match_pairs(m, d, n, rows, best, second, nacc):
+        """problem p: frame p vs frame P+p, then frame P+p vs frame p (two batched launches of P problems each)."""
+        fs = rows * 32
+        for q0 in (0, P):
+            t0 = P - q0
+            m.knn2_batch_dev(d.data_ptr() + q0 * fs, n.data_ptr() + 4 * q0, fs, d.data_ptr() + t0 * fs, n.data_ptr() + 4 * t0, fs, P, rows,
+                             rows, best.data_ptr() + q0 * rows * 16, second.data_ptr() + q0 * rows * 16, False)
+            launches[0] += m.last_launches()
+            m.ratio_batch_dev(best.data_ptr() + q0 * rows * 16, second.data_ptr() + q0 * rows * 16, n.data_ptr() + 4 * q0, P, rows, RATIO,
+                              MAX_DIST, 0, nacc.data_ptr() + 4 * q0, False)
+            launches[0] += m.last_launches()
+
+    def step_dev(imgs_ptr=None):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event(); ev.record(main)
+        s_orb.wait_event(ev)
+        orb.extract_batch_dev(imgs_ptr or d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_nkp.data_ptr())
+        launches[0] += orb.last_launches()
+        if use_line:
+            s_line.wait_event(ev)
+            line.extract_batch_dev(imgs_ptr or d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr(), LINE_CAP, d_nkl.data_ptr())
+            launches[0] += line.last_launches()
+        if use_match:
+            s_match.wait_stream(s_orb)
+            match_pairs(mat, d_desc, d_nkp, cap, d_best, d_second, d_nacc)
+            if use_line:
+                s_lmatch.wait_stream(s_line)
+                match_pairs(lmat, d_ldesc, d_nkl, LINE_CAP, d_lbest, d_lsecond, d_lnacc)
+        for s in (s_orb, s_line, s_match, s_lmatch):
+            main.wait_stream(s)
+        # per-frame statistics {n_kp, n_lines, n_point_matches, n_line_matches}; NCCL gathers them across ranks
+        stats[:, 0].copy_(d_nkp); stats[:, 2].copy_(d_nacc)
+        if use_line:
+            stats[:, 1].copy_(d_nkl); stats[:, 3].copy_(d_lnacc)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, stats)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    n_launch = launches[0]
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * F * args.steps / (ms_max / 1000.0)
+    st = stats.cpu().numpy()
+
+    # ---- per-stage kernel times, each pipeline alone on the device (no cross-stream overlap) ----
+    stage_ms, stage_launch = {}, {}
+    reps = 3
+    for hdl, fn in ((orb, lambda: orb.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_nkp.data_ptr())),
+                    (line, (lambda: line.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr(), LINE_CAP,
+                                                           d_nkl.data_ptr())) if use_line else None),
+                    (mat, (lambda: mat.knn2_batch_dev(d_desc.data_ptr(), d_nkp.data_ptr(), cap * 32, d_desc.data_ptr() + P * cap * 32,
+                                                      d_nkp.data_ptr() + 4 * P, cap * 32, P, cap, cap, d_best.data_ptr(),
+                                                      d_second.data_ptr(), False)) if use_match else None)):
+        if hdl is None or fn is None:
+            continue
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            fn()
+            for name, t_ms, nl in hdl.stage_times():
+                stage_ms[name] = stage_ms.get(name, 0.0) + t_ms / reps
+                stage_launch[name] = nl
+    torch.cuda.synchronize()
+    alg = algorithmic_bytes()
+    peak, peak_src = _peaks()
+    stage_rows = []
+    for name, t_ms in stage_ms.items():
+        frames_in_call = P if name.startswith("match") else F
+        nbytes = alg.get(name, 0) * frames_in_call
+        gbs = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        stage_rows.append({"stage": name, "ms": round(t_ms, 4), "launches": stage_launch.get(name, 0), "alg_bytes": int(nbytes),
+                           "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+    dom = max(stage_rows, key=lambda r: r["ms"]) if stage_rows else None
+    roofline = None
+    if dom:
+        nl = max(1, dom["launches"])
+        roofline = {"bound": "hbm", "kernel": dom["stage"], "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": None, "peak_source": peak_src, "launches_per_step": nl, "avg_launch_ms": dom["ms"] / nl,
+                    "alg_bytes_per_launch": dom["alg_bytes"] // nl,
+                    "note": "stage time by CUDA events on the handle's stream, pipeline run alone, mean of %d calls" % reps}
+
+    # ---- end to end through the host-buffer C ABI (`e2e`): pinned host frames in, results back on the host ----
+    e2e = None
+    if not args.no_e2e:
+        himgs = pinned.numpy()
+        h2d = d2h = 0
+
+        def step_e2e():
+            nonlocal h2d, d2h
+            res = orb.extract_batch(himgs)
+            h2d += himgs.nbytes; d2h += sum(k.nbytes + d.nbytes for k, d in res) + 4 * F
+            lres = None
+            if use_line:
+                lres = line.extract_batch(himgs, capacity=LINE_CAP)
+                h2d += himgs.nbytes; d2h += sum(k.nbytes + d.nbytes for k, d in lres) + 4 * F
+            nm = 0
+            if use_match:
+                for p in range(P):
+                    for q, t_ in ((p, P + p), (P + p, p)):
+                        out, n = mat.ratioMatch(res[q][1], res[t_][1], RATIO, MAX_DIST)
+                        nm += n; h2d += res[q][1].nbytes + res[t_][1].nbytes; d2h += out.nbytes + 4
+                        if use_line and len(lres[q][1]) and len(lres[t_][1]):
+                            out, n = lmat.ratioMatch(lres[q][1], lres[t_][1], RATIO, MAX_DIST)
+                            h2d += lres[q][1].nbytes + lres[t_][1].nbytes; d2h += out.nbytes + 4
+            return nm
+
+        for hdl in (orb, mat, line, lmat):
+            if hdl is not None:
+                hdl.set_stream(0); hdl.set_profiling(False)
+        e2e_steps = max(1, min(args.steps, 3))
+        step_e2e()
+        barrier()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * F * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d // e2e_steps),
+               "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps,
+               "api": "ORBextractor.extract_batch / Lineextractor.extract_batch / BinaryDescriptorMatcher.ratioMatch on host arrays "
+                      "(sdpl_orb_extract_batch, sdpl_line_extract_batch, sdpl_match_ratio)"}
+
+    if rank == 0:
+        cpu = None if args.no_cpu else cpu_baseline(stages)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+               "data": "synthetic (seeded noise-texture + rectangles frames, sdpl_slam_b200/synth.py; %d distinct frames per GPU)" % F,
+               "config": _config(stages, F), "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roofline,
+               "cpu_baseline": cpu, "stages": stage_rows,
+               "frame_stats_mean": {"keypoints": float(st[:, 0].mean()), "keylines": float(st[:, 1].mean()),
+                                    "point_matches": float(st[:, 2].mean()), "line_matches": float(st[:, 3].mean())}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step (even)")
+    ap.add_argument("--stages", default="orb,line,match")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    stages = [s for s in args.stages.split(",") if s]
+    if args.impl == "reference":
+        run_reference(args, stages)
+    else:
+        run_gpu(args, stages)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,7 +134,21 @@ int sdpl_match_radius(sdpl_matcher* h, const uint8_t* q, int nq, const uint8_t* 
 int sdpl_match_knn2_batch_dev(sdpl_matcher* h, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t,
                               const int* d_nt, size_t t_stride, int npairs, int max_q, int max_t, sdpl_dmatch* d_best,
                               sdpl_dmatch* d_second, int sync);
+/* Batched DEVICE ratio test on knn2 results: d_n_acc[p] = accepted count of problem p; d_out (may be NULL) receives the
+ * filtered best matches (train = -1 where rejected), laid out like d_best. */
+int sdpl_match_ratio_batch_dev(sdpl_matcher* h, const sdpl_dmatch* d_best, const sdpl_dmatch* d_second, const int* d_nq, int npairs,
+                               int max_q, float ratio, int max_dist, sdpl_dmatch* d_out, int* d_n_acc, int sync);
 int sdpl_matcher_last_launches(const sdpl_matcher* h);
+
+/* Per-stage device timing (CUDA events on the handle's stream).  set_profiling(1) makes every following call record
+ * one event per stage; stage_times returns the stages of the LAST call: ms[i], names[i] (static strings), launches[i]
+ * = kernels launched in stage i; return value = number of stages written (<= cap).  Synchronises on the last event. */
+int sdpl_orb_set_profiling(sdpl_orb* h, int on);
+int sdpl_orb_stage_times(sdpl_orb* h, float* ms, const char** names, int* launches, int cap);
+int sdpl_line_set_profiling(sdpl_line* h, int on);
+int sdpl_line_stage_times(sdpl_line* h, float* ms, const char** names, int* launches, int cap);
+int sdpl_matcher_set_profiling(sdpl_matcher* h, int on);
+int sdpl_matcher_stage_times(sdpl_matcher* h, float* ms, const char** names, int* launches, int cap);
 
 /* Bind a handle's work to a caller stream (cudaStream_t as void*; NULL = the handle's own stream). */
 int sdpl_orb_set_stream(sdpl_orb* h, void* cuda_stream);

@@ -291,8 +291,11 @@ struct Lsd {
         if (y < 0 || y >= h) continue;
         double left = (y <= c1) ? px[0] + (y - py[0]) * flstep : px[1] + (y - py[1]) * slstep;
         double right = (y < c3) ? px[0] + (y - py[0]) * frstep : px[3] + (y - py[3]) * srstep;
-        for (int x = (int)std::ceil(left); x <= (int)right; ++x) {
-          if (x < 0 || x >= w) continue;
+        // same pixel set as `for (x = ceil(left); x <= int(right); ++x) if (0 <= x < w)`, without walking the
+        // out-of-image part of the span (near-horizontal edges give spans of 1e5+ columns)
+        if (!(right >= 0) || !(left <= (double)(w - 1))) continue;
+        const int xb = (int)std::ceil(left > 0 ? left : 0.0), xe = (int)(right < (double)(w - 1) ? right : (double)(w - 1));
+        for (int x = xb; x <= xe; ++x) {
           ++total_pts;
           if (aligned(x, y, rec.theta, rec.prec)) ++alg_pts;
         }

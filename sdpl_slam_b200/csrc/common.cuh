@@ -50,6 +50,43 @@ struct DevBuf {
   template <class T> T* as() const { return (T*)p; }
 };
 
+// Per-stage device timing with CUDA events recorded on the handle's stream (bench.py's live roofline numbers).
+// mark(name) closes the stage `name` that started at the previous mark; the first mark of a call is "begin".
+struct StageTimer {
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+  std::vector<int> launches;      // kernels launched in the stage
+  int n = 0;
+  bool enabled = false;
+  void begin(cudaStream_t st) { n = 0; mark(st, "begin"); }
+  void mark(cudaStream_t st, const char* name) {
+    if (!enabled) return;
+    if (n == (int)ev.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { enabled = false; return; }
+      ev.push_back(e); names.push_back(name); launches.push_back(0);
+    }
+    names[n] = name; launches[n] = g_launches;
+    cudaEventRecord(ev[n], st);
+    n++;
+  }
+  // stage i (0-based) = interval between mark i and mark i+1; returns the number of stages of the last call
+  int read(float* ms, const char** nm, int* nlaunch, int cap) {
+    if (!enabled || n < 2) return 0;
+    cudaEventSynchronize(ev[n - 1]);
+    int k = 0;
+    for (int i = 0; i + 1 < n && k < cap; i++, k++) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      if (ms) ms[k] = t;
+      if (nm) nm[k] = names[i + 1];
+      if (nlaunch) nlaunch[k] = launches[i + 1] - launches[i];
+    }
+    return k;
+  }
+  void release() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); names.clear(); launches.clear(); n = 0; }
+};
+
 // ---- host helpers (OpenCV rounding conventions) ----
 static inline int h_cv_round(float v) { return (int)lrintf(v); }
 static inline int h_cv_round(double v) { return (int)lrint(v); }

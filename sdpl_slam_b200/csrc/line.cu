@@ -13,4 +13,6 @@ int sdpl_line_lbd_compute(sdpl_line*, const uint8_t*, int, int, int, const sdpl_
 int sdpl_line_lsd_segments(sdpl_line*, int, int, float*, int, int*) { return SDPL_ERR_UNSUPPORTED; }
 int sdpl_line_last_launches(const sdpl_line*) { return 0; }
 int sdpl_line_set_stream(sdpl_line*, void*) { return SDPL_ERR_UNSUPPORTED; }
+int sdpl_line_set_profiling(sdpl_line*, int) { return SDPL_ERR_UNSUPPORTED; }
+int sdpl_line_stage_times(sdpl_line*, float*, const char**, int*, int) { return 0; }
 }

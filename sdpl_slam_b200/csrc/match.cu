@@ -114,6 +114,23 @@ __global__ void __launch_bounds__(256) k_match_ratio(const sdpl_dmatch* __restri
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_acc, __popc(m));
 }
 
+// batched ratio + max-distance filter: problem p = blockIdx.y; out may be NULL (count only)
+__global__ void __launch_bounds__(256) k_match_ratio_batch(const sdpl_dmatch* __restrict__ best, const sdpl_dmatch* __restrict__ second,
+                                                           const int* __restrict__ nq_arr, int max_q, float ratio, float max_dist,
+                                                           sdpl_dmatch* __restrict__ out, int* __restrict__ n_acc) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i < nq_arr[p]) {
+    sdpl_dmatch b = best[(size_t)p * max_q + i], s = second[(size_t)p * max_q + i];
+    ok = b.train >= 0 && b.distance <= max_dist && b.distance < __fmul_rn(ratio, s.distance);
+    if (!ok) b.train = -1;
+    if (out) out[(size_t)p * max_q + i] = b;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_acc + p, __popc(m));
+}
+
 // radius search: one warp per query; counts all train rows within radius and keeps the k nearest
 // (ascending (distance, index)) by k rounds of warp-wide arg-min selection over a per-lane scan.
 __global__ void __launch_bounds__(256) k_match_radius(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt,
@@ -179,6 +196,7 @@ struct sdpl_matcher {
   DevBuf q, t, best, second, out, partial, scal, counts;
   int launches = 0;
   int sm_count = 148;
+  StageTimer timer;
 };
 
 static int match_run_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t, const int* d_nt,
@@ -189,11 +207,14 @@ static int match_run_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, s
   nsplit = std::min(nsplit, 64);
   int rc = m->partial.reserve(sizeof(Top2) * (size_t)npairs * max_q * nsplit);
   if (rc) return rc;
+  m->timer.begin(m->stream);
   k_match_partial<<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q, nsplit,
                                                                                  m->partial.as<Top2>());
   SDPL_LAUNCH_CHECK();
+  m->timer.mark(m->stream, "match_partial");
   k_match_merge<<<dim3(div_up(max_q, 256), npairs), 256, 0, m->stream>>>(m->partial.as<Top2>(), d_nq, max_q, nsplit, d_best, d_second);
   SDPL_LAUNCH_CHECK();
+  m->timer.mark(m->stream, "match_merge");
   return SDPL_OK;
 }
 
@@ -221,11 +242,18 @@ void sdpl_matcher_destroy(sdpl_matcher* m) {
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
   for (DevBuf* b : {&m->q, &m->t, &m->best, &m->second, &m->out, &m->partial, &m->scal, &m->counts}) b->release();
+  m->timer.release();
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
 }
 int sdpl_matcher_set_stream(sdpl_matcher* m, void* s) { if (!m) return SDPL_ERR_ARG; m->stream = s ? (cudaStream_t)s : m->own_stream; return SDPL_OK; }
 int sdpl_matcher_last_launches(const sdpl_matcher* m) { return m ? m->launches : 0; }
+int sdpl_matcher_set_profiling(sdpl_matcher* m, int on) { if (!m) return SDPL_ERR_ARG; m->timer.enabled = on != 0; return SDPL_OK; }
+int sdpl_matcher_stage_times(sdpl_matcher* m, float* ms, const char** names, int* launches, int cap) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  return m->timer.read(ms, names, launches, cap);
+}
 
 int sdpl_match_knn2_batch_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t, const int* d_nt,
                               size_t t_stride, int npairs, int max_q, int max_t, sdpl_dmatch* d_best, sdpl_dmatch* d_second, int sync) {
@@ -238,6 +266,23 @@ int sdpl_match_knn2_batch_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_
   int rc = match_run_dev(m, d_q, d_nq, q_stride, d_t, d_nt, t_stride, npairs, max_q, max_t, d_best, d_second);
   m->launches = g_launches;
   if (rc) return rc;
+  if (sync) SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  return SDPL_OK;
+}
+
+int sdpl_match_ratio_batch_dev(sdpl_matcher* m, const sdpl_dmatch* d_best, const sdpl_dmatch* d_second, const int* d_nq, int npairs,
+                               int max_q, float ratio, int max_dist, sdpl_dmatch* d_out, int* d_n_acc, int sync) {
+  if (!m || !d_best || !d_second || !d_nq || npairs < 1 || max_q < 1 || !d_n_acc) {
+    set_last_error("sdpl_match_ratio_batch_dev: bad argument");
+    return SDPL_ERR_ARG;
+  }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  g_launches = 0;
+  SDPL_CUDA(cudaMemsetAsync(d_n_acc, 0, sizeof(int) * npairs, m->stream));
+  k_match_ratio_batch<<<dim3(div_up(max_q, 256), npairs), 256, 0, m->stream>>>(d_best, d_second, d_nq, max_q, ratio, (float)max_dist, d_out,
+                                                                              d_n_acc);
+  SDPL_LAUNCH_CHECK();
+  m->launches = g_launches;
   if (sync) SDPL_CUDA(cudaStreamSynchronize(m->stream));
   return SDPL_OK;
 }

@@ -718,6 +718,7 @@ struct sdpl_orb {
   int fast_tiles = 0, blur_tiles = 0, max_quota = 0, kp_cap_total = 0, qt_cap = 64;
   int last_B = 0, launches = 0;
   int last_capacity = 0;
+  StageTimer timer;
 };
 
 static int orb_setup(sdpl_orb* o, int w, int h, int B) {
@@ -879,6 +880,7 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
   D.B = B;
   cudaStream_t st = o->stream;
   const int nl = o->nlevels;
+  o->timer.begin(st);
   {
     const LvlDev& L = D.L[0];
     dim3 g(div_up(L.pstride / 4, 128), L.h + 2 * kBorder, B);
@@ -891,10 +893,12 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
     k_pyr_resize<<<g, 128, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
+  o->timer.mark(st, "pyramid");
   if (o->fast_tiles > 0) {
     k_fast_score<<<dim3(o->fast_tiles, B), 256, 0, st>>>(D, o->fast_tiles);
     SDPL_LAUNCH_CHECK();
   }
+  o->timer.mark(st, "fast_score");
   if (D.cells_per_frame > 0) {
     dim3 g(div_up(D.cells_per_frame, 8), B);
     k_cell_nms<false><<<g, 256, 0, st>>>(D);
@@ -902,6 +906,7 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
     k_cell_nms<true><<<g, 256, 0, st>>>(D);
     SDPL_LAUNCH_CHECK();
   }
+  o->timer.mark(st, "cell_nms");
   {
     int cap = o->qt_cap;
     size_t smem = qt_smem_bytes(cap);
@@ -910,10 +915,13 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
     k_quadtree<<<dim3(nl, B), kQT, smem, st>>>(D, cap);
     SDPL_LAUNCH_CHECK();
   }
+  o->timer.mark(st, "quadtree");
   k_blur7<<<dim3(o->blur_tiles, B), 256, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
+  o->timer.mark(st, "blur7");
   k_orient_describe<<<dim3(div_up(D.kp_per_frame, 8), B), 256, 0, st>>>(D, d_kps, d_desc, capacity, d_n_out);
   SDPL_LAUNCH_CHECK();
+  o->timer.mark(st, "orient_describe");
   o->last_B = B; o->last_capacity = capacity;
   return SDPL_OK;
 }
@@ -983,6 +991,7 @@ void sdpl_orb_destroy(sdpl_orb* o) {
                     &o->kp_xy, &o->kp_resp, &o->cellsdev, &o->tables, &o->err, &o->in_stage, &o->out_kps, &o->out_desc, &o->out_n})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
+  o->timer.release();
   if (o->own_stream) cudaStreamDestroy(o->own_stream);
   delete o;
 }
@@ -1012,6 +1021,12 @@ int sdpl_orb_max_keypoints(const sdpl_orb* o) {
   return t;
 }
 int sdpl_orb_last_launches(const sdpl_orb* o) { return o ? o->launches : 0; }
+int sdpl_orb_set_profiling(sdpl_orb* o, int on) { if (!o) return SDPL_ERR_ARG; o->timer.enabled = on != 0; return SDPL_OK; }
+int sdpl_orb_stage_times(sdpl_orb* o, float* ms, const char** names, int* launches, int cap) {
+  if (!o) return 0;
+  cudaSetDevice(o->device);
+  return o->timer.read(ms, names, launches, cap);
+}
 
 int sdpl_orb_extract_batch_dev(sdpl_orb* o, const uint8_t* d_imgs, int nframes, int w, int h, int stride, size_t frame_stride,
                                sdpl_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_n_out, int sync) {

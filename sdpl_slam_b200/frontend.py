@@ -66,6 +66,9 @@ def load_library(path=None):
     L.sdpl_orb_level_counts.argtypes = [vp, i, vp]
     L.sdpl_orb_last_launches.argtypes = [vp]
     L.sdpl_orb_set_stream.argtypes = [vp, vp]
+    for name in ("orb", "line", "matcher"):
+        getattr(L, "sdpl_%s_set_profiling" % name).argtypes = [vp, i]
+        getattr(L, "sdpl_%s_stage_times" % name).argtypes = [vp, vp, vp, vp, i]
     # lines
     L.sdpl_line_create.argtypes = [C.POINTER(vp), i, i, f, i, f, i, i]
     L.sdpl_line_destroy.argtypes = [vp]; L.sdpl_line_destroy.restype = None
@@ -85,6 +88,7 @@ def load_library(path=None):
     L.sdpl_match_ratio.argtypes = [vp, vp, i, vp, i, f, i, vp, ip]
     L.sdpl_match_radius.argtypes = [vp, vp, i, vp, i, i, i, vp, vp]
     L.sdpl_match_knn2_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i, i, i, vp, vp, i]
+    L.sdpl_match_ratio_batch_dev.argtypes = [vp, vp, vp, vp, i, i, f, i, vp, vp, i]
     L.sdpl_matcher_last_launches.argtypes = [vp]
     L.sdpl_matcher_set_stream.argtypes = [vp, vp]
     if path is None:
@@ -108,6 +112,20 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class _Profiled:
+    """set_profiling / stage_times shared by the three handle classes (sdpl_*_set_profiling, sdpl_*_stage_times)."""
+    _kind = ""
+
+    def set_profiling(self, on=True):
+        _check(getattr(self._L, "sdpl_%s_set_profiling" % self._kind)(self._h, int(bool(on))))
+
+    def stage_times(self, cap=64):
+        """[(stage name, milliseconds, kernels launched)] of the last call (synchronises on its last event)."""
+        ms = (C.c_float * cap)(); names = (C.c_char_p * cap)(); nl = (C.c_int * cap)()
+        n = getattr(self._L, "sdpl_%s_stage_times" % self._kind)(self._h, ms, names, nl, cap)
+        return [(names[k].decode(), float(ms[k]), int(nl[k])) for k in range(n)]
+
+
 def _gray(image):
     img = np.asarray(image)
     if img.dtype != np.uint8 or img.ndim != 2:
@@ -118,7 +136,8 @@ def _gray(image):
     return img
 
 
-class ORBextractor:
+class ORBextractor(_Profiled):
+    _kind = "orb"
     """SDPL_SLAM::ORBextractor.  `extractor(image, mask) -> (keypoints, descriptors)`; keypoints is a structured
     array with cv::KeyPoint's fields, descriptors an (N, 32) uint8 array."""
 
@@ -235,7 +254,8 @@ class ORBextractor:
         return self._L.sdpl_orb_last_launches(self._h)
 
 
-class Lineextractor:
+class Lineextractor(_Profiled):
+    _kind = "line"
     """SDPL_SLAM::Lineextractor.  `extractor(image, mask) -> (keylines, descriptors_line)`."""
 
     def __init__(self, lsd_nfeatures=0, lsd_refine=2, lsd_scale=0.8, nlevels=2, scale=2.0, extractor=0, device=0):
@@ -316,7 +336,8 @@ class Lineextractor:
         return self._L.sdpl_line_last_launches(self._h)
 
 
-class BinaryDescriptorMatcher:
+class BinaryDescriptorMatcher(_Profiled):
+    _kind = "matcher"
     """Brute-force 256-bit Hamming matcher with the surface of cv::line_descriptor::BinaryDescriptorMatcher
     (match / knnMatch / radiusMatch).  Results are structured arrays with cv::DMatch's fields."""
 
@@ -368,6 +389,10 @@ class BinaryDescriptorMatcher:
         _check(self._L.sdpl_match_knn2_batch_dev(self._h, C.c_void_p(d_q), C.c_void_p(d_nq), q_stride, C.c_void_p(d_t),
                                                  C.c_void_p(d_nt), t_stride, npairs, max_q, max_t, C.c_void_p(d_best),
                                                  C.c_void_p(d_second), int(sync)))
+
+    def ratio_batch_dev(self, d_best, d_second, d_nq, npairs, max_q, ratio, max_dist, d_out, d_n_acc, sync=False):
+        _check(self._L.sdpl_match_ratio_batch_dev(self._h, C.c_void_p(d_best), C.c_void_p(d_second), C.c_void_p(d_nq), npairs, max_q,
+                                                  float(ratio), int(max_dist), C.c_void_p(d_out), C.c_void_p(d_n_acc), int(sync)))
 
     def set_stream(self, cuda_stream):
         _check(self._L.sdpl_matcher_set_stream(self._h, C.c_void_p(cuda_stream)))
