@@ -110,7 +110,11 @@ int sdpl_line_lbd_compute(sdpl_line* h, const uint8_t* img, int w, int h_, int s
 /* raw cv::LineSegmentDetector::detect output (x1,y1,x2,y2 per line) of pyramid level `octave` of the last
  * single-frame call, for parity tests */
 int sdpl_line_lsd_segments(sdpl_line* h, int frame, int octave, float* xyxy, int capacity, int* n_out);
+/* introspection: rectangles handed to the NFA stage in seed order, 8 doubles each {x1,y1,x2,y2,width,p,accepted,tag} */
+int sdpl_line_debug_pending(sdpl_line* h, int frame, int octave, double* out, int capacity, int* n_out);
 int sdpl_line_last_launches(const sdpl_line* h);
+/* test knob: 1 = grow LSD regions strictly one seed at a time (no speculative waves); results are identical */
+int sdpl_line_set_serial(sdpl_line* h, int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Descriptor matcher -- 256-bit Hamming (cv::line_descriptor::match, bitops_custom.hpp:86-99) brute force;

@@ -68,6 +68,7 @@ def lib(path=None):
         L.orc_line_destroy.argtypes = [C.c_void_p]
         L.orc_line_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_line_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.orc_line_last_segments.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     if hasattr(L, "orc_lsd_detect"):
         L.orc_lsd_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                      C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -220,6 +221,12 @@ class LineOracle:
             raise RuntimeError("oracle line extractor failed: %d" % n)
         assert n <= cap
         return kls[:n].copy(), desc[:n].copy()
+
+    def last_segments(self, octave, cap=100000):
+        """raw cv::LineSegmentDetector output (x1,y1,x2,y2) of pyramid octave `octave` of the last call"""
+        out = np.empty((cap, 4), np.float32)
+        n = self.L.orc_line_last_segments(self.h, int(octave), _p(out), cap)
+        return out[:n].copy()
 
     def tables(self):
         n = self.nlevels

@@ -12,7 +12,11 @@ pids=""
 for s in $SRCS; do
   o="$HERE/build/$(basename "$s" .cu).o"
   OBJS="$OBJS $o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/../../include/sdpl_frontend.h" -nt "$o" ]; then
+  stale=0
+  for d in "$s" "$HERE"/*.cuh "$HERE"/../../include/*.h "$HERE"/../../include/*.inc "$HERE/build.sh"; do
+    if [ ! -f "$o" ] || [ "$d" -nt "$o" ]; then stale=1; fi
+  done
+  if [ $stale = 1 ]; then
     ( $NVCC $FLAGS -c "$s" -o "$o" > "$HERE/build/$(basename "$s" .cu).log" 2>&1 || { cat "$HERE/build/$(basename "$s" .cu).log"; exit 1; } ) &
     pids="$pids $!"
   fi

@@ -81,6 +81,8 @@ def load_library(path=None):
     L.sdpl_line_lsd_segments.argtypes = [vp, i, i, vp, i, ip]
     L.sdpl_line_last_launches.argtypes = [vp]
     L.sdpl_line_set_stream.argtypes = [vp, vp]
+    L.sdpl_line_set_serial.argtypes = [vp, i]
+    L.sdpl_line_debug_pending.argtypes = [vp, i, i, vp, i, ip]
     # matcher
     L.sdpl_matcher_create.argtypes = [C.POINTER(vp), i]
     L.sdpl_matcher_destroy.argtypes = [vp]; L.sdpl_matcher_destroy.restype = None
@@ -323,6 +325,14 @@ class Lineextractor(_Profiled):
         _check(self._L.sdpl_line_lbd_compute(self._h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kls), kls.shape[0],
                                              _p(desc)))
         return desc
+
+    def pending_rects(self, octave, frame=0, capacity=8192):
+        out = np.zeros((capacity, 8), np.float64); n = C.c_int()
+        _check(self._L.sdpl_line_debug_pending(self._h, frame, octave, _p(out), capacity, C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_serial(self, on=True):
+        _check(self._L.sdpl_line_set_serial(self._h, int(bool(on))))
 
     def lsd_segments(self, octave, frame=0, capacity=65536):
         out = np.empty((capacity, 4), np.float32); n = C.c_int()

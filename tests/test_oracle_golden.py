@@ -71,7 +71,9 @@ def test_orb_tables_and_geometry(oracle):
                                                     (416, 126), (347, 105)]
     np.testing.assert_array_equal(oracle.OrbOracle(2500, 1.2, 8, 20, 7).tables()["quota"], [543, 452, 377, 314, 262, 218, 182, 152])
     inc = open(os.path.join(os.path.dirname(G), "..", "include", "sdpl_orb_pattern.inc")).read()
-    ints = [int(x) for x in inc.replace("\n", " ").split(",") if x.strip().lstrip("-").isdigit()]
+    import re
+    inc = re.sub(r"/\*.*?\*/", "", inc, flags=re.S)
+    ints = [int(x) for x in re.findall(r"-?\d+", inc)]
     assert len(ints) == 1024
     assert hashlib.sha256(",".join(str(i) for i in ints).encode()).hexdigest() == \
         "88df8ca875cc8db56799edd57bb914edad8acb2d48c202b7a464a575b55dbdb8"
