@@ -112,8 +112,12 @@ int sdpl_line_lbd_compute(sdpl_line* h, const uint8_t* img, int w, int h_, int s
 int sdpl_line_lsd_segments(sdpl_line* h, int frame, int octave, float* xyxy, int capacity, int* n_out);
 /* introspection: rectangles handed to the NFA stage in seed order, 8 doubles each {x1,y1,x2,y2,width,p,accepted,tag} */
 int sdpl_line_debug_pending(sdpl_line* h, int frame, int octave, double* out, int capacity, int* n_out);
+/* introspection: region-growing kernel counters of one (frame, octave): cycles in {select, speculate, evaluate+commit, re-run},
+ * then {waves, re-runs, dead seeds, seeds} */
+int sdpl_line_debug_grow_profile(sdpl_line* h, int frame, int octave, long long* out8);
 int sdpl_line_last_launches(const sdpl_line* h);
-/* test knob: 1 = grow LSD regions strictly one seed at a time (no speculative waves); results are identical */
+/* test / tuning knob, LSD region-growing schedule: 0 = speculative lock-step waves of 32 seeds (default), 1 = strictly one seed
+ * at a time, 2 = speculative with dynamic lane scheduling and a re-order buffer (experimental); all give identical results */
 int sdpl_line_set_serial(sdpl_line* h, int on);
 
 /* ------------------------------------------------------------------------------------------------

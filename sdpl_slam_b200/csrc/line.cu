@@ -54,6 +54,9 @@ struct LineDev {
   int* reg; lsd::Pending* pend; int pend_cap; int* npend;
   uint8_t* g; short* sdx; short* sdy;
   int* err;
+  long long* prof;
+  const double* lgam; int lgam_n;
+  lsd::Rect* rob_rect; lsd::RobEntry* rob; int rob_w, rob_w_run;
   double rho, prec, p, density_th, log_eps, scale;
   int refine, serial_mode;
   double min_length;
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(kBins) k_lsd_sort_scan(LineDev D) {
 
 // ------------------------------------------------------------------------------------------------
 // L5: region growing + rectangle fitting + refine (lsd_grow.cuh).  One warp (= one CTA) per (frame, octave).
-// L6: NFA validation, one warp per pending rectangle.
+// L6: NFA validation, one thread per pending rectangle.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::Task& T) {
   const OctDev& O = D.O[o];
@@ -297,25 +300,35 @@ __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::T
   T.pend = D.pend + (size_t)task * D.pend_cap; T.pend_cap = D.pend_cap; T.npend = D.npend + task;
   T.prec = D.prec; T.p = D.p; T.log_nt = O.log_nt; T.density_th = D.density_th; T.log_eps = D.log_eps; T.scale = D.scale;
   T.min_reg = O.min_reg; T.refine = D.refine; T.err = D.err;
+  T.prof = D.prof ? D.prof + (size_t)task * 8 : nullptr;
+  T.lgam = D.lgam; T.lgam_n = D.lgam_n;
+  T.rob_rect = D.rob_rect + (size_t)task * D.rob_w; T.rob = D.rob + (size_t)task * D.rob_w; T.rob_w = D.rob_w_run;
 }
 
 __global__ void __launch_bounds__(32) k_lsd_grow(LineDev D) {
-  __shared__ int sel[32];
+  __shared__ lsd::RobShared S;
   // big octave-0 tasks first: blockIdx.x enumerates (octave-major, frame-minor)
   const int o = blockIdx.x / D.B, f = blockIdx.x % D.B;
   lsd::Task T;
   make_task(D, f, o, T);
-  lsd::grow_task(T, D.serial_mode, sel);
+  if (D.serial_mode == 2) lsd::grow_task_rob(T, S);               // 2: dynamic lane scheduling + re-order buffer (experimental)
+  else lsd::grow_task(T, D.serial_mode == 1, S.sel);               // 0: 32-seed lock-step waves (default), 1: one seed at a time
 }
 
-__global__ void __launch_bounds__(128) k_lsd_nfa(LineDev D) {
+constexpr int kLgamN = 32768;
+__global__ void k_lgam_table(double* t, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) t[i] = i > 0 ? lsd::log_gamma((double)i) : 0.0;
+}
+
+__global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
   const int task = blockIdx.y;
   const int f = task / D.nl, o = task % D.nl;
   const int np = D.npend[task];
-  if ((int)blockIdx.x * 4 >= np) return;
+  if ((int)(blockIdx.x * blockDim.x) >= np) return;
   lsd::Task T;
   make_task(D, f, o, T);
-  for (int i = blockIdx.x * 4 + (threadIdx.x >> 5); i < np; i += gridDim.x * 4) lsd::validate_pending(T, i);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) lsd::validate_pending(T, i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -617,7 +630,8 @@ struct sdpl_line {
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
   DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
-  DevBuf in_stage, out_kls, out_desc, out_n;
+  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob;
+  int rob_w = 2048, rob_w_run = 2048;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
   int last_B = 0, launches = 0, serial_mode = 0;
@@ -689,7 +703,8 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
     O.lbd_off = lbd_off; lbd_off += align_up((size_t)lw * lh, 16);
     O.nchunks = div_up(O.npx, kSortChunk);
     O.hist_off = hist_off; hist_off += (size_t)O.nchunks * kBins;
-    O.lane_cap = std::max(4096, O.npx / 32);
+    O.lane_cap = 4096;                                   // per-lane list ring, power of two >= npx/32
+    while (O.lane_cap < O.npx / 32) O.lane_cap *= 2;
     O.reg_off = reg_off; reg_off += (size_t)32 * O.lane_cap + O.npx;
     O.log_nt = 5 * (log10((double)O.sw) + log10((double)O.sh)) / 2 + log10(11.0);
     O.min_reg = (int)(size_t)(-O.log_nt / log10(D.p));
@@ -762,6 +777,15 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->sdy.reserve(sizeof(short) * D.lbd_frame * B))) return rc;
   if ((rc = o->tmpkl.reserve(sizeof(sdpl_keyline) * (size_t)D.pend_cap * nl * (o->nfeatures ? B : 1)))) return rc;
   if ((rc = o->err.reserve(sizeof(int)))) return rc;
+  if ((rc = o->prof.reserve(sizeof(long long) * 8 * nl * B))) return rc;
+  if ((rc = o->robrect.reserve(sizeof(lsd::Rect) * (size_t)o->rob_w * nl * B))) return rc;
+  if ((rc = o->rob.reserve(sizeof(lsd::RobEntry) * (size_t)o->rob_w * nl * B))) return rc;
+  if (!o->lgam.p) {
+    if ((rc = o->lgam.reserve(sizeof(double) * kLgamN))) return rc;
+    k_lgam_table<<<div_up(kLgamN, 256), 256, 0, o->stream>>>(o->lgam.as<double>(), kLgamN);
+    SDPL_CUDA(cudaGetLastError());
+    SDPL_CUDA(cudaStreamSynchronize(o->stream));
+  }
   const size_t u16_bytes = align_up(t_u16.size() * 2 + 2, 16), s16_bytes = align_up(t_s16.size() * 2 + 2, 16);
   if ((rc = o->tables.reserve(u16_bytes + s16_bytes + t_i32.size() * 4 + 16))) return rc;
   char* tb = (char*)o->tables.p;
@@ -785,7 +809,8 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   D.state = o->state.as<uint32_t>(); D.order = o->order.as<uint32_t>(); D.hist = o->hist.as<uint32_t>();
   D.maxg2 = o->maxg2.as<int>(); D.ndef = o->ndef.as<int>(); D.reg = o->reg.as<int>(); D.pend = o->pend.as<lsd::Pending>();
   D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sdx = o->sdx.as<short>(); D.sdy = o->sdy.as<short>();
-  D.err = o->err.as<int>();
+  D.err = o->err.as<int>(); D.prof = o->prof.as<long long>(); D.lgam = o->lgam.as<double>(); D.lgam_n = kLgamN;
+  D.rob_rect = o->robrect.as<lsd::Rect>(); D.rob = o->rob.as<lsd::RobEntry>(); D.rob_w = o->rob_w;
   D.B = B;
   o->gw = w; o->gh = h; o->gB = B;
   return SDPL_OK;
@@ -797,7 +822,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   int rc = line_setup(o, w, h, B);
   if (rc) return rc;
   LineDev& D = o->D;
-  D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride; D.serial_mode = o->serial_mode;
+  D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride; D.serial_mode = o->serial_mode; D.rob_w_run = o->rob_w_run;
   cudaStream_t st = o->stream;
   const int nl = o->nlevels;
   o->timer.begin(st);
@@ -831,7 +856,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   k_lsd_grow<<<nl * B, 32, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_grow");
-  k_lsd_nfa<<<dim3(48, nl * B), 128, 0, st>>>(D);
+  k_lsd_nfa<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_nfa");
   k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());
@@ -921,7 +946,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
   for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->reg, &o->pend, &o->npend,
-                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n})
+                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
   o->timer.release();
@@ -950,8 +975,18 @@ int sdpl_line_stage_times(sdpl_line* o, float* ms, const char** names, int* laun
   cudaSetDevice(o->device);
   return o->timer.read(ms, names, launches, cap);
 }
-// test / debugging knob: 1 = grow regions strictly one seed at a time (no speculation); results must be identical
-int sdpl_line_set_serial(sdpl_line* o, int on) { if (!o) return SDPL_ERR_ARG; o->serial_mode = on != 0; return SDPL_OK; }
+// test / tuning knob: region-growing schedule. 0 = speculative lock-step waves of 32 seeds (default), 1 = strictly one seed at a
+// time (no speculation), 2 = speculative with dynamic lane scheduling and a re-order buffer (experimental: measured slower than
+// the waves on B200).  All three give identical results.
+int sdpl_line_set_serial(sdpl_line* o, int on) {
+  if (!o || on < 0) return SDPL_ERR_ARG;
+  // bits 0-1: schedule; bits 8..: re-order buffer size override (power of two, <= allocated), for tuning
+  const int w = on >> 8;
+  if ((on & 3) > 2 || (w && (w < 32 || w > 2048 || (w & (w - 1))))) return SDPL_ERR_ARG;
+  o->serial_mode = on & 3;
+  if (w) o->rob_w_run = w;
+  return SDPL_OK;
+}
 
 int sdpl_line_extract_batch_dev(sdpl_line* o, const uint8_t* d_imgs, int nframes, int w, int h, int stride, size_t frame_stride,
                                 sdpl_keyline* d_kls, uint8_t* d_desc, int capacity, int* d_n_out, int sync) {
@@ -1091,6 +1126,15 @@ int sdpl_line_debug_pending(sdpl_line* o, int frame, int octave, double* out, in
     d[6] = P[i].npix; d[7] = P[i].tag;
   }
   *n_out = np;
+  return SDPL_OK;
+}
+
+// introspection: grow-kernel cycle counters of one task: {select, speculate, evaluate+commit, re-run, waves, re-runs, dead, seeds}
+int sdpl_line_debug_grow_profile(sdpl_line* o, int frame, int octave, long long* out8) {
+  if (!o || o->gw == 0 || frame < 0 || frame >= o->last_B || octave < 0 || octave >= o->nlevels || !out8) return SDPL_ERR_ARG;
+  SDPL_CUDA(cudaSetDevice(o->device));
+  SDPL_CUDA(cudaStreamSynchronize(o->stream));
+  SDPL_CUDA(cudaMemcpy(out8, o->D.prof + (size_t)(frame * o->nlevels + octave) * 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
   return SDPL_OK;
 }
 

@@ -82,6 +82,7 @@ def load_library(path=None):
     L.sdpl_line_last_launches.argtypes = [vp]
     L.sdpl_line_set_stream.argtypes = [vp, vp]
     L.sdpl_line_set_serial.argtypes = [vp, i]
+    L.sdpl_line_debug_grow_profile.argtypes = [vp, i, i, vp]
     L.sdpl_line_debug_pending.argtypes = [vp, i, i, vp, i, ip]
     # matcher
     L.sdpl_matcher_create.argtypes = [C.POINTER(vp), i]
@@ -331,8 +332,14 @@ class Lineextractor(_Profiled):
         _check(self._L.sdpl_line_debug_pending(self._h, frame, octave, _p(out), capacity, C.byref(n)))
         return out[:n.value].copy()
 
+    def grow_profile(self, octave, frame=0):
+        out = np.zeros(8, np.int64)
+        _check(self._L.sdpl_line_debug_grow_profile(self._h, frame, octave, _p(out)))
+        return dict(zip(("select", "speculate", "commit", "rerun", "waves", "reruns", "dead", "seeds"), out.tolist()))
+
     def set_serial(self, on=True):
-        _check(self._L.sdpl_line_set_serial(self._h, int(bool(on))))
+        """region-growing schedule: 0/False speculative lock-step waves (default), 1/True one seed at a time, 2 re-order buffer"""
+        _check(self._L.sdpl_line_set_serial(self._h, int(on)))
 
     def lsd_segments(self, octave, frame=0, capacity=65536):
         out = np.empty((capacity, 4), np.float32); n = C.c_int()

@@ -2,7 +2,7 @@ import sys, numpy as np
 sys.path.insert(0, '.')
 from sdpl_slam_b200 import frontend as fe, synth
 gs = fe.Lineextractor(0, 2, 0.8, 2, 2.0, 0); gs.set_serial(True)
-gp = fe.Lineextractor(0, 2, 0.8, 2, 2.0, 0)
+gp = fe.Lineextractor(0, 2, 0.8, 2, 2.0, 0); gp.set_serial(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 for seed in range(1, 13):
     h, w = (375, 1242) if seed % 3 else (480, 640)
     img = synth.frame(seed, h, w)
