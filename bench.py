@@ -4,8 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
 
-One "step" = one pass of the front-end over a batch of F frames per GPU (frames come as (frame, partner) pairs;
-every frame's ORB and LBD descriptors are matched against its pair partner's).  `value` is timed with the frames
+One "step" = one pass of the front-end over a batch of F consecutive frames per GPU (the synthetic sequence alternates
+frame(seed), partner(seed); every frame's ORB and LBD descriptors are matched against the previous frame's).  `value` is timed with the frames
 already resident in HBM; `e2e` goes through the host-buffer C ABI (H2D and D2H copies inside the timed region).
 Prints ONE JSON line on rank 0.  The oracle under oracle/ is used here only for the cpu_baseline / --impl reference
 legs (it is the CPU restatement of the reference; the reference itself needs OpenCV 3.4 C++ and cannot be built here).
@@ -199,7 +199,7 @@ def run_reference(args, stages):
 
 def _config(stages, frames_per_gpu):
     return {"workload": "KITTI-size 1242x375 point+line front-end: ORB 2000 (8 levels, x1.2, FAST 20/7) + LSD/LBD lines "
-                        "(refine ADV, 0.8, 2 octaves) + frame-to-partner Hamming knn-2 ratio matching of ORB and LBD descriptors "
+                        "(refine ADV, 0.8, 2 octaves) + frame-to-frame (t vs t-1) Hamming knn-2 ratio matching of ORB and LBD descriptors "
                         "[BASELINE.json configs[1]]",
             "stages": "+".join(stages), "frames_per_gpu_per_step": frames_per_gpu, "width": W, "height": H,
             "l2": "per-step working set (pyramids, score/blur planes, gradient maps) exceeds the 126 MB L2 many times; "
@@ -226,12 +226,13 @@ def run_gpu(args, stages):
     F = args.frames - args.frames % 2
     P = F // 2
     use_line, use_match = "line" in stages, "match" in stages
-    # ---- synthetic frames: rank r owns pairs [r*P, (r+1)*P) (weak scaling: per-GPU work is fixed).
-    #      layout: frames [0,P) = frame(seed), frames [P,2P) = partner(seed); frame p is matched against frame P+p and back
+    # ---- synthetic frames: rank r owns seeds [r*P, (r+1)*P) (weak scaling: per-GPU work is fixed).  The batch is a
+    #      sequence frame(s0), partner(s0), frame(s1), partner(s1), ...; frame t is matched against frame t-1
+    #      (frame 0 against the last frame of the previous step)
     host = np.empty((F, H, W), np.uint8)
     for p in range(P):
         seed = rank * P + p
-        host[p] = synth.frame(seed, H, W); host[P + p] = synth.partner(seed, H, W)
+        host[2 * p] = synth.frame(seed, H, W); host[2 * p + 1] = synth.partner(seed, H, W)
     pinned = torch.from_numpy(host).pin_memory()
     d_imgs = pinned.to(dev)
 
@@ -244,14 +245,15 @@ def run_gpu(args, stages):
         lmat = fe.BinaryDescriptorMatcher(device=local)
     cap = orb.max_keypoints()
     u8, i32 = torch.uint8, torch.int32
-    d_kps = torch.empty((F, cap, 28), dtype=u8, device=dev); d_desc = torch.zeros((F, cap, 32), dtype=u8, device=dev)
-    d_nkp = torch.zeros(F, dtype=i32, device=dev)
+    # descriptor blocks have F+1 slots: slot 0 = last frame of the previous step, slot t+1 = frame t
+    d_kps = torch.empty((F, cap, 28), dtype=u8, device=dev); d_desc = torch.zeros((F + 1, cap, 32), dtype=u8, device=dev)
+    d_nkp = torch.zeros(F + 1, dtype=i32, device=dev)
     d_best = torch.empty((F, cap, 16), dtype=u8, device=dev); d_second = torch.empty((F, cap, 16), dtype=u8, device=dev)
     d_nacc = torch.zeros(F, dtype=i32, device=dev)
     d_kls = d_ldesc = d_nkl = d_lbest = d_lsecond = d_lnacc = None
     if use_line:
-        d_kls = torch.empty((F, LINE_CAP, 68), dtype=u8, device=dev); d_ldesc = torch.zeros((F, LINE_CAP, 32), dtype=u8, device=dev)
-        d_nkl = torch.zeros(F, dtype=i32, device=dev)
+        d_kls = torch.empty((F, LINE_CAP, 68), dtype=u8, device=dev); d_ldesc = torch.zeros((F + 1, LINE_CAP, 32), dtype=u8, device=dev)
+        d_nkl = torch.zeros(F + 1, dtype=i32, device=dev)
         d_lbest = torch.empty((F, LINE_CAP, 16), dtype=u8, device=dev); d_lsecond = torch.empty((F, LINE_CAP, 16), dtype=u8, device=dev)
         d_lnacc = torch.zeros(F, dtype=i32, device=dev)
     stats = torch.zeros((F, 4), dtype=i32, device=dev)
@@ -266,40 +268,40 @@ def run_gpu(args, stages):
             hdl.set_profiling(True)
     launches = [0]
 
-    def match_pairs(m, d, n, rows, best, second, nacc):
-        """problem p: frame p vs frame P+p, then frame P+p vs frame p (two batched launches of P problems each)."""
+    def match_prev(m, stream, d, n, rows, best, second, nacc):
+        """F problems: slot t+1 (frame t) against slot t (frame t-1); then slot F becomes slot 0 of the next step."""
         fs = rows * 32
-        for q0 in (0, P):
-            t0 = P - q0
-            m.knn2_batch_dev(d.data_ptr() + q0 * fs, n.data_ptr() + 4 * q0, fs, d.data_ptr() + t0 * fs, n.data_ptr() + 4 * t0, fs, P, rows,
-                             rows, best.data_ptr() + q0 * rows * 16, second.data_ptr() + q0 * rows * 16, False)
-            launches[0] += m.last_launches()
-            m.ratio_batch_dev(best.data_ptr() + q0 * rows * 16, second.data_ptr() + q0 * rows * 16, n.data_ptr() + 4 * q0, P, rows, RATIO,
-                              MAX_DIST, 0, nacc.data_ptr() + 4 * q0, False)
-            launches[0] += m.last_launches()
+        m.knn2_batch_dev(d.data_ptr() + fs, n.data_ptr() + 4, fs, d.data_ptr(), n.data_ptr(), fs, F, rows, rows, best.data_ptr(),
+                         second.data_ptr(), False)
+        launches[0] += m.last_launches()
+        m.ratio_batch_dev(best.data_ptr(), second.data_ptr(), n.data_ptr() + 4, F, rows, RATIO, MAX_DIST, 0, nacc.data_ptr(), False)
+        launches[0] += m.last_launches()
+        with torch.cuda.stream(stream):
+            d[0].copy_(d[F]); n[0:1].copy_(n[F:F + 1])
 
-    def step_dev(imgs_ptr=None):
+    def step_dev():
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event(); ev.record(main)
         s_orb.wait_event(ev)
-        orb.extract_batch_dev(imgs_ptr or d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_nkp.data_ptr())
+        orb.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_nkp.data_ptr() + 4)
         launches[0] += orb.last_launches()
         if use_line:
             s_line.wait_event(ev)
-            line.extract_batch_dev(imgs_ptr or d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr(), LINE_CAP, d_nkl.data_ptr())
+            line.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr() + LINE_CAP * 32, LINE_CAP,
+                                   d_nkl.data_ptr() + 4)
             launches[0] += line.last_launches()
         if use_match:
             s_match.wait_stream(s_orb)
-            match_pairs(mat, d_desc, d_nkp, cap, d_best, d_second, d_nacc)
+            match_prev(mat, s_match, d_desc, d_nkp, cap, d_best, d_second, d_nacc)
             if use_line:
                 s_lmatch.wait_stream(s_line)
-                match_pairs(lmat, d_ldesc, d_nkl, LINE_CAP, d_lbest, d_lsecond, d_lnacc)
+                match_prev(lmat, s_lmatch, d_ldesc, d_nkl, LINE_CAP, d_lbest, d_lsecond, d_lnacc)
         for s in (s_orb, s_line, s_match, s_lmatch):
             main.wait_stream(s)
         # per-frame statistics {n_kp, n_lines, n_point_matches, n_line_matches}; NCCL gathers them across ranks
-        stats[:, 0].copy_(d_nkp); stats[:, 2].copy_(d_nacc)
+        stats[:, 0].copy_(d_nkp[1:]); stats[:, 2].copy_(d_nacc)
         if use_line:
-            stats[:, 1].copy_(d_nkl); stats[:, 3].copy_(d_lnacc)
+            stats[:, 1].copy_(d_nkl[1:]); stats[:, 3].copy_(d_lnacc)
         if world > 1:
             dist.all_gather_into_tensor(gathered, stats)
 
@@ -336,12 +338,13 @@ def run_gpu(args, stages):
     # ---- per-stage kernel times, each pipeline alone on the device (no cross-stream overlap) ----
     stage_ms, stage_launch = {}, {}
     reps = 3
-    for hdl, fn in ((orb, lambda: orb.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_nkp.data_ptr())),
-                    (line, (lambda: line.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr(), LINE_CAP,
-                                                           d_nkl.data_ptr())) if use_line else None),
-                    (mat, (lambda: mat.knn2_batch_dev(d_desc.data_ptr(), d_nkp.data_ptr(), cap * 32, d_desc.data_ptr() + P * cap * 32,
-                                                      d_nkp.data_ptr() + 4 * P, cap * 32, P, cap, cap, d_best.data_ptr(),
-                                                      d_second.data_ptr(), False)) if use_match else None)):
+    for hdl, fn in ((orb, lambda: orb.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr() + cap * 32, cap,
+                                                        d_nkp.data_ptr() + 4)),
+                    (line, (lambda: line.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr() + LINE_CAP * 32,
+                                                           LINE_CAP, d_nkl.data_ptr() + 4)) if use_line else None),
+                    (mat, (lambda: mat.knn2_batch_dev(d_desc.data_ptr() + cap * 32, d_nkp.data_ptr() + 4, cap * 32, d_desc.data_ptr(),
+                                                      d_nkp.data_ptr(), cap * 32, F, cap, cap, d_best.data_ptr(), d_second.data_ptr(),
+                                                      False)) if use_match else None)):
         if hdl is None or fn is None:
             continue
         for _ in range(reps):
@@ -355,7 +358,7 @@ def run_gpu(args, stages):
     peak, peak_src = _peaks()
     stage_rows = []
     for name, t_ms in stage_ms.items():
-        frames_in_call = P if name.startswith("match") else F
+        frames_in_call = F
         nbytes = alg.get(name, 0) * frames_in_call
         gbs = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
         stage_rows.append({"stage": name, "ms": round(t_ms, 4), "launches": stage_launch.get(name, 0), "alg_bytes": int(nbytes),
@@ -371,48 +374,35 @@ def run_gpu(args, stages):
 
     # ---- end to end through the host-buffer C ABI (`e2e`): pinned host frames in, results back on the host ----
     e2e = None
-    if not args.no_e2e:
-        himgs = pinned.numpy()
-        h2d = d2h = 0
-
-        def step_e2e():
-            nonlocal h2d, d2h
-            res = orb.extract_batch(himgs)
-            h2d += himgs.nbytes; d2h += sum(k.nbytes + d.nbytes for k, d in res) + 4 * F
-            lres = None
-            if use_line:
-                lres = line.extract_batch(himgs, capacity=LINE_CAP)
-                h2d += himgs.nbytes; d2h += sum(k.nbytes + d.nbytes for k, d in lres) + 4 * F
-            nm = 0
-            if use_match:
-                for p in range(P):
-                    for q, t_ in ((p, P + p), (P + p, p)):
-                        out, n = mat.ratioMatch(res[q][1], res[t_][1], RATIO, MAX_DIST)
-                        nm += n; h2d += res[q][1].nbytes + res[t_][1].nbytes; d2h += out.nbytes + 4
-                        if use_line and len(lres[q][1]) and len(lres[t_][1]):
-                            out, n = lmat.ratioMatch(lres[q][1], lres[t_][1], RATIO, MAX_DIST)
-                            h2d += lres[q][1].nbytes + lres[t_][1].nbytes; d2h += out.nbytes + 4
-            return nm
-
+    if not args.no_e2e and use_line and use_match:
+        # release the device-resident arm's buffers first
         for hdl in (orb, mat, line, lmat):
-            if hdl is not None:
-                hdl.set_stream(0); hdl.set_profiling(False)
-        e2e_steps = max(1, min(args.steps, 3))
-        step_e2e()
+            hdl.set_stream(0)
+        del orb, mat, line, lmat
+        front = fe.FrontEnd(ORB_CFG["nfeatures"], ORB_CFG["scale"], ORB_CFG["nlevels"], ORB_CFG["ini"], ORB_CFG["mn"], LINE_CFG["nfeatures"],
+                            LINE_CFG["refine"], LINE_CFG["lsd_scale"], LINE_CFG["nlevels"], LINE_CFG["scale"], RATIO, MAX_DIST, device=local)
+        himgs = pinned.numpy()
+        e2e_steps = max(1, min(args.steps, 5))
+        res = front.process(himgs)
+        res = front.process(himgs)
         barrier()
-        h2d = d2h = 0
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            step_e2e()
+            res = front.process(himgs)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * F * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d // e2e_steps),
-               "d2h_bytes_per_step": int(d2h // e2e_steps), "steps": e2e_steps,
-               "api": "ORBextractor.extract_batch / Lineextractor.extract_batch / BinaryDescriptorMatcher.ratioMatch on host arrays "
-                      "(sdpl_orb_extract_batch, sdpl_line_extract_batch, sdpl_match_ratio)"}
+        est = res["stats"]
+        d2h = int(est["n_kp"].sum()) * (28 + 32 + 16) + int(est["n_lines"].sum()) * (68 + 32 + 16) + 16 * F
+        e2e = {"value": world * F * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(himgs.nbytes),
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "gpu_launches_per_step": front.last_launches(),
+               "api": "FrontEnd.process(host frames) = sdpl_frontend_process: pinned host frames in (one H2D), keypoints + ORB "
+                      "descriptors + keylines + LBD descriptors + ratio-filtered matches + per-frame counts back on the host",
+               "frame_stats_mean": {"keypoints": float(est["n_kp"].mean()), "keylines": float(est["n_lines"].mean()),
+                                    "point_matches": float(est["n_pt_matches"].mean()), "line_matches": float(est["n_ln_matches"].mean())}}
+        del front
 
     if rank == 0:
         cpu = None if args.no_cpu else cpu_baseline(stages)
@@ -434,7 +424,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=128, help="frames per GPU per step (even)")
+    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step (even); BASELINE configs[3]: 4096 frames over 8 GPUs")
     ap.add_argument("--stages", default="orb,line,match")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -148,6 +148,34 @@ int sdpl_match_ratio_batch_dev(sdpl_matcher* h, const sdpl_dmatch* d_best, const
                                int max_q, float ratio, int max_dist, sdpl_dmatch* d_out, int* d_n_acc, int sync);
 int sdpl_matcher_last_launches(const sdpl_matcher* h);
 
+/* read-and-clear the device-side overflow flag of the last asynchronous (*_dev, sync == 0) calls; synchronises the stream.
+ * SDPL_OK, or SDPL_ERR_OVERFLOW when an internal buffer (FAST candidates, quadtree nodes, pending rectangles) overflowed. */
+int sdpl_orb_check(sdpl_orb* h);
+int sdpl_line_check(sdpl_line* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * The whole per-frame front-end in one call: Frame::Frame's ExtractORB + ExtractLines (src/Frame.cc:314,328 -> :927-949)
+ * plus frame-to-frame descriptor association of points and lines (frame t against frame t-1; frame 0 of a call against
+ * the last frame of the previous call, none on the very first call / after sdpl_frontend_reset).
+ * One upload of the frames; ORB and line pipelines run concurrently on two streams, the two matchers on two more.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sdpl_frontend sdpl_frontend;
+typedef struct { int32_t n_kp, n_lines, n_pt_matches, n_ln_matches; } sdpl_frame_stats;
+int sdpl_frontend_create(sdpl_frontend** h, int nfeatures, float scale, int nlevels, int ini_th, int min_th, int lsd_nfeatures,
+                         int lsd_refine, float lsd_scale, int lsd_levels, float lsd_pyr_scale, float ratio, int max_dist, int device);
+void sdpl_frontend_destroy(sdpl_frontend* h);
+/* rows per frame of the output arrays of sdpl_frontend_process */
+int sdpl_frontend_capacities(const sdpl_frontend* h, int* kp_capacity, int* kl_capacity);
+/* forget the previous frame (start of a new sequence) */
+int sdpl_frontend_reset(sdpl_frontend* h);
+/* imgs: HOST, n frames frame_stride bytes apart.  Outputs (HOST): frame f owns rows [f*cap, f*cap + count):
+ * kps/desc/pt_matches with cap = kp_capacity, kls/ldesc/ln_matches with cap = kl_capacity; stats[f] holds the counts.
+ * pt_matches[f*cap + i] is the ratio-filtered best match of keypoint i of frame f in frame f-1 (train = -1: rejected). */
+int sdpl_frontend_process(sdpl_frontend* h, const uint8_t* imgs, int nframes, int w, int h_, int stride, size_t frame_stride,
+                          sdpl_keypoint* kps, uint8_t* desc, sdpl_keyline* kls, uint8_t* ldesc, sdpl_dmatch* pt_matches,
+                          sdpl_dmatch* ln_matches, sdpl_frame_stats* stats);
+int sdpl_frontend_last_launches(const sdpl_frontend* h);
+
 /* Per-stage device timing (CUDA events on the handle's stream).  set_profiling(1) makes every following call record
  * one event per stage; stage_times returns the stages of the LAST call: ms[i], names[i] (static strings), launches[i]
  * = kernels launched in stage i; return value = number of stages written (<= cap).  Synchronises on the last event. */

@@ -969,6 +969,12 @@ int sdpl_line_tables(const sdpl_line* o, float* sf, float* isf, float* s2, float
   return SDPL_OK;
 }
 int sdpl_line_last_launches(const sdpl_line* o) { return o ? o->launches : 0; }
+int sdpl_line_check(sdpl_line* o) {
+  if (!o) return SDPL_ERR_ARG;
+  if (!o->err.p) return SDPL_OK;
+  SDPL_CUDA(cudaSetDevice(o->device));
+  return line_check_err(o);
+}
 int sdpl_line_set_profiling(sdpl_line* o, int on) { if (!o) return SDPL_ERR_ARG; o->timer.enabled = on != 0; return SDPL_OK; }
 int sdpl_line_stage_times(sdpl_line* o, float* ms, const char** names, int* launches, int cap) {
   if (!o) return 0;

@@ -1021,6 +1021,12 @@ int sdpl_orb_max_keypoints(const sdpl_orb* o) {
   return t;
 }
 int sdpl_orb_last_launches(const sdpl_orb* o) { return o ? o->launches : 0; }
+int sdpl_orb_check(sdpl_orb* o) {
+  if (!o) return SDPL_ERR_ARG;
+  if (!o->err.p) return SDPL_OK;
+  SDPL_CUDA(cudaSetDevice(o->device));
+  return orb_check_err(o);
+}
 int sdpl_orb_set_profiling(sdpl_orb* o, int on) { if (!o) return SDPL_ERR_ARG; o->timer.enabled = on != 0; return SDPL_OK; }
 int sdpl_orb_stage_times(sdpl_orb* o, float* ms, const char** names, int* launches, int cap) {
   if (!o) return 0;

@@ -94,6 +94,13 @@ def load_library(path=None):
     L.sdpl_match_ratio_batch_dev.argtypes = [vp, vp, vp, vp, i, i, f, i, vp, vp, i]
     L.sdpl_matcher_last_launches.argtypes = [vp]
     L.sdpl_matcher_set_stream.argtypes = [vp, vp]
+    L.sdpl_orb_check.argtypes = [vp]; L.sdpl_line_check.argtypes = [vp]
+    L.sdpl_frontend_create.argtypes = [C.POINTER(vp), i, f, i, i, i, i, i, f, i, f, f, i, i]
+    L.sdpl_frontend_destroy.argtypes = [vp]; L.sdpl_frontend_destroy.restype = None
+    L.sdpl_frontend_capacities.argtypes = [vp, ip, ip]
+    L.sdpl_frontend_reset.argtypes = [vp]
+    L.sdpl_frontend_process.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp, vp, vp, vp, vp]
+    L.sdpl_frontend_last_launches.argtypes = [vp]
     if path is None:
         _lib = L
     return L
@@ -416,6 +423,60 @@ class BinaryDescriptorMatcher(_Profiled):
 
     def last_launches(self):
         return self._L.sdpl_matcher_last_launches(self._h)
+
+
+FS_DTYPE = np.dtype([("n_kp", "<i4"), ("n_lines", "<i4"), ("n_pt_matches", "<i4"), ("n_ln_matches", "<i4")])
+
+
+class FrontEnd:
+    """The per-frame front-end in one call (sdpl_frontend_*): what Frame::Frame does with its two extractors
+    (src/Frame.cc:314,328) plus frame-to-frame Hamming association of ORB and LBD descriptors.  process(images) takes a
+    (B, H, W) uint8 host array of consecutive frames and returns padded host arrays plus per-frame counts."""
+
+    def __init__(self, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, lsd_nfeatures=0, lsd_refine=2,
+                 lsd_scale=0.8, lsd_levels=2, lsd_pyr_scale=2.0, ratio=0.8, max_dist=64, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        _check(self._L.sdpl_frontend_create(C.byref(self._h), nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, lsd_nfeatures,
+                                            lsd_refine, lsd_scale, lsd_levels, lsd_pyr_scale, ratio, max_dist, device))
+        a, b = C.c_int(), C.c_int()
+        _check(self._L.sdpl_frontend_capacities(self._h, C.byref(a), C.byref(b)))
+        self.kp_capacity, self.kl_capacity = a.value, b.value
+        self._bufs = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.sdpl_frontend_destroy(h)
+            self._h = None
+
+    def reset(self):
+        _check(self._L.sdpl_frontend_reset(self._h))
+
+    def _outputs(self, B):
+        if self._bufs is None or self._bufs[0].shape[0] < B:
+            KC, LC = self.kp_capacity, self.kl_capacity
+            self._bufs = (np.empty((B, KC), KP_DTYPE), np.empty((B, KC, 32), np.uint8), np.empty((B, LC), KL_DTYPE),
+                          np.empty((B, LC, 32), np.uint8), np.empty((B, KC), DM_DTYPE), np.empty((B, LC), DM_DTYPE),
+                          np.empty(B, FS_DTYPE))
+        return self._bufs
+
+    def process(self, images):
+        """-> dict(kps, desc, kls, ldesc, pt_matches, ln_matches: padded (B, cap, ...) arrays; stats: per-frame counts).
+        The arrays are reused by the next call."""
+        imgs = np.asarray(images)
+        if imgs.dtype != np.uint8 or imgs.ndim != 3:
+            raise TypeError("images must be a (B, H, W) uint8 array")
+        if not imgs.flags["C_CONTIGUOUS"]:
+            imgs = np.ascontiguousarray(imgs)
+        B, H, W = imgs.shape
+        kps, desc, kls, ldesc, pm, lm, st = self._outputs(B)
+        _check(self._L.sdpl_frontend_process(self._h, _p(imgs), B, W, H, W, W * H, _p(kps), _p(desc), _p(kls), _p(ldesc), _p(pm), _p(lm),
+                                             _p(st)))
+        return dict(kps=kps, desc=desc, kls=kls, ldesc=ldesc, pt_matches=pm, ln_matches=lm, stats=st[:B])
+
+    def last_launches(self):
+        return self._L.sdpl_frontend_last_launches(self._h)
 
 
 def device_count():

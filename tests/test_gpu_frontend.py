@@ -1,0 +1,77 @@
+"""GPU: the one-call front-end (sdpl_frontend_process) equals the three separate extractors / the oracle, keeps the
+previous frame across calls, and the N-rank sharding of a frame batch gives byte-identical per-frame results."""
+import numpy as np
+import pytest
+
+from sdpl_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _seq(n, h=240, w=416):
+    out = []
+    for s in range((n + 1) // 2):
+        out += [synth.frame(500 + s, h, w), synth.partner(500 + s, h, w)]
+    return np.stack(out[:n])
+
+
+def test_frontend_matches_separate_calls_and_oracle(frontend, oracle):
+    imgs = _seq(6)
+    fe = frontend.FrontEnd(500, 1.2, 8, 20, 7, 0, 2, 0.8, 2, 2.0, 0.8, 64)
+    r = fe.process(imgs)
+    st = r["stats"]
+    orb = frontend.ORBextractor(500, 1.2, 8, 20, 7)
+    line = frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 0)
+    prev_d = prev_ld = None
+    for f in range(len(imgs)):
+        k, d = orb(imgs[f]); kl, dl = line(imgs[f])
+        assert st["n_kp"][f] == len(k) and st["n_lines"][f] == len(kl)
+        assert r["kps"][f, :len(k)].tobytes() == k.tobytes() and (r["desc"][f, :len(k)] == d).all()
+        assert r["kls"][f, :len(kl)].tobytes() == kl.tobytes() and (r["ldesc"][f, :len(kl)] == dl).all()
+        if f == 0:
+            assert st["n_pt_matches"][0] == 0 and st["n_ln_matches"][0] == 0
+            assert (r["pt_matches"][0, :len(k)]["train"] == -1).all()
+        else:
+            ref, nacc = oracle.match_ratio(d, prev_d, 0.8, 64)
+            assert st["n_pt_matches"][f] == nacc
+            np.testing.assert_array_equal(r["pt_matches"][f, :len(k)]["train"], ref["train"])
+            np.testing.assert_array_equal(r["pt_matches"][f, :len(k)]["distance"], ref["distance"])
+            if len(dl) and len(prev_ld):
+                refl, naccl = oracle.match_ratio(dl, prev_ld, 0.8, 64)
+                assert st["n_ln_matches"][f] == naccl
+                np.testing.assert_array_equal(r["ln_matches"][f, :len(kl)]["train"], refl["train"])
+        prev_d, prev_ld = d, dl
+    # odd frames are shifted copies of the even ones: most keypoints find their partner
+    assert st["n_pt_matches"][1] > 0.4 * st["n_kp"][1]
+
+
+def test_frontend_keeps_previous_frame_across_calls(frontend):
+    imgs = _seq(4)
+    a = frontend.FrontEnd(500, 1.2, 8, 20, 7)
+    whole = a.process(imgs)
+    w_stats = whole["stats"].copy(); w_pm = whole["pt_matches"].copy()
+    b = frontend.FrontEnd(500, 1.2, 8, 20, 7)
+    s1 = b.process(imgs[:2])["stats"].copy()
+    r2 = b.process(imgs[2:])
+    np.testing.assert_array_equal(np.concatenate([s1, r2["stats"]]), w_stats)
+    n = w_stats["n_kp"][2]
+    np.testing.assert_array_equal(r2["pt_matches"][0, :n]["train"], w_pm[2, :n]["train"])
+    b.reset()
+    assert b.process(imgs[2:])["stats"]["n_pt_matches"][0] == 0
+
+
+def test_sharded_batch_equals_single_rank(frontend):
+    """BASELINE configs[3] in miniature: contiguous shards of a frame batch processed by independent handles give the same
+    per-frame keypoints / keylines as the un-sharded batch (frames are independent units)."""
+    imgs = _seq(8)
+    orb = frontend.ORBextractor(500, 1.2, 8, 20, 7); line = frontend.Lineextractor()
+    full_o = orb.extract_batch(imgs); full_l = line.extract_batch(imgs)
+    for world in (2, 4):
+        per = len(imgs) // world
+        for rank in range(world):
+            o2 = frontend.ORBextractor(500, 1.2, 8, 20, 7); l2 = frontend.Lineextractor()
+            so = o2.extract_batch(imgs[rank * per:(rank + 1) * per]); sl = l2.extract_batch(imgs[rank * per:(rank + 1) * per])
+            for j in range(per):
+                f = rank * per + j
+                assert so[j][0].tobytes() == full_o[f][0].tobytes() and so[j][1].tobytes() == full_o[f][1].tobytes()
+                assert sl[j][0].tobytes() == full_l[f][0].tobytes() and sl[j][1].tobytes() == full_l[f][1].tobytes()
