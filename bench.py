@@ -212,7 +212,7 @@ def _config(stages, frames_per_gpu):
 def run_gpu(args, stages):
     import torch
     import torch.distributed as dist
-    from sdpl_slam_b200 import frontend as fe, synth
+    from sdpl_slam_b200 import frontend as fe, shard, synth
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -257,7 +257,7 @@ def run_gpu(args, stages):
         d_lbest = torch.empty((F, LINE_CAP, 16), dtype=u8, device=dev); d_lsecond = torch.empty((F, LINE_CAP, 16), dtype=u8, device=dev)
         d_lnacc = torch.zeros(F, dtype=i32, device=dev)
     stats = torch.zeros((F, 4), dtype=i32, device=dev)
-    gathered = torch.zeros((world * F, 4), dtype=i32, device=dev) if world > 1 else None
+    gathered = [None]
 
     s_orb, s_line, s_match, s_lmatch = (torch.cuda.Stream(device=dev) for _ in range(4))
     orb.set_stream(s_orb.cuda_stream); mat.set_stream(s_match.cuda_stream)
@@ -303,7 +303,7 @@ def run_gpu(args, stages):
         if use_line:
             stats[:, 1].copy_(d_nkl[1:]); stats[:, 3].copy_(d_lnacc)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, stats)
+            gathered[0] = shard.gather_frame_stats(stats)      # NCCL all-gather of 16 B per frame: the only collective of the path
 
     def barrier():
         torch.cuda.synchronize()

@@ -116,8 +116,9 @@ int sdpl_line_debug_pending(sdpl_line* h, int frame, int octave, double* out, in
  * then {waves, re-runs, dead seeds, seeds} */
 int sdpl_line_debug_grow_profile(sdpl_line* h, int frame, int octave, long long* out8);
 int sdpl_line_last_launches(const sdpl_line* h);
-/* test / tuning knob, LSD region-growing schedule: 0 = speculative lock-step waves of 32 seeds (default), 1 = strictly one seed
- * at a time, 2 = speculative with dynamic lane scheduling and a re-order buffer (experimental); all give identical results */
+/* test / tuning knob, LSD region-growing schedule (bits 0-1; bits 8.. an optional size override): 0 = speculative waves of
+ * 32*NW seeds, one CTA of NW warps per (frame, octave) (default, NW = 4), 1 = strictly one seed at a time, 2 = speculative with
+ * dynamic lane scheduling and a re-order buffer (experimental), 3 = single-warp waves of 32 seeds; all give identical results */
 int sdpl_line_set_serial(sdpl_line* h, int on);
 
 /* ------------------------------------------------------------------------------------------------

@@ -312,7 +312,16 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineDev D) {
   lsd::Task T;
   make_task(D, f, o, T);
   if (D.serial_mode == 2) lsd::grow_task_rob(T, S);               // 2: dynamic lane scheduling + re-order buffer (experimental)
-  else lsd::grow_task(T, D.serial_mode == 1, S.sel);               // 0: 32-seed lock-step waves (default), 1: one seed at a time
+  else lsd::grow_task(T, D.serial_mode == 1, S.sel);               // 3: 32-seed lock-step waves, 1: one seed at a time
+}
+
+// default schedule: waves of 32*NW seeds, one CTA of NW warps per task
+__global__ void __launch_bounds__(32 * lsd::kMaxGrowWarps) k_lsd_grow_block(LineDev D) {
+  __shared__ lsd::BlockShared S;
+  const int o = blockIdx.x / D.B, f = blockIdx.x % D.B;
+  lsd::Task T;
+  make_task(D, f, o, T);
+  lsd::grow_task_block(T, S);
 }
 
 constexpr int kLgamN = 32768;
@@ -631,7 +640,7 @@ struct sdpl_line {
   LineDev D;
   DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob;
-  int rob_w = 2048, rob_w_run = 2048;
+  int rob_w = 2048, rob_w_run = 2048, grow_warps = 8;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
   int last_B = 0, launches = 0, serial_mode = 0;
@@ -853,7 +862,8 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "lsd_sort");
-  k_lsd_grow<<<nl * B, 32, 0, st>>>(D);
+  if (o->serial_mode == 0) k_lsd_grow_block<<<nl * B, 32 * o->grow_warps, 0, st>>>(D);
+  else k_lsd_grow<<<nl * B, 32, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_grow");
   k_lsd_nfa<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
@@ -981,16 +991,18 @@ int sdpl_line_stage_times(sdpl_line* o, float* ms, const char** names, int* laun
   cudaSetDevice(o->device);
   return o->timer.read(ms, names, launches, cap);
 }
-// test / tuning knob: region-growing schedule. 0 = speculative lock-step waves of 32 seeds (default), 1 = strictly one seed at a
-// time (no speculation), 2 = speculative with dynamic lane scheduling and a re-order buffer (experimental: measured slower than
-// the waves on B200).  All three give identical results.
+// test / tuning knob: region-growing schedule (bits 0-1). 0 = speculative waves of 32*NW seeds, one CTA of NW warps per task
+// (default, NW = 4; bits 8.. override NW), 1 = strictly one seed at a time (no speculation), 2 = speculative with dynamic lane
+// scheduling and a re-order buffer (experimental: measured slower on B200; bits 8.. override the buffer size),
+// 3 = single-warp waves of 32 seeds.  All give identical results.
 int sdpl_line_set_serial(sdpl_line* o, int on) {
   if (!o || on < 0) return SDPL_ERR_ARG;
   // bits 0-1: schedule; bits 8..: re-order buffer size override (power of two, <= allocated), for tuning
   const int w = on >> 8;
-  if ((on & 3) > 2 || (w && (w < 32 || w > 2048 || (w & (w - 1))))) return SDPL_ERR_ARG;
+  if (w && (w < 1 || w > 2048 || (w & (w - 1)))) return SDPL_ERR_ARG;
   o->serial_mode = on & 3;
-  if (w) o->rob_w_run = w;
+  if (w && o->serial_mode == 2) o->rob_w_run = std::max(w, 32);
+  if (w && o->serial_mode == 0) o->grow_warps = std::min(w, lsd::kMaxGrowWarps);
   return SDPL_OK;
 }
 

@@ -92,7 +92,8 @@ __device__ __forceinline__ uint32_t ld_state(const uint32_t* p) { return *(const
 //                           (met a pixel stamped by an earlier seed of this wave, or ran out of list space).
 // ------------------------------------------------------------------------------------------------
 template <bool SPEC>
-__device__ bool region_grow(const Task& T, int seed, int* reg, int cap, int& n_out, double& reg_angle, double prec, uint32_t stamp) {
+__device__ bool region_grow(const Task& T, int seed, int* reg, int cap, int& n_out, double& reg_angle, double prec, uint32_t stamp,
+                            int& bx0, int& by0, int& bx1, int& by1) {
   const int w = T.w, h = T.h;
   int n = 1;
   reg[0] = seed;
@@ -138,6 +139,7 @@ __device__ bool region_grow(const Task& T, int seed, int* reg, int cap, int& n_o
         T.state[q] = kUsed;
       }
       reg[n++] = q;
+      bx0 = min(bx0, px - 1 + k % 3); bx1 = max(bx1, px - 1 + k % 3); by0 = min(by0, py - 1 + k / 3); by1 = max(by1, py - 1 + k / 3);
       sumdx = __fadd_rn(sumdx, pa[k].c);
       sumdy = __fadd_rn(sumdy, pa[k].s);
       ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
@@ -229,6 +231,7 @@ struct SeedResult {
   int nf;          // pixels finally marked: reg[foff, foff+nf)
   int foff;
   int has_rect;
+  int bx0, by0, bx1, by1;   // bounding box of every pixel the seed touched (speculative runs and the re-run)
   Rect rec;
 };
 
@@ -237,9 +240,10 @@ struct SeedResult {
 template <bool SPEC>
 __device__ void process_seed(const Task& T, int seed, int* reg, int cap, uint32_t stamp, SeedResult& R) {
   R.ok = 1; R.n2_orig = 0; R.has_rect = 0; R.foff = 0; R.nf = 0;
+  R.bx0 = R.bx1 = seed % T.w; R.by0 = R.by1 = seed / T.w;
   double reg_angle = 0;
   int n1 = 0;
-  if (!region_grow<SPEC>(T, seed, reg, cap, n1, reg_angle, T.prec, stamp)) { R.ok = 0; R.n1 = n1; return; }
+  if (!region_grow<SPEC>(T, seed, reg, cap, n1, reg_angle, T.prec, stamp, R.bx0, R.by0, R.bx1, R.by1)) { R.ok = 0; R.n1 = n1; return; }
   R.n1 = n1; R.nf = n1;
   if (n1 < T.min_reg) return;
   region2rect(T, reg, n1, reg_angle, T.prec, T.p, R.rec);
@@ -267,7 +271,7 @@ __device__ void process_seed(const Task& T, int seed, int* reg, int cap, uint32_
   const int cap2 = SPEC ? cap - n1 : cap;
   int n2 = 0;
   if (SPEC && cap2 < 1) { R.ok = 0; return; }
-  if (!region_grow<SPEC>(T, seed, reg2, cap2, n2, reg_angle, tau, stamp | 1u)) { R.ok = 0; R.n2_orig = n2; return; }
+  if (!region_grow<SPEC>(T, seed, reg2, cap2, n2, reg_angle, tau, stamp | 1u, R.bx0, R.by0, R.bx1, R.by1)) { R.ok = 0; R.n2_orig = n2; return; }
   R.n2_orig = SPEC ? n2 : 0;
   R.foff = SPEC ? n1 : 0;
   R.nf = n2;
@@ -280,6 +284,44 @@ __device__ void process_seed(const Task& T, int seed, int* reg, int cap, uint32_
     if (!keep) return;
   }
   R.has_rect = 1;
+}
+
+
+// Does every pixel of list[0,n) still carry the stamp key `key` (i.e. is it still exclusively mine and uncommitted)?
+// Four independent list/state loads in flight per step.
+__device__ __forceinline__ bool owns_all(const Task& T, const int* list, int n, uint32_t key) {
+  int ok = 1, i = 0;
+  for (; i + 4 <= n && ok; i += 4) {
+    const int q0 = list[i], q1 = list[i + 1], q2 = list[i + 2], q3 = list[i + 3];
+    const uint32_t s0 = ld_state(T.state + q0), s1 = ld_state(T.state + q1), s2 = ld_state(T.state + q2), s3 = ld_state(T.state + q3);
+    ok = ((s0 >> 1) == key) & ((s1 >> 1) == key) & ((s2 >> 1) == key) & ((s3 >> 1) == key);
+  }
+  for (; i < n && ok; i++) ok = (ld_state(T.state + list[i]) >> 1) == key;
+  return ok != 0;
+}
+__device__ __forceinline__ void mark_used(const Task& T, const int* list, int n) {
+  int i = 0;
+  for (; i + 4 <= n; i += 4) {
+    const int q0 = list[i], q1 = list[i + 1], q2 = list[i + 2], q3 = list[i + 3];
+    T.state[q0] = kUsed; T.state[q1] = kUsed; T.state[q2] = kUsed; T.state[q3] = kUsed;
+  }
+  for (; i < n; i++) T.state[list[i]] = kUsed;
+}
+
+// Warp-cooperative version of mark_used: lanes with `active` own a list; lists longer than 32 entries are marked by the
+// whole warp (32 list loads in flight instead of one dependent chain), short ones by their owner.
+__device__ __forceinline__ void mark_used_coop(const Task& T, bool active, const int* list, int n) {
+  const int lane = threadIdx.x & 31;
+  uint32_t longm = __ballot_sync(0xffffffffu, active && n > 32);
+  while (longm) {
+    const int src = __ffs(longm) - 1;
+    longm &= longm - 1;
+    const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(size_t)list, src);
+    const int m = __shfl_sync(0xffffffffu, n, src);
+    const int* l = (const int*)(size_t)p;
+    for (int i = lane; i < m; i += 32) T.state[l[i]] = kUsed;
+  }
+  if (active && n <= 32) mark_used(T, list, n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,12 +380,7 @@ __device__ void grow_task(const Task& T, int serial_mode, int* sel /* 32 ints of
         if (!dead && R.ok && !serial_mode) {
           // E = first region + re-grown region slots: every pixel must still carry my stamp (either phase) => no earlier
           // seed of the wave touched it and it is free in the committed map
-          good = true;
-          const int nE = R.n1 + R.n2_orig;
-          const uint32_t key = stamp >> 1;
-          for (int i = 0; i < nE; i++) {
-            if ((ld_state(T.state + my_reg[i]) >> 1) != key) { good = false; break; }
-          }
+          good = owns_all(T, my_reg, R.n1 + R.n2_orig, stamp >> 1);
         }
       }
       const uint32_t deadm = __ballot_sync(0xffffffffu, dead), goodm = __ballot_sync(0xffffffffu, good);
@@ -389,6 +426,155 @@ __device__ void grow_task(const Task& T, int serial_mode, int* sel /* 32 ints of
   if (lane == 0 && T.prof) {
     T.prof[0] = t_sel; T.prof[1] = t_spec; T.prof[2] = t_commit - t_redo; T.prof[3] = t_redo; T.prof[4] = wave; T.prof[5] = n_redo;
     T.prof[6] = n_dead; T.prof[7] = n_seed;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-level waves: the same speculate / validate / commit scheme with NW warps per task, i.e. waves of K = 32*NW seeds.
+// Thread t of the CTA owns the t-th seed of the wave (stamp priority K-1-t).  Fewer waves per task, and a long region only
+// keeps its own warp busy while the other warps of the CTA idle at the barrier without consuming issue slots.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxGrowWarps = 8;
+struct BlockShared {
+  int sel[32 * kMaxGrowWarps];
+  uint32_t deadm[kMaxGrowWarps], goodm[kMaxGrowWarps], rectm[kMaxGrowWarps], pend[kMaxGrowWarps];
+  int nsel, cursor, npend, has;
+  int rb[4];                    // bounding box written by the last re-run
+};
+
+__device__ void grow_task_block(const Task& T, BlockShared& S) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NW = blockDim.x >> 5, K = blockDim.x;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int cap = (32 * T.lane_cap) / K;
+  int* my_reg = T.reg_spec + (size_t)tid * cap;
+  if (tid == 0) { S.cursor = 0; S.npend = 0; }
+  uint32_t wave = 0;
+  long long t_sel = 0, t_spec = 0, t_commit = 0, t_redo = 0, n_redo = 0, n_dead = 0, n_seed = 0, t_eval = 0;
+  __syncthreads();
+  while (true) {
+    long long c0 = clock64();
+    // ---- warp 0 selects the next (up to) K free seeds in order ----
+    if (warp == 0) {
+      int cursor = S.cursor, nsel = 0;
+      while (nsel < K && cursor < T.ndef) {
+        const int idx = cursor + lane;
+        const int p = idx < T.ndef ? (int)T.order[idx] : -1;
+        const bool fr = p >= 0 && !(ld_state(T.state + (p >= 0 ? p : 0)) & kUsed);
+        const uint32_t m = __ballot_sync(0xffffffffu, fr);
+        const int c = __popc(m);
+        const int take = min(c, K - nsel);
+        const int rank = __popc(m & lt);
+        if (fr && rank < take) S.sel[nsel + rank] = p;
+        if (c > take) cursor += (int)__fns(m, 0, take) + 1;
+        else cursor += 32;
+        nsel += take;
+      }
+      if (lane == 0) { S.cursor = cursor; S.nsel = nsel; }
+    }
+    __syncthreads();
+    const int nsel = S.nsel;
+    if (nsel == 0) break;
+    wave++;
+    n_seed += nsel;
+    const int my_seed = tid < nsel ? S.sel[tid] : -1;
+    long long c1 = clock64(); t_sel += c1 - c0;
+    SeedResult R;
+    R.ok = 0; R.n1 = 0; R.n2_orig = 0; R.nf = 0; R.foff = 0; R.has_rect = 0;
+    const uint32_t stamp = (wave << 11) | ((uint32_t)(K - 1 - tid) << 1);   // bit0 = phase, 10 bits of seed priority
+    if (tid < nsel) process_seed<true>(T, my_seed, my_reg, cap, stamp, R);
+    // pending set of the wave
+    if (lane == 0) {
+      const int first = warp * 32;
+      S.pend[warp] = nsel >= first + 32 ? 0xffffffffu : (nsel > first ? ((1u << (nsel - first)) - 1u) : 0u);
+    }
+    __syncthreads();
+    long long c2 = clock64(); t_spec += c2 - c1;
+    bool retired = false;
+    int verdict = 0;        // cached verdict: 0 unknown, 1 good (invalidated only by a re-run that wrote near me), 2 dead, 3 must re-run
+    while (true) {
+      long long ce = clock64();
+      const bool mine = ((S.pend[warp] >> lane) & 1u) && !retired;
+      bool dead = false, good = false;
+      if (mine) {
+        if (verdict == 0) {
+          dead = (ld_state(T.state + my_seed) & kUsed) != 0;
+          if (!dead && R.ok) good = owns_all(T, my_reg, R.n1 + R.n2_orig, stamp >> 1);
+          verdict = dead ? 2 : (good ? 1 : 3);
+        } else if (verdict == 3) {
+          // lost a pixel (or never finished): that is permanent; only "my seed was taken meanwhile" can still change
+          dead = (ld_state(T.state + my_seed) & kUsed) != 0;
+          if (dead) verdict = 2;
+        } else {
+          dead = verdict == 2; good = verdict == 1;
+        }
+      }
+      const uint32_t dm = __ballot_sync(0xffffffffu, dead), gm = __ballot_sync(0xffffffffu, good);
+      if (lane == 0) { S.deadm[warp] = dm; S.goodm[warp] = gm; }
+      __syncthreads();
+      t_eval += clock64() - ce;
+      // first pending seed of the wave that is neither dead nor provably good
+      int kstar = K, any = 0;
+      for (int v = 0; v < NW; v++) {
+        const uint32_t pm = S.pend[v];
+        any |= pm != 0;
+        const uint32_t bad = pm & ~S.deadm[v] & ~S.goodm[v];
+        if (bad && kstar == K) kstar = v * 32 + __ffs(bad) - 1;
+      }
+      if (!any) break;
+      const bool below = tid < kstar;
+      const bool do_commit = mine && good && below;
+      const bool do_drop = mine && dead && below;
+      mark_used_coop(T, do_commit, my_reg + R.foff, R.nf);
+      if (do_commit || do_drop) retired = true;
+      n_dead += do_drop ? 1 : 0;
+      const uint32_t rm = __ballot_sync(0xffffffffu, do_commit && R.has_rect);
+      if (lane == 0) S.rectm[warp] = rm;
+      __syncthreads();
+      int before = S.npend, total = 0;
+      for (int v = 0; v < NW; v++) { const int c = __popc(S.rectm[v]); if (v < warp) before += c; total += c; }
+      if (do_commit && R.has_rect) append_rect(T, before + __popc(rm & lt), R.rec, (int)((wave << 11) | (tid << 1) | 0), my_seed, R.nf);
+      __syncthreads();
+      if (tid == 0) { S.npend += total; S.has = 0; }
+      __syncthreads();
+      if (kstar < K) {
+        long long c3 = clock64();
+        // the commits just made (seeds before kstar) may have taken kstar's seed: then the sequential algorithm skips it
+        if (tid == kstar) {
+          if (!(ld_state(T.state + my_seed) & kUsed)) {
+            SeedResult Q;
+            process_seed<false>(T, my_seed, T.reg_serial, T.npx, 0u, Q);
+            if (Q.has_rect) { append_rect(T, S.npend, Q.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, Q.nf); S.has = 1; }
+            S.rb[0] = Q.bx0; S.rb[1] = Q.by0; S.rb[2] = Q.bx1; S.rb[3] = Q.by1;
+          } else {
+            S.rb[0] = 1; S.rb[2] = 0;      // nothing written
+          }
+          retired = true;
+        }
+        n_redo++;
+        __syncthreads();
+        if (tid == 0) S.npend += S.has;
+        // the re-run wrote `used` inside its bounding box only: cached "good" verdicts elsewhere stay valid
+        if (verdict == 1 && !(S.rb[0] > R.bx1 || S.rb[2] < R.bx0 || S.rb[1] > R.by1 || S.rb[3] < R.by0)) verdict = 0;
+        t_redo += clock64() - c3;
+      }
+      // everything up to and including kstar is settled
+      if (lane == 0) {
+        const int first = warp * 32;
+        uint32_t keep = 0xffffffffu;
+        if (kstar >= first + 32) keep = 0u;
+        else if (kstar >= first) keep = (kstar - first) >= 31 ? 0u : ~((2u << (kstar - first)) - 1u);
+        S.pend[warp] &= keep;
+      }
+      __syncthreads();
+      if (kstar >= K) break;
+    }
+    t_commit += clock64() - c2;
+  }
+  if (tid == 0) *T.npend = min(S.npend, T.pend_cap);
+  if (tid == 0 && T.prof) {
+    T.prof[0] = t_sel; T.prof[1] = t_spec; T.prof[2] = t_commit - t_redo; T.prof[3] = t_redo; T.prof[4] = wave; T.prof[5] = n_redo;
+    T.prof[6] = t_eval; T.prof[7] = n_seed;
   }
 }
 

@@ -345,7 +345,8 @@ class Lineextractor(_Profiled):
         return dict(zip(("select", "speculate", "commit", "rerun", "waves", "reruns", "dead", "seeds"), out.tolist()))
 
     def set_serial(self, on=True):
-        """region-growing schedule: 0/False speculative lock-step waves (default), 1/True one seed at a time, 2 re-order buffer"""
+        """region-growing schedule: 0/False block-level speculative waves (default), 1/True one seed at a time, 2 re-order buffer,
+        3 single-warp waves; `on | (n << 8)` overrides the number of warps per task (mode 0) or the buffer size (mode 2)"""
         _check(self._L.sdpl_line_set_serial(self._h, int(on)))
 
     def lsd_segments(self, octave, frame=0, capacity=65536):

@@ -1,0 +1,51 @@
+"""Frame-batch sharding across the GPUs of one box (BASELINE.json configs[3]).
+
+Frames are independent units, so the data path has no collective: rank g of G processes the contiguous block
+[g*B/G, (g+1)*B/G) of a B-frame batch with its own handles, streams and device arenas.  The only exchange is one
+all-gather of the per-frame statistics {n_kp, n_lines, n_pt_matches, n_ln_matches} (16 B per frame) at the end of a
+step: NCCL over NVLink on the GPU box, gloo in the CPU tests.  Frame-to-frame matching across a shard edge uses the
+neighbour rank's last frame, which the owner of the edge simply recomputes (one extra frame per rank, no 64 KB send)."""
+import numpy as np
+
+
+def shard_range(n_frames: int, rank: int, world: int):
+    """Contiguous block of rank `rank`: the first n_frames % world ranks get one frame more."""
+    if world < 1 or not (0 <= rank < world) or n_frames < 0:
+        raise ValueError("bad shard arguments")
+    base, extra = divmod(n_frames, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_with_halo(n_frames: int, rank: int, world: int):
+    """(first frame to process, first frame owned, end): ranks > 0 also process the frame before their block so that the
+    first owned frame can be matched against its predecessor without any transfer."""
+    s, e = shard_range(n_frames, rank, world)
+    return (max(s - 1, 0) if s < e else s), s, e
+
+
+def gather_frame_stats(stats, group=None):
+    """All-gather of per-rank (n_local, 4) int32 statistics into the (n_total, 4) table of the whole batch, in frame order.
+    `stats` is a torch tensor on the device the process group communicates on (CUDA for NCCL, CPU for gloo).  Ragged shards
+    are padded to the longest shard for the collective."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return stats
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([stats.shape[0]], dtype=torch.int64, device=stats.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts) if counts else 0
+    padded = torch.zeros((m, stats.shape[1]), dtype=stats.dtype, device=stats.device)
+    padded[:stats.shape[0]] = stats
+    out = torch.zeros((world * m, stats.shape[1]), dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * m:r * m + counts[r]] for r in range(world)], 0)
+
+
+def frame_checksum(img: np.ndarray) -> np.ndarray:
+    """Cheap deterministic 4-int summary of a frame; stands in for the GPU statistics in the CPU (gloo) tests."""
+    a = img.astype(np.int64)
+    return np.array([a.sum() % 65521, (a[::7, ::5] * 3).sum() % 65521, int(a.max()), int((a > 128).sum() % 65521)], np.int32)

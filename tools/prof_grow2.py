@@ -8,4 +8,4 @@ for mode in [int(x) for x in sys.argv[2:]]:
     g.extract_batch(imgs); r = g.extract_batch(imgs)
     st = dict((n, ms) for n, ms, _ in g.stage_times())
     p = g.grow_profile(0, 0)
-    print("F", F, "mode", mode & 3, "W", mode >> 8, "grow ms", round(st["lsd_grow"], 1), {k: (round(v / 1.9e3) if k in ("select", "speculate", "commit", "rerun") else v) for k, v in p.items()})
+    print("F", F, "mode", mode & 3, "W", mode >> 8, "lines", sum(len(k) for k, d in r), "grow ms", round(st["lsd_grow"], 1), {k: (round(v / 1.9e3) if k in ("select", "speculate", "commit", "rerun") else v) for k, v in p.items()})
