@@ -640,7 +640,7 @@ struct sdpl_line {
   LineDev D;
   DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob;
-  int rob_w = 2048, rob_w_run = 2048, grow_warps = 8;
+  int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
   int last_B = 0, launches = 0, serial_mode = 0;
@@ -862,7 +862,12 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "lsd_sort");
-  if (o->serial_mode == 0) k_lsd_grow_block<<<nl * B, 32 * o->grow_warps, 0, st>>>(D);
+  if (o->serial_mode == 0) {
+    // warps per task: 8 (256-seed waves, shortest latency) while every task gets an SM to itself, 4 (two CTAs per SM,
+    // measured +24 % throughput at 512 frames) for big batches; sdpl_line_set_serial can pin it
+    const int nw = o->grow_warps > 0 ? o->grow_warps : (nl * B <= o->sm_count ? 8 : 4);
+    k_lsd_grow_block<<<nl * B, 32 * nw, 0, st>>>(D);
+  }
   else k_lsd_grow<<<nl * B, 32, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_grow");
@@ -945,6 +950,7 @@ int sdpl_line_create(sdpl_line** out, int nfeatures, int refine, float lsd_scale
     if (l > 0) o->sf[l] = o->sf[l - 1] * scale;
     o->isf[l] = 1.0f / o->sf[l];
   }
+  cudaDeviceGetAttribute(&o->sm_count, cudaDevAttrMultiProcessorCount, device);
   SDPL_CUDA(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
   o->stream = o->own_stream;
   *out = o;
