@@ -57,6 +57,7 @@ struct LineDev {
   long long* prof;
   const double* lgam; int lgam_n;
   lsd::Rect* rob_rect; lsd::RobEntry* rob; int rob_w, rob_w_run;
+  int* nbig; int* bigidx;
   double rho, prec, p, density_th, log_eps, scale;
   int refine, serial_mode;
   double min_length;
@@ -330,6 +331,8 @@ __global__ void k_lgam_table(double* t, int n) {
   if (i < n) t[i] = i > 0 ? lsd::log_gamma((double)i) : 0.0;
 }
 
+// small rectangles: one thread each; rectangles whose scan visits more than kBigRect pixels are queued for the warp kernel
+constexpr double kBigRect = 384.0;
 __global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
   const int task = blockIdx.y;
   const int f = task / D.nl, o = task % D.nl;
@@ -337,7 +340,25 @@ __global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
   if ((int)(blockIdx.x * blockDim.x) >= np) return;
   lsd::Task T;
   make_task(D, f, o, T);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) lsd::validate_pending(T, i);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+    if (D.refine >= 2 && lsd::rect_area_bound(T.pend[i].rec) > kBigRect) {
+      const int k = atomicAdd(D.nbig + task, 1);
+      D.bigidx[(size_t)task * D.pend_cap + k] = i;
+    } else {
+      lsd::validate_pending<false>(T, i);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_lsd_nfa_big(LineDev D) {
+  const int task = blockIdx.y;
+  const int f = task / D.nl, o = task % D.nl;
+  const int nb = D.nbig[task];
+  if ((int)blockIdx.x * 4 >= nb) return;
+  lsd::Task T;
+  make_task(D, f, o, T);
+  for (int k = blockIdx.x * 4 + (threadIdx.x >> 5); k < nb; k += gridDim.x * 4)
+    lsd::validate_pending<true>(T, D.bigidx[(size_t)task * D.pend_cap + k]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -639,7 +660,7 @@ struct sdpl_line {
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
   DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
-  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob;
+  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
@@ -789,6 +810,8 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->prof.reserve(sizeof(long long) * 8 * nl * B))) return rc;
   if ((rc = o->robrect.reserve(sizeof(lsd::Rect) * (size_t)o->rob_w * nl * B))) return rc;
   if ((rc = o->rob.reserve(sizeof(lsd::RobEntry) * (size_t)o->rob_w * nl * B))) return rc;
+  if ((rc = o->nbig.reserve(sizeof(int) * nl * B))) return rc;
+  if ((rc = o->bigidx.reserve(sizeof(int) * (size_t)D.pend_cap * nl * B))) return rc;
   if (!o->lgam.p) {
     if ((rc = o->lgam.reserve(sizeof(double) * kLgamN))) return rc;
     k_lgam_table<<<div_up(kLgamN, 256), 256, 0, o->stream>>>(o->lgam.as<double>(), kLgamN);
@@ -820,6 +843,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sdx = o->sdx.as<short>(); D.sdy = o->sdy.as<short>();
   D.err = o->err.as<int>(); D.prof = o->prof.as<long long>(); D.lgam = o->lgam.as<double>(); D.lgam_n = kLgamN;
   D.rob_rect = o->robrect.as<lsd::Rect>(); D.rob = o->rob.as<lsd::RobEntry>(); D.rob_w = o->rob_w;
+  D.nbig = o->nbig.as<int>(); D.bigidx = o->bigidx.as<int>();
   D.B = B;
   o->gw = w; o->gh = h; o->gB = B;
   return SDPL_OK;
@@ -871,7 +895,10 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   else k_lsd_grow<<<nl * B, 32, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_grow");
+  SDPL_CUDA(cudaMemsetAsync(D.nbig, 0, sizeof(int) * nl * B, st));
   k_lsd_nfa<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
+  SDPL_LAUNCH_CHECK();
+  k_lsd_nfa_big<<<dim3(64, nl * B), 128, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_nfa");
   k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());
@@ -962,7 +989,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
   for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->reg, &o->pend, &o->npend,
-                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob})
+                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
   o->timer.release();

@@ -962,7 +962,7 @@ __device__ __forceinline__ bool double_equal(double a, double b) {
 
 __device__ __forceinline__ double log_gamma_int(const Task& T, int i) { return i < T.lgam_n ? T.lgam[i] : log_gamma((double)i); }
 
-__device__ double nfa(const Task& T, int n, int k, double p) {
+__device__ __noinline__ double nfa(const Task& T, int n, int k, double p) {
   const double log_nt = T.log_nt;
   if (n == 0 || k == 0) return -log_nt;
   if (n == k) return -log_nt - (double)n * log10(p);
@@ -976,7 +976,22 @@ __device__ double nfa(const Task& T, int n, int k, double p) {
   }
   double bin_tail = term;
   const double tolerance = 0.1;
-  for (int i = k + 1; i <= n; ++i) {
+  int i0 = k + 1;
+  {
+    // while i <= (n+1)/2 the binomial ratio (n-i+1)/i is >= 1 and the reference loop only multiplies and accumulates: run
+    // that part with the (independent) divisions of four steps in flight; the products and the sum stay strictly in order
+    const int m = min(n, (n + 1) / 2);
+    for (; i0 + 3 <= m; i0 += 4) {
+      const double b0 = (double)(n - i0 + 1) / (double)i0, b1 = (double)(n - i0) / (double)(i0 + 1);
+      const double b2 = (double)(n - i0 - 1) / (double)(i0 + 2), b3 = (double)(n - i0 - 2) / (double)(i0 + 3);
+      const double m0 = b0 * p_term, m1 = b1 * p_term, m2 = b2 * p_term, m3 = b3 * p_term;
+      term *= m0; bin_tail += term;
+      term *= m1; bin_tail += term;
+      term *= m2; bin_tail += term;
+      term *= m3; bin_tail += term;
+    }
+  }
+  for (int i = i0; i <= n; ++i) {
     const double bin_term = (double)(n - i + 1) / (double)i;
     const double mult_term = bin_term * p_term;
     term *= mult_term;
@@ -989,9 +1004,12 @@ __device__ double nfa(const Task& T, int n, int k, double p) {
   return -log10(bin_tail) - log_nt;
 }
 
-// counts the pixels of the rotated rectangle and those aligned with it (one thread per rectangle: integer counting,
-// order-independent, so any traversal gives the oracle's totals)
-__device__ double rect_nfa(const Task& T, const Rect& rec) {
+// counts the pixels of the rotated rectangle and those aligned with it.  Integer counting is order-independent, so any
+// traversal gives the oracle's totals.  COOP = false: one thread per rectangle; COOP = true: one warp per rectangle (lanes
+// over rows for tall rectangles, over columns otherwise; the NFA itself is evaluated by lane 0 and broadcast).
+template <bool COOP>
+__device__ __noinline__ double rect_nfa(const Task& T, const Rect& rec) {
+  const int lane = COOP ? (threadIdx.x & 31) : 0;
   const double hw = rec.width / 2.0;
   const double dyhw = rec.dy * hw, dxhw = rec.dx * hw;
   double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
@@ -1010,29 +1028,37 @@ __device__ double rect_nfa(const Task& T, const Rect& rec) {
   const double srstep = (c2 != c3) ? (px[2] - px[3]) / (py[2] - py[3]) : 0.0;
   const int ya = max(c0, 0), yb = min(c2, T.h - 1);
   int total = 0, alg = 0;
-  for (int yy = ya; yy <= yb; ++yy) {
+  const bool by_rows = COOP && (yb - ya + 1) >= 24;
+  const int ystep = by_rows ? 32 : 1, xstep = (COOP && !by_rows) ? 32 : 1;
+  for (int yy = ya + (by_rows ? lane : 0); yy <= yb; yy += ystep) {
     const double left = (yy <= c1) ? px[0] + ((double)yy - py[0]) * flstep : px[1] + ((double)yy - py[1]) * slstep;
     const double right = (yy < c3) ? px[0] + ((double)yy - py[0]) * frstep : px[3] + ((double)yy - py[3]) * srstep;
     if (!(right >= 0) || !(left <= (double)(T.w - 1))) continue;
     const int xb = (int)ceil(left > 0 ? left : 0.0), xe = (int)(right < (double)(T.w - 1) ? right : (double)(T.w - 1));
     const PxA* row = T.px + (size_t)yy * T.w;
-    for (int x = xb; x <= xe; ++x) {
+    for (int x = xb + ((COOP && !by_rows) ? lane : 0); x <= xe; x += xstep) {
       ++total;
       if (aligned_angle(row[x].ang, rec.theta, rec.prec)) ++alg;
     }
   }
-  return nfa(T, total, alg, rec.p);
+  if (!COOP) return nfa(T, total, alg, rec.p);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { total += __shfl_xor_sync(0xffffffffu, total, o); alg += __shfl_xor_sync(0xffffffffu, alg, o); }
+  double v = 0;
+  if (lane == 0) v = nfa(T, total, alg, rec.p);
+  return __shfl_sync(0xffffffffu, v, 0);
 }
 
+template <bool COOP>
 __device__ double rect_improve(const Task& T, Rect& rec) {
   const double delta = 0.5, delta_2 = delta / 2.0;
   const double log_eps = T.log_eps;
-  double log_nfa = rect_nfa(T, rec);
+  double log_nfa = rect_nfa<COOP>(T, rec);
   if (log_nfa > log_eps) return log_nfa;
   Rect r = rec;
   for (int n = 0; n < 5; ++n) {
     r.p /= 2; r.prec = r.p * kPI;
-    const double v = rect_nfa(T, r);
+    const double v = rect_nfa<COOP>(T, r);
     if (v > log_nfa) { log_nfa = v; rec = r; }
   }
   if (log_nfa > log_eps) return log_nfa;
@@ -1040,7 +1066,7 @@ __device__ double rect_improve(const Task& T, Rect& rec) {
   for (int n = 0; n < 5; ++n) {
     if ((r.width - delta) >= 0.5) {
       r.width -= delta;
-      const double v = rect_nfa(T, r);
+      const double v = rect_nfa<COOP>(T, r);
       if (v > log_nfa) { rec = r; log_nfa = v; }
     }
   }
@@ -1050,7 +1076,7 @@ __device__ double rect_improve(const Task& T, Rect& rec) {
     if ((r.width - delta) >= 0.5) {
       r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
       r.width -= delta;
-      const double v = rect_nfa(T, r);
+      const double v = rect_nfa<COOP>(T, r);
       if (v > log_nfa) { rec = r; log_nfa = v; }
     }
   }
@@ -1060,7 +1086,7 @@ __device__ double rect_improve(const Task& T, Rect& rec) {
     if ((r.width - delta) >= 0.5) {
       r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
       r.width -= delta;
-      const double v = rect_nfa(T, r);
+      const double v = rect_nfa<COOP>(T, r);
       if (v > log_nfa) { rec = r; log_nfa = v; }
     }
   }
@@ -1069,22 +1095,26 @@ __device__ double rect_improve(const Task& T, Rect& rec) {
   for (int n = 0; n < 5; ++n) {
     if ((r.width - delta) >= 0.5) {
       r.p /= 2; r.prec = r.p * kPI;
-      const double v = rect_nfa(T, r);
+      const double v = rect_nfa<COOP>(T, r);
       if (v > log_nfa) { rec = r; log_nfa = v; }
     }
   }
   return log_nfa;
 }
 
-// one thread: validate pending rectangle i of task T and write its segment
+// upper bound of the number of pixels one scan of the rectangle visits (width only shrinks during rect_improve)
+__device__ __forceinline__ double rect_area_bound(const Rect& r) { return (dist(r.x1, r.y1, r.x2, r.y2) + 2.0) * (r.width + 2.0); }
+
+// validate pending rectangle i of task T and write its segment (COOP = false: by one thread; true: by one warp)
+template <bool COOP>
 __device__ void validate_pending(const Task& T, int i) {
   Rect rec = T.pend[i].rec;
   bool acc = true;
   if (T.refine >= 2) {
-    const double v = rect_improve(T, rec);
+    const double v = rect_improve<COOP>(T, rec);
     acc = v > T.log_eps;
   }
-  {
+  if (!COOP || (threadIdx.x & 31) == 0) {
     Pending& P = T.pend[i];
     P.accepted = acc ? 1 : 0;
     if (acc) {
