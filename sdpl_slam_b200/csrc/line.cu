@@ -316,8 +316,9 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineDev D) {
   else lsd::grow_task(T, D.serial_mode == 1, S.sel);               // 3: 32-seed lock-step waves, 1: one seed at a time
 }
 
-// default schedule: waves of 32*NW seeds, one CTA of NW warps per task
-__global__ void __launch_bounds__(32 * lsd::kMaxGrowWarps) k_lsd_grow_block(LineDev D) {
+// default schedule: waves of 32*NW seeds, one CTA of NW warps per task.  MINB = CTAs per SM the register budget is cut for.
+template <int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) k_lsd_grow_block(LineDev D) {
   __shared__ lsd::BlockShared S;
   const int o = blockIdx.x / D.B, f = blockIdx.x % D.B;
   lsd::Task T;
@@ -661,7 +662,7 @@ struct sdpl_line {
   LineDev D;
   DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx;
-  int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148;
+  int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
   int last_B = 0, launches = 0, serial_mode = 0;
@@ -887,10 +888,23 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   }
   o->timer.mark(st, "lsd_sort");
   if (o->serial_mode == 0) {
-    // warps per task: 8 (256-seed waves, shortest latency) while every task gets an SM to itself, 4 (two CTAs per SM,
-    // measured +24 % throughput at 512 frames) for big batches; sdpl_line_set_serial can pin it
-    const int nw = o->grow_warps > 0 ? o->grow_warps : (nl * B <= o->sm_count ? 8 : 4);
-    k_lsd_grow_block<<<nl * B, 32 * nw, 0, st>>>(D);
+    // warps per task / CTAs per SM: 8 warps and one CTA per SM (256-seed waves, shortest latency) while every task gets an
+    // SM to itself; 4 warps and 4 CTAs per SM (127 registers) for big batches (measured best at 512 frames: 134 ms vs 158 ms
+    // for 8x2 and 250 ms for 8x1); sdpl_line_set_serial can pin both
+    const bool small = nl * B <= o->sm_count;
+    const int nw = o->grow_warps > 0 ? o->grow_warps : (small ? 8 : 4);
+    const int mb = o->grow_minb > 0 ? o->grow_minb : (small ? 1 : 4);
+    if (nw >= 8 && mb >= 2) k_lsd_grow_block<8, 2><<<nl * B, 256, 0, st>>>(D);
+    else if (nw >= 8) k_lsd_grow_block<8, 1><<<nl * B, 256, 0, st>>>(D);
+    else if (nw >= 4 && mb == 3) k_lsd_grow_block<4, 3><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb == 4) k_lsd_grow_block<4, 4><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb == 5) k_lsd_grow_block<4, 5><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb >= 6) k_lsd_grow_block<4, 6><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4) k_lsd_grow_block<4, 2><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 2 && mb >= 8) k_lsd_grow_block<2, 8><<<nl * B, 64, 0, st>>>(D);
+    else if (nw >= 2 && mb >= 6) k_lsd_grow_block<2, 6><<<nl * B, 64, 0, st>>>(D);
+    else if (nw >= 2) k_lsd_grow_block<2, 4><<<nl * B, 64, 0, st>>>(D);
+    else k_lsd_grow_block<1, 8><<<nl * B, 32, 0, st>>>(D);
   }
   else k_lsd_grow<<<nl * B, 32, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
@@ -1032,10 +1046,10 @@ int sdpl_line_set_serial(sdpl_line* o, int on) {
   if (!o || on < 0) return SDPL_ERR_ARG;
   // bits 0-1: schedule; bits 8..: re-order buffer size override (power of two, <= allocated), for tuning
   const int w = on >> 8;
-  if (w && (w < 1 || w > 2048 || (w & (w - 1)))) return SDPL_ERR_ARG;
+  if (w && (on & 3) == 2 && (w < 1 || w > 2048 || (w & (w - 1)))) return SDPL_ERR_ARG;
   o->serial_mode = on & 3;
   if (w && o->serial_mode == 2) o->rob_w_run = std::max(w, 32);
-  if (w && o->serial_mode == 0) o->grow_warps = std::min(w, lsd::kMaxGrowWarps);
+  if (w && o->serial_mode == 0) { o->grow_warps = std::min(w & 15, lsd::kMaxGrowWarps); if (w >> 4) o->grow_minb = w >> 4; }
   return SDPL_OK;
 }
 

@@ -442,6 +442,174 @@ struct BlockShared {
   int rb[4];                    // bounding box written by the last re-run
 };
 
+// Compact single-copy version of the per-seed pipeline for the block kernel: growth, rectangle fit and the refine state
+// machine each appear ONCE in the instruction stream (the templated process_seed<> above expands to two growths and three
+// rectangle fits per instantiation; with both instantiations inlined the kernel was 315 KB of SASS and instruction-fetch
+// bound).  `spec` selects speculative (stamps, no writes to `used`) or sequential (writes `used`) semantics at run time.
+// Arithmetic and its order are identical to process_seed<>.
+__device__ __forceinline__ void process_seed_u(const Task& T, const int seed, int* const reg, const int cap, const uint32_t stamp0,
+                                               const bool spec, SeedResult& R) {
+  const int w = T.w, h = T.h;
+  R.ok = 1; R.n1 = 0; R.n2_orig = 0; R.has_rect = 0; R.foff = 0; R.nf = 0;
+  const int sx = seed % w, sy = seed / w;
+  R.bx0 = R.bx1 = sx; R.by0 = R.by1 = sy;
+  int state = 0;                 // 0: first growth, 1: re-growth with the refined tolerance, 2: radius reduction passes
+  int* cur = reg;
+  int n = 0, capc = cap;
+  double prec = T.prec, ra = 0, rad_sq = 0;
+  uint32_t stamp = stamp0;
+  const double seed_ang = T.px[seed].ang;
+#pragma unroll 1
+  while (true) {
+    if (state <= 1) {
+      // ---------------- region_grow ----------------
+      if (spec) {
+        if (capc < 1 || ld_state(T.state + seed) > stamp) { R.ok = 0; return; }
+        atomicMax(&T.state[seed], stamp);
+      } else {
+        T.state[seed] = kUsed;
+      }
+      cur[0] = seed; n = 1;
+      ra = seed_ang;
+      double sn, cs;
+      sincos(ra, &sn, &cs);
+      float sumdx = (float)cs, sumdy = (float)sn;
+      int nxt = seed;
+      bool aborted = false;
+#pragma unroll 1
+      for (int i = 0; i < n && !aborted; i++) {
+        const int p = nxt;
+        const int n_start = n;
+        const int py = p / w, px = p - py * w;
+        uint32_t st[9];
+        PxA pa[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          const int yy = py - 1 + k / 3, xx = px - 1 + k % 3;
+          const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w && k != 4;
+          const int q = yy * w + xx;
+          st[k] = in ? ld_state(T.state + q) : kUsed;
+          if (in) pa[k] = T.px[q]; else pa[k].ang = kNotDef;
+        }
+        if (i + 1 < n_start) nxt = cur[i + 1];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          if (k == 4 || aborted) continue;
+          const uint32_t s = st[k];
+          if (s & kUsed) continue;
+          if (spec && s == stamp) continue;
+          if (!aligned_angle(pa[k].ang, ra, prec)) continue;
+          const int q = (py - 1 + k / 3) * w + (px - 1 + k % 3);
+          if (spec) {
+            if (s > stamp || n >= capc) { aborted = true; continue; }
+            atomicMax(&T.state[q], stamp);
+          } else {
+            T.state[q] = kUsed;
+          }
+          if (n == i + 1) nxt = q;
+          cur[n++] = q;
+          R.bx0 = min(R.bx0, px - 1 + k % 3); R.bx1 = max(R.bx1, px - 1 + k % 3);
+          R.by0 = min(R.by0, py - 1 + k / 3); R.by1 = max(R.by1, py - 1 + k / 3);
+          sumdx = __fadd_rn(sumdx, pa[k].c);
+          sumdy = __fadd_rn(sumdy, pa[k].s);
+          ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
+        }
+      }
+      if (state == 0) { R.n1 = n; R.nf = n; } else { R.n2_orig = spec ? n : 0; R.nf = n; }
+      if (aborted) { R.ok = 0; return; }
+      if (state == 0 ? (n < T.min_reg) : (n < 2)) return;
+    } else {
+      // ---------------- one pass of reduce_region_radius ----------------
+      rad_sq *= 0.75 * 0.75;
+      for (int i = 0; i < n; ++i) {
+        const int q = cur[i];
+        if (dist_sq((double)sx, (double)sy, (double)(q % w), (double)(q / w)) > rad_sq) {
+          if (!spec) T.state[q] = 0;
+          cur[i] = cur[n - 1];
+          cur[n - 1] = q;
+          --n;
+          --i;
+        }
+      }
+      R.nf = n;
+      if (n < 2) return;
+    }
+    // ---------------- region2rect (with get_theta) ----------------
+    {
+      double x = 0, y = 0, sum = 0;
+      for (int i = 0; i < n; ++i) {
+        const int q = cur[i];
+        const int qy = q / w, qx = q - qy * w;
+        const double wgt = modgrad_of(T.g2[q]);
+        x += (double)qx * wgt;
+        y += (double)qy * wgt;
+        sum += wgt;
+      }
+      x /= sum; y /= sum;
+      double Ixx = 0, Iyy = 0, Ixy = 0;
+      for (int i = 0; i < n; ++i) {
+        const int q = cur[i];
+        const int qy = q / w, qx = q - qy * w;
+        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[q]);
+        Ixx += dy * dy * wgt;
+        Iyy += dx * dx * wgt;
+        Ixy -= dx * dy * wgt;
+      }
+      const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+      double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
+                                             : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+      theta *= kDegToRad;
+      if (angle_diff(theta, ra) > T.prec) theta += kPI;
+      double dy_, dx_;
+      sincos(theta, &dy_, &dx_);
+      double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+      for (int i = 0; i < n; ++i) {
+        const int q = cur[i];
+        const int qy = q / w, qx = q - qy * w;
+        const double rdx = (double)qx - x, rdy = (double)qy - y;
+        const double l = rdx * dx_ + rdy * dy_;
+        const double ww = -rdx * dy_ + rdy * dx_;
+        if (l > l_max) l_max = l; else if (l < l_min) l_min = l;
+        if (ww > w_max) w_max = ww; else if (ww < w_min) w_min = ww;
+      }
+      Rect& rec = R.rec;
+      rec.x1 = x + l_min * dx_; rec.y1 = y + l_min * dy_;
+      rec.x2 = x + l_max * dx_; rec.y2 = y + l_max * dy_;
+      rec.width = w_max - w_min;
+      rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx_; rec.dy = dy_; rec.prec = T.prec; rec.p = T.p;
+      if (rec.width < 1.0) rec.width = 1.0;
+    }
+    const double density = (double)n / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
+    if (state == 0) {
+      if (T.refine <= 0 || density >= T.density_th) { R.has_rect = 1; return; }
+      // ---------------- refine: tolerance from the angle spread near the seed ----------------
+      double sum = 0, s_sum = 0;
+      int cnt = 0;
+      for (int i = 0; i < n; ++i) {
+        const int q = cur[i];
+        if (!spec) T.state[q] = 0;
+        if (dist((double)sx, (double)sy, (double)(q % w), (double)(q / w)) < R.rec.width) {
+          const double d = angle_diff_signed(T.px[q].ang, seed_ang);
+          sum += d;
+          s_sum += d * d;
+          ++cnt;
+        }
+      }
+      const double mean_angle = sum / (double)cnt;
+      prec = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+      if (spec) { cur = reg + n; capc = cap - n; R.foff = n; stamp = stamp0 | 1u; }   // keep the first region: it is part of E
+      state = 1;
+      continue;
+    }
+    if (density >= T.density_th) { R.has_rect = 1; return; }
+    if (state == 1) {
+      const double r1 = dist_sq((double)sx, (double)sy, R.rec.x1, R.rec.y1), r2 = dist_sq((double)sx, (double)sy, R.rec.x2, R.rec.y2);
+      rad_sq = r1 > r2 ? r1 : r2;
+      state = 2;
+    }
+  }
+}
+
 __device__ void grow_task_block(const Task& T, BlockShared& S) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NW = blockDim.x >> 5, K = blockDim.x;
@@ -450,7 +618,7 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
   int* my_reg = T.reg_spec + (size_t)tid * cap;
   if (tid == 0) { S.cursor = 0; S.npend = 0; }
   uint32_t wave = 0;
-  long long t_sel = 0, t_spec = 0, t_commit = 0, t_redo = 0, n_redo = 0, n_dead = 0, n_seed = 0, t_eval = 0;
+  long long t_sel = 0, t_spec = 0, t_commit = 0, t_redo = 0, n_redo = 0, n_round = 0, n_seed = 0;
   __syncthreads();
   while (true) {
     long long c0 = clock64();
@@ -482,18 +650,42 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
     SeedResult R;
     R.ok = 0; R.n1 = 0; R.n2_orig = 0; R.nf = 0; R.foff = 0; R.has_rect = 0;
     const uint32_t stamp = (wave << 11) | ((uint32_t)(K - 1 - tid) << 1);   // bit0 = phase, 10 bits of seed priority
-    if (tid < nsel) process_seed<true>(T, my_seed, my_reg, cap, stamp, R);
-    // pending set of the wave
     if (lane == 0) {
       const int first = warp * 32;
       S.pend[warp] = nsel >= first + 32 ? 0xffffffffu : (nsel > first ? ((1u << (nsel - first)) - 1u) : 0u);
     }
-    __syncthreads();
-    long long c2 = clock64(); t_spec += c2 - c1;
     bool retired = false;
     int verdict = 0;        // cached verdict: 0 unknown, 1 good (invalidated only by a re-run that wrote near me), 2 dead, 3 must re-run
+    int kstar = -1;         // -1: the speculative pass of the wave; otherwise the seed that is re-run sequentially this round
+    long long c2 = c1;
+    // every round starts with ONE call site of the per-seed pipeline: all seeds speculatively in the first round, the first
+    // doubtful seed sequentially in the later ones
     while (true) {
-      long long ce = clock64();
+      n_round++;
+      long long cr = clock64();
+      const bool run_spec = kstar < 0 && tid < nsel;
+      bool run_seq = kstar >= 0 && tid == kstar;
+      // the commits of the previous round may have taken kstar's seed: then the sequential algorithm skips it
+      if (run_seq && (ld_state(T.state + my_seed) & kUsed)) { run_seq = false; retired = true; S.rb[0] = 1; S.rb[2] = 0; }
+      if (run_spec || run_seq) {
+        process_seed_u(T, my_seed, run_seq ? T.reg_serial : my_reg, run_seq ? T.npx : cap, stamp, run_spec, R);
+        if (run_seq) {
+          if (R.has_rect) { append_rect(T, S.npend, R.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, R.nf); S.has = 1; }
+          S.rb[0] = R.bx0; S.rb[1] = R.by0; S.rb[2] = R.bx1; S.rb[3] = R.by1;
+          retired = true;
+        }
+      }
+      __syncthreads();
+      if (kstar < 0) { c2 = clock64(); t_spec += c2 - c1; }
+      else {
+        if (tid == 0) S.npend += S.has;
+        // the re-run wrote `used` inside its bounding box only: cached "good" verdicts elsewhere stay valid
+        if (verdict == 1 && !(S.rb[0] > R.bx1 || S.rb[2] < R.bx0 || S.rb[1] > R.by1 || S.rb[3] < R.by0)) verdict = 0;
+        // kstar is settled
+        if (lane == 0 && kstar >= warp * 32 && kstar < warp * 32 + 32) S.pend[warp] &= ~(1u << (kstar - warp * 32));
+        __syncthreads();
+        t_redo += clock64() - cr;
+      }
       const bool mine = ((S.pend[warp] >> lane) & 1u) && !retired;
       bool dead = false, good = false;
       if (mine) {
@@ -512,69 +704,47 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
       const uint32_t dm = __ballot_sync(0xffffffffu, dead), gm = __ballot_sync(0xffffffffu, good);
       if (lane == 0) { S.deadm[warp] = dm; S.goodm[warp] = gm; }
       __syncthreads();
-      t_eval += clock64() - ce;
       // first pending seed of the wave that is neither dead nor provably good
-      int kstar = K, any = 0;
+      int ks = K, any = 0;
       for (int v = 0; v < NW; v++) {
         const uint32_t pm = S.pend[v];
         any |= pm != 0;
         const uint32_t bad = pm & ~S.deadm[v] & ~S.goodm[v];
-        if (bad && kstar == K) kstar = v * 32 + __ffs(bad) - 1;
+        if (bad && ks == K) ks = v * 32 + __ffs(bad) - 1;
       }
       if (!any) break;
-      const bool below = tid < kstar;
+      const bool below = tid < ks;
       const bool do_commit = mine && good && below;
       const bool do_drop = mine && dead && below;
       mark_used_coop(T, do_commit, my_reg + R.foff, R.nf);
       if (do_commit || do_drop) retired = true;
-      n_dead += do_drop ? 1 : 0;
       const uint32_t rm = __ballot_sync(0xffffffffu, do_commit && R.has_rect);
       if (lane == 0) S.rectm[warp] = rm;
       __syncthreads();
       int before = S.npend, total = 0;
       for (int v = 0; v < NW; v++) { const int c = __popc(S.rectm[v]); if (v < warp) before += c; total += c; }
       if (do_commit && R.has_rect) append_rect(T, before + __popc(rm & lt), R.rec, (int)((wave << 11) | (tid << 1) | 0), my_seed, R.nf);
-      __syncthreads();
-      if (tid == 0) { S.npend += total; S.has = 0; }
-      __syncthreads();
-      if (kstar < K) {
-        long long c3 = clock64();
-        // the commits just made (seeds before kstar) may have taken kstar's seed: then the sequential algorithm skips it
-        if (tid == kstar) {
-          if (!(ld_state(T.state + my_seed) & kUsed)) {
-            SeedResult Q;
-            process_seed<false>(T, my_seed, T.reg_serial, T.npx, 0u, Q);
-            if (Q.has_rect) { append_rect(T, S.npend, Q.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, Q.nf); S.has = 1; }
-            S.rb[0] = Q.bx0; S.rb[1] = Q.by0; S.rb[2] = Q.bx1; S.rb[3] = Q.by1;
-          } else {
-            S.rb[0] = 1; S.rb[2] = 0;      // nothing written
-          }
-          retired = true;
-        }
-        n_redo++;
-        __syncthreads();
-        if (tid == 0) S.npend += S.has;
-        // the re-run wrote `used` inside its bounding box only: cached "good" verdicts elsewhere stay valid
-        if (verdict == 1 && !(S.rb[0] > R.bx1 || S.rb[2] < R.bx0 || S.rb[1] > R.by1 || S.rb[3] < R.by0)) verdict = 0;
-        t_redo += clock64() - c3;
-      }
-      // everything up to and including kstar is settled
+      // everything before ks is settled
       if (lane == 0) {
         const int first = warp * 32;
         uint32_t keep = 0xffffffffu;
-        if (kstar >= first + 32) keep = 0u;
-        else if (kstar >= first) keep = (kstar - first) >= 31 ? 0u : ~((2u << (kstar - first)) - 1u);
+        if (ks >= first + 32) keep = 0u;
+        else if (ks > first) keep = ~((1u << (ks - first)) - 1u);
         S.pend[warp] &= keep;
       }
       __syncthreads();
-      if (kstar >= K) break;
+      if (tid == 0) { S.npend += total; S.has = 0; }
+      if (ks >= K) break;
+      kstar = ks;
+      n_redo++;
+      __syncthreads();
     }
     t_commit += clock64() - c2;
   }
   if (tid == 0) *T.npend = min(S.npend, T.pend_cap);
   if (tid == 0 && T.prof) {
     T.prof[0] = t_sel; T.prof[1] = t_spec; T.prof[2] = t_commit - t_redo; T.prof[3] = t_redo; T.prof[4] = wave; T.prof[5] = n_redo;
-    T.prof[6] = t_eval; T.prof[7] = n_seed;
+    T.prof[6] = n_round; T.prof[7] = n_seed;
   }
 }
 
