@@ -267,7 +267,10 @@ def run_gpu(args, stages):
     stats = torch.zeros((F, 4), dtype=i32, device=dev)
     gathered = [None]
 
-    s_orb, s_line, s_match, s_lmatch = (torch.cuda.Stream(device=dev) for _ in range(4))
+    # the latency-bound line pipeline gets the high-priority stream: its CTAs are placed first, the ORB / matching kernels
+    # fill the SMs it leaves idle (tail of the region-growing kernel)
+    s_line = torch.cuda.Stream(device=dev, priority=-1)
+    s_orb, s_match, s_lmatch = (torch.cuda.Stream(device=dev, priority=0) for _ in range(3))
     orb.set_stream(s_orb.cuda_stream); mat.set_stream(s_match.cuda_stream)
     if use_line:
         line.set_stream(s_line.cuda_stream); lmat.set_stream(s_lmatch.cuda_stream)
@@ -290,14 +293,14 @@ def run_gpu(args, stages):
     def step_dev():
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event(); ev.record(main)
-        s_orb.wait_event(ev)
-        orb.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_nkp.data_ptr() + 4)
-        launches[0] += orb.last_launches()
         if use_line:
             s_line.wait_event(ev)
             line.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr() + LINE_CAP * 32, LINE_CAP,
                                    d_nkl.data_ptr() + 4)
             launches[0] += line.last_launches()
+        s_orb.wait_event(ev)
+        orb.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr() + cap * 32, cap, d_nkp.data_ptr() + 4)
+        launches[0] += orb.last_launches()
         if use_match:
             s_match.wait_stream(s_orb)
             match_prev(mat, s_match, d_desc, d_nkp, cap, d_best, d_second, d_nacc)

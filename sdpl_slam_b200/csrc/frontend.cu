@@ -69,7 +69,14 @@ int sdpl_frontend_create(sdpl_frontend** out, int nfeatures, float scale, int nl
   f->kp_cap = sdpl_orb_max_keypoints(f->orb);
   f->kl_cap = lsd_nfeatures > 0 ? lsd_nfeatures : 2048;
   SDPL_CUDA(cudaSetDevice(device));
-  for (cudaStream_t* s : {&f->s_io, &f->s_orb, &f->s_line, &f->s_pm, &f->s_lm}) SDPL_CUDA(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+  {
+    // the latency-bound line pipeline runs on the high-priority stream: its CTAs are placed first and the ORB / matching
+    // kernels fill the SMs it leaves idle
+    int lo = 0, hi = 0;
+    SDPL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (cudaStream_t* s : {&f->s_io, &f->s_orb, &f->s_pm, &f->s_lm}) SDPL_CUDA(cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, lo));
+    SDPL_CUDA(cudaStreamCreateWithPriority(&f->s_line, cudaStreamNonBlocking, hi));
+  }
   for (cudaEvent_t* e : {&f->ev_in, &f->ev_orb, &f->ev_line, &f->ev_pm, &f->ev_lm}) SDPL_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   sdpl_orb_set_stream(f->orb, f->s_orb); sdpl_line_set_stream(f->line, f->s_line);
   sdpl_matcher_set_stream(f->pm, f->s_pm); sdpl_matcher_set_stream(f->lm, f->s_lm);
@@ -133,15 +140,15 @@ int sdpl_frontend_process(sdpl_frontend* f, const uint8_t* imgs, int n, int w, i
   }
   SDPL_CUDA(cudaEventRecord(f->ev_in, f->s_io));
   int launches = 0;
-  // ---- ORB and lines concurrently ----
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, f->ev_in, 0));
-  if ((rc = sdpl_orb_extract_batch_dev(f->orb, f->d_imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dk, dd, KC, dn, 0))) return rc;
-  launches += sdpl_orb_last_launches(f->orb);
-  SDPL_CUDA(cudaEventRecord(f->ev_orb, f->s_orb));
+  // ---- lines (high priority, launched first) and ORB concurrently ----
   SDPL_CUDA(cudaStreamWaitEvent(f->s_line, f->ev_in, 0));
   if ((rc = sdpl_line_extract_batch_dev(f->line, f->d_imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dl, dld, LC, dln, 0))) return rc;
   launches += sdpl_line_last_launches(f->line);
   SDPL_CUDA(cudaEventRecord(f->ev_line, f->s_line));
+  SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, f->ev_in, 0));
+  if ((rc = sdpl_orb_extract_batch_dev(f->orb, f->d_imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dk, dd, KC, dn, 0))) return rc;
+  launches += sdpl_orb_last_launches(f->orb);
+  SDPL_CUDA(cudaEventRecord(f->ev_orb, f->s_orb));
   // ---- frame t against frame t-1 (slot t+1 against slot t), points then lines ----
   SDPL_CUDA(cudaStreamWaitEvent(f->s_pm, f->ev_orb, 0));
   if ((rc = sdpl_match_knn2_batch_dev(f->pm, dd, dn, (size_t)32 * KC, f->d_desc.as<uint8_t>(), f->d_nkp.as<int>(), (size_t)32 * KC, n, KC, KC,
