@@ -788,6 +788,8 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   }
   D.lvl_frame = align_up(std::max<size_t>(lvl_off, 16), 256); D.px_frame = align_up(px_off, 256); D.lbd_frame = align_up(lbd_off, 256);
   D.hist_frame = hist_off; D.reg_frame = reg_off;
+  // rectangles per (frame, octave): scales with the working image (1242x375 -> 6400; an overflow is reported, never silent)
+  o->pend_cap = std::max(4096, (int)align_up((size_t)D.O[0].npx / 48, 256));
   D.pend_cap = o->pend_cap;
   D.in_w = w; D.in_h = h;
   int rc;
@@ -1080,6 +1082,7 @@ int sdpl_line_extract_batch(sdpl_line* o, const uint8_t* imgs, int nframes, int 
   if (stride < w || !kls || !desc || capacity < 1) { set_last_error("sdpl_line_extract_batch: bad argument"); return SDPL_ERR_ARG; }
   SDPL_CUDA(cudaSetDevice(o->device));
   int rc;
+  if ((rc = line_setup(o, w, h, nframes))) return rc;     // fixes pend_cap for this geometry
   const int cap_dev = o->nfeatures ? std::max(o->nfeatures, 1) : o->pend_cap * o->nlevels;
   const size_t in_bytes = (size_t)w * h * nframes;
   if ((rc = o->in_stage.reserve(in_bytes))) return rc;

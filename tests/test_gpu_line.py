@@ -137,3 +137,12 @@ def test_line_unsupported_configurations(frontend):
         frontend.Lineextractor(0, 2, 0.5, 2, 2.0, 0)       # only the reference's 0.8 pre-scaling is implemented
     with pytest.raises(TypeError):
         frontend.Lineextractor()(np.zeros((10, 10), np.float32))
+
+
+def test_line_highres_stress(frontend, oracle):
+    # BASELINE config 5 geometry: 2048x1536 (LSD works on 1638x1229 and 819x614)
+    img = synth.frame(77, 1536, 2048)
+    kg, dg = frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 0)(img, capacity=16384)
+    kr, dr = oracle.LineOracle(0, 2, 0.8, 2, 2.0, 0)(img, cap=30000)
+    frac = _compare_lines(kg, dg, kr, dr)
+    assert frac >= 0.99 and len(kg) > 200
