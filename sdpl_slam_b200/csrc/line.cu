@@ -344,11 +344,24 @@ __global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
     if (D.refine >= 2 && lsd::rect_area_bound(T.pend[i].rec) > kBigRect) {
       const int k = atomicAdd(D.nbig + task, 1);
-      D.bigidx[(size_t)task * D.pend_cap + k] = i;
-    } else {
-      lsd::validate_pending<false>(T, i);
+      D.bigidx[(size_t)task * D.pend_cap + k] = i;                           // big list grows from the front
+    } else if (!lsd::validate_first(T, i)) {
+      const int k = atomicAdd(D.nbig + (size_t)D.nl * D.B + task, 1);
+      D.bigidx[(size_t)task * D.pend_cap + D.pend_cap - 1 - k] = i;          // retry list grows from the back
     }
   }
+}
+
+// second pass over the small rectangles whose first evaluation failed (compacted: uniform work per thread)
+__global__ void __launch_bounds__(64) k_lsd_nfa_rest(LineDev D) {
+  const int task = blockIdx.y;
+  const int f = task / D.nl, o = task % D.nl;
+  const int nf = D.nbig[(size_t)D.nl * D.B + task];
+  if ((int)(blockIdx.x * blockDim.x) >= nf) return;
+  lsd::Task T;
+  make_task(D, f, o, T);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nf; k += gridDim.x * blockDim.x)
+    lsd::validate_rest(T, D.bigidx[(size_t)task * D.pend_cap + D.pend_cap - 1 - k]);
 }
 
 __global__ void __launch_bounds__(128) k_lsd_nfa_big(LineDev D) {
@@ -813,7 +826,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->prof.reserve(sizeof(long long) * 8 * nl * B))) return rc;
   if ((rc = o->robrect.reserve(sizeof(lsd::Rect) * (size_t)o->rob_w * nl * B))) return rc;
   if ((rc = o->rob.reserve(sizeof(lsd::RobEntry) * (size_t)o->rob_w * nl * B))) return rc;
-  if ((rc = o->nbig.reserve(sizeof(int) * nl * B))) return rc;
+  if ((rc = o->nbig.reserve(sizeof(int) * 2 * nl * B))) return rc;
   if ((rc = o->bigidx.reserve(sizeof(int) * (size_t)D.pend_cap * nl * B))) return rc;
   if (!o->lgam.p) {
     if ((rc = o->lgam.reserve(sizeof(double) * kLgamN))) return rc;
@@ -911,10 +924,12 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   else k_lsd_grow<<<nl * B, 32, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_grow");
-  SDPL_CUDA(cudaMemsetAsync(D.nbig, 0, sizeof(int) * nl * B, st));
+  SDPL_CUDA(cudaMemsetAsync(D.nbig, 0, sizeof(int) * 2 * nl * B, st));
   k_lsd_nfa<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   k_lsd_nfa_big<<<dim3(64, nl * B), 128, 0, st>>>(D);
+  SDPL_LAUNCH_CHECK();
+  k_lsd_nfa_rest<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_nfa");
   k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());

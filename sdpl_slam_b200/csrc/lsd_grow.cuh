@@ -1219,12 +1219,11 @@ __device__ __noinline__ double rect_nfa(const Task& T, const Rect& rec) {
   return __shfl_sync(0xffffffffu, v, 0);
 }
 
+// rect_improve after its first evaluation (log_nfa = rect_nfa(rec) <= log_eps): the 25 refinement attempts
 template <bool COOP>
-__device__ double rect_improve(const Task& T, Rect& rec) {
+__device__ double rect_improve_rest(const Task& T, Rect& rec, double log_nfa) {
   const double delta = 0.5, delta_2 = delta / 2.0;
   const double log_eps = T.log_eps;
-  double log_nfa = rect_nfa<COOP>(T, rec);
-  if (log_nfa > log_eps) return log_nfa;
   Rect r = rec;
   for (int n = 0; n < 5; ++n) {
     r.p /= 2; r.prec = r.p * kPI;
@@ -1272,8 +1271,45 @@ __device__ double rect_improve(const Task& T, Rect& rec) {
   return log_nfa;
 }
 
+template <bool COOP>
+__device__ double rect_improve(const Task& T, Rect& rec) {
+  const double log_nfa = rect_nfa<COOP>(T, rec);
+  if (log_nfa > T.log_eps) return log_nfa;
+  return rect_improve_rest<COOP>(T, rec, log_nfa);
+}
+
 // upper bound of the number of pixels one scan of the rectangle visits (width only shrinks during rect_improve)
 __device__ __forceinline__ double rect_area_bound(const Rect& r) { return (dist(r.x1, r.y1, r.x2, r.y2) + 2.0) * (r.width + 2.0); }
+
+__device__ __forceinline__ void write_segment(const Task& T, int i, const Rect& rec, bool acc);
+
+// small rectangles, pass 1: the first NFA evaluation.  Returns true when the rectangle is settled (accepted); otherwise the
+// value is parked in the (not yet used) segment slot and the rectangle goes to the second pass, where every thread of a warp
+// has the same 25 evaluations ahead of it instead of a mix of 1 and 26
+__device__ bool validate_first(const Task& T, int i) {
+  const Rect rec = T.pend[i].rec;
+  if (T.refine < 2) { write_segment(T, i, rec, true); return true; }
+  const double v = rect_nfa<false>(T, rec);
+  if (v > T.log_eps) { write_segment(T, i, rec, true); return true; }
+  *reinterpret_cast<double*>(T.pend[i].seg) = v;
+  return false;
+}
+__device__ void validate_rest(const Task& T, int i) {
+  Rect rec = T.pend[i].rec;
+  const double v0 = *reinterpret_cast<const double*>(T.pend[i].seg);
+  const double v = rect_improve_rest<false>(T, rec, v0);
+  write_segment(T, i, rec, v > T.log_eps);
+}
+
+__device__ __forceinline__ void write_segment(const Task& T, int i, const Rect& rec, bool acc) {
+  Pending& P = T.pend[i];
+  P.accepted = acc ? 1 : 0;
+  if (acc) {
+    double x1 = rec.x1 + 0.5, y1 = rec.y1 + 0.5, x2 = rec.x2 + 0.5, y2 = rec.y2 + 0.5;
+    if (T.scale != 1.0) { x1 /= T.scale; y1 /= T.scale; x2 /= T.scale; y2 /= T.scale; }
+    P.seg[0] = (float)x1; P.seg[1] = (float)y1; P.seg[2] = (float)x2; P.seg[3] = (float)y2;
+  }
+}
 
 // validate pending rectangle i of task T and write its segment (COOP = false: by one thread; true: by one warp)
 template <bool COOP>

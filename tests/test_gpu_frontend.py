@@ -75,3 +75,16 @@ def test_sharded_batch_equals_single_rank(frontend):
                 f = rank * per + j
                 assert so[j][0].tobytes() == full_o[f][0].tobytes() and so[j][1].tobytes() == full_o[f][1].tobytes()
                 assert sl[j][0].tobytes() == full_l[f][0].tobytes() and sl[j][1].tobytes() == full_l[f][1].tobytes()
+
+
+def test_handles_survive_geometry_changes(frontend):
+    """One handle, alternating image sizes and batch sizes: results equal those of fresh handles."""
+    orb = frontend.ORBextractor(500, 1.2, 8, 20, 7); line = frontend.Lineextractor()
+    for (h, w, n) in ((240, 416, 1), (188, 320, 3), (240, 416, 2), (375, 1242, 1), (188, 320, 1)):
+        imgs = np.stack([synth.frame(900 + i, h, w) for i in range(n)])
+        a = orb.extract_batch(imgs); b = line.extract_batch(imgs)
+        fo = frontend.ORBextractor(500, 1.2, 8, 20, 7); fl = frontend.Lineextractor()
+        for i in range(n):
+            k, d = fo(imgs[i]); kl, dl = fl(imgs[i])
+            assert a[i][0].tobytes() == k.tobytes() and a[i][1].tobytes() == d.tobytes()
+            assert b[i][0].tobytes() == kl.tobytes() and b[i][1].tobytes() == dl.tobytes()
