@@ -385,15 +385,51 @@ class BinaryDescriptorMatcher(_Profiled):
             raise TypeError("descriptors must be (N, 32) uint8")
         return d
 
-    def knnMatch(self, queryDescriptors, trainDescriptors, k=2):
+    # --- train set kept on the matcher: BinaryDescriptorMatcher::add / train / clear (descriptor_custom.hpp:1015-1126) ---
+    def add(self, descriptors):
+        """Append train descriptors (one (N, 32) array or a list of them); img index = position in the list."""
+        ds = descriptors if isinstance(descriptors, (list, tuple)) else [descriptors]
+        if not hasattr(self, "_train"):
+            self._train = []
+        self._train += [self._desc(d) for d in ds]
+
+    def train(self):
+        """The reference builds its multi-index hash tables here; brute force needs no index."""
+
+    def clear(self):
+        self._train = []
+
+    def _stored(self):
+        tr = getattr(self, "_train", [])
+        if not tr:
+            raise ValueError("no train descriptors: call add() first or pass trainDescriptors")
+        img = np.concatenate([np.full(len(d), i, np.int32) for i, d in enumerate(tr)])
+        base = np.concatenate([np.arange(len(d), dtype=np.int32) for d in tr])
+        return np.concatenate(tr), img, base
+
+    def _localise(self, m, img, base):
+        ok = m["train"] >= 0
+        m["img"][ok] = img[m["train"][ok]]
+        m["train"][ok] = base[m["train"][ok]]
+        return m
+
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2):
+        """k nearest train descriptors per query, ascending (distance, index).  k == 2 -> (best, second) arrays;
+        other k -> an (nq, k) array (missing neighbours have train = -1).  Without trainDescriptors the stored set is used."""
+        if trainDescriptors is None:
+            t, img, base = self._stored()
+            r = self.knnMatch(queryDescriptors, t, k)
+            if k == 2:
+                return self._localise(r[0], img, base), self._localise(r[1], img, base)
+            return self._localise(r.reshape(-1), img, base).reshape(r.shape)
         if k != 2:
-            raise ValueError("only k=2 is implemented (best / second best)")
+            return self.radiusMatch(queryDescriptors, trainDescriptors, 256, k=int(k))[1]
         q, t = self._desc(queryDescriptors), self._desc(trainDescriptors)
         best = np.zeros(q.shape[0], DM_DTYPE); second = np.zeros(q.shape[0], DM_DTYPE)
         _check(self._L.sdpl_match_knn2(self._h, _p(q), q.shape[0], _p(t), t.shape[0], _p(best), _p(second)))
         return best, second
 
-    def match(self, queryDescriptors, trainDescriptors):
+    def match(self, queryDescriptors, trainDescriptors=None):
         return self.knnMatch(queryDescriptors, trainDescriptors, 2)[0]
 
     def ratioMatch(self, queryDescriptors, trainDescriptors, ratio=0.8, max_dist=100):

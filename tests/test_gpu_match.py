@@ -91,3 +91,25 @@ def test_hamming_properties_full_size(frontend):
     # second best of i is j  =>  distance(j -> i) is at most that distance
     j = s["train"]
     assert (s["distance"][j] <= s["distance"]).all()
+
+
+def test_knn_general_k_and_stored_train_set(frontend, oracle):
+    rng = np.random.default_rng(8)
+    t1, t2 = _rand_desc(rng, 300), _rand_desc(rng, 200)
+    q = _noisy_copy(rng, np.concatenate([t1[:40], t2[:40]]), 12)
+    g = frontend.BinaryDescriptorMatcher()
+    # k = 4 nearest == brute force over the full distance matrix (ties -> lowest index)
+    allt = np.concatenate([t1, t2])
+    r = g.knnMatch(q, allt, k=4)
+    full = np.unpackbits(q[:, None, :] ^ allt[None, :, :], axis=2).sum(2)
+    order = np.lexsort((np.broadcast_to(np.arange(full.shape[1]), full.shape), full), axis=1)[:, :4]
+    np.testing.assert_array_equal(r["train"], order)
+    np.testing.assert_array_equal(r["distance"], np.take_along_axis(full, order, 1))
+    # add / train / match on the stored set: img index and per-image train index
+    g.add([t1, t2]); g.train()
+    m = g.match(q)
+    assert (m["img"][:40] == 0).all() and (m["img"][40:] == 1).all()
+    assert (m["train"][:40] == np.arange(40)).all() and (m["train"][40:] == np.arange(40)).all()
+    g.clear()
+    with pytest.raises(ValueError):
+        g.match(q)
