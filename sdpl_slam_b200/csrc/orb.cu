@@ -146,66 +146,78 @@ __device__ __forceinline__ bool has_arc9(uint32_t m16) {
   return m != 0;
 }
 
+// Two horizontally adjacent pixels per step as packed s16x2 lanes: the 16 ring differences d[k] = ring[k] - centre are one
+// VIADD.16x2 each, the "minimum over every arc of 9" is two levels of the native three-input VIMNMX3.S16x2
+// (min3 of min3's), the dark side is the same with max3 on the same differences (min over the arc of (c - r) = -max(r - c)).
+// Shared memory holds the tile twice, the second copy shifted by one byte, so every ring pair is an aligned 16-bit load.
+__device__ __forceinline__ unsigned expand2(unsigned v16) { return __byte_perm(v16, 0u, 0x4140); }   // (b0, b1) -> s16x2
+
 __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
-  __shared__ uint8_t tile[kFT_H + 6][kFT_W + 8];
+  constexpr int S = kFT_W + 8;                                  // row stride (even)
+  __shared__ __align__(4) uint8_t tileA[(kFT_H + 6) * S];
+  __shared__ __align__(4) uint8_t tileB[(kFT_H + 6) * S];       // tileB[i] == tileA[i + 1]
   int t = blockIdx.x;
   int l = 0;
 #pragma unroll 1
   for (int i = 1; i < D.nl; i++) if (t >= D.L[i].fast_tile_base) l = i;
   const LvlDev& L = D.L[l];
   t -= L.fast_tile_base;
-  int tx = t % L.fast_tiles_x, ty = t / L.fast_tiles_x;
-  int x0 = kBorder + tx * kFT_W, y0 = kBorder + ty * kFT_H;   // level (interior) coordinates of the tile
+  const int tx = t % L.fast_tiles_x, ty = t / L.fast_tiles_x;
+  const int x0 = kBorder + tx * kFT_W, y0 = kBorder + ty * kFT_H;   // level (interior) coordinates of the tile
   const uint8_t* img = D.pyr + (size_t)blockIdx.y * D.pyr_frame + L.pyr_off + (size_t)kBorder * L.pstride + kBorder;
-  // stage tile + 3 px halo (always inside the padded plane)
-  for (int i = threadIdx.x; i < (kFT_H + 6) * (kFT_W + 6); i += 256) {
-    int yy = i / (kFT_W + 6), xx = i - yy * (kFT_W + 6);
-    int gy = y0 - 3 + yy, gx = x0 - 3 + xx;
+  // stage tile + 3 px halo (always inside the padded plane), plus one extra column for the shifted copy
+  for (int i = threadIdx.x; i < (kFT_H + 6) * (kFT_W + 7); i += 256) {
+    const int yy = i / (kFT_W + 7), xx = i - yy * (kFT_W + 7);
+    const int gy = y0 - 3 + yy, gx = x0 - 3 + xx;
     uint8_t v = 0;
     if (gy < L.h + kBorder && gx < L.w + kBorder) v = img[(ptrdiff_t)gy * L.pstride + gx];
-    tile[yy][xx] = v;
+    tileA[yy * S + xx] = v;
+    if (xx > 0) tileB[yy * S + xx - 1] = v;
   }
   __syncthreads();
   uint8_t* sc = D.score + (size_t)blockIdx.y * D.s_frame + L.s_off;
   const int xe = L.w - kBorder, ye = L.h - kBorder;
   const int tmin = D.min_th;
+  // ring offsets (dx, dy), k = 0..15 (cv::FAST order)
+  constexpr int RX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+  constexpr int RY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 #pragma unroll 1
-  for (int i = threadIdx.x; i < kFT_W * kFT_H; i += 256) {
-    int yy = i / kFT_W, xx = i % kFT_W;
-    int gx = x0 + xx, gy = y0 + yy;
+  for (int i = threadIdx.x; i < (kFT_W / 2) * kFT_H; i += 256) {
+    const int yy = i / (kFT_W / 2), xx = (i % (kFT_W / 2)) * 2;   // even column inside the tile
+    const int gx = x0 + xx, gy = y0 + yy;
     if (gx >= xe || gy >= ye) continue;
-    const uint8_t* p = &tile[yy + 3][xx + 3];
-    constexpr int S = kFT_W + 8;
-    int v = p[0];
-    int r[16] = {p[3 * S],      p[3 * S + 1],  p[2 * S + 2],  p[S + 3],  p[3],      p[-S + 3],  p[-2 * S + 2], p[-3 * S + 1],
-                 p[-3 * S],     p[-3 * S - 1], p[-2 * S - 2], p[-S - 3], p[-3],     p[S - 3],   p[2 * S - 2],  p[3 * S - 1]};
-    uint32_t bm = 0, dm = 0;
+    const int base = (yy + 3) * S + xx + 3;                        // odd byte offset of the centre pair
+    const unsigned c2 = expand2(*(const unsigned short*)(tileB + base - 1));
+    unsigned d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      bm |= (uint32_t)(r[k] > v + tmin) << k;
-      dm |= (uint32_t)(r[k] < v - tmin) << k;
+      const int off = base + RY[k] * S + RX[k];                    // parity known at compile time: RX odd -> even offset
+      const unsigned short v = (RX[k] & 1) ? *(const unsigned short*)(tileA + off) : *(const unsigned short*)(tileB + off - 1);
+      d[k] = __vsub2(expand2(v), c2);
     }
-    int s = 0;
-    bool hb = ((bm | (bm >> 8)) & 0xFF) == 0xFF && has_arc9(bm);
-    bool hd = ((dm | (dm >> 8)) & 0xFF) == 0xFF && has_arc9(dm);
-    if (hb || hd) {
-      int d[16];
-      int best = -256;
-      if (hb) {
+    unsigned m3[16], M3[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = r[k] - v;
-        best = arc9_max_of_min(d);
-      }
-      if (hd) {
-#pragma unroll
-        for (int k = 0; k < 16; k++) d[k] = v - r[k];
-        best = max(best, arc9_max_of_min(d));
-      }
-      s = best - 1;
-      if (s < tmin) s = 0;
-      if (s > 255) s = 255;
+    for (int k = 0; k < 16; k++) {
+      m3[k] = __vimin3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+      M3[k] = __vimax3_s16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
     }
-    sc[(size_t)gy * L.sstride + gx] = (uint8_t)s;
+    unsigned bb = 0x80008000u, dd = 0x7fff7fffu;                   // max of arc-minima (bright), min of arc-maxima (dark)
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      const unsigned a0 = __vimin3_s16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+      const unsigned a1 = __vimin3_s16x2(m3[k + 1], m3[(k + 4) & 15], m3[(k + 7) & 15]);
+      bb = __vimax3_s16x2(bb, a0, a1);
+      const unsigned b0 = __vimax3_s16x2(M3[k], M3[(k + 3) & 15], M3[(k + 6) & 15]);
+      const unsigned b1 = __vimax3_s16x2(M3[k + 1], M3[(k + 4) & 15], M3[(k + 7) & 15]);
+      dd = __vimin3_s16x2(dd, b0, b1);
+    }
+    const unsigned best = __vmaxs2(bb, __vsub2(0u, dd));           // per lane: max(bright, dark)
+    int s0 = (int)(short)(best & 0xffffu) - 1, s1 = (int)(short)(best >> 16) - 1;
+    s0 = s0 < tmin ? 0 : min(s0, 255);
+    s1 = s1 < tmin ? 0 : min(s1, 255);
+    uint8_t* o = sc + (size_t)gy * L.sstride + gx;
+    o[0] = (uint8_t)s0;
+    if (gx + 1 < xe) o[1] = (uint8_t)s1;
   }
 }
 
