@@ -610,6 +610,192 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
   }
 }
 
+// Warp-cooperative version of the SEQUENTIAL per-seed pipeline (exactly the semantics and arithmetic order of
+// process_seed<false>): the whole warp works on ONE seed.  Used for the re-runs, which otherwise leave 127 of 128 threads
+// idle behind one dependent-instruction chain.  All scalar state is warp-uniform (every lane holds the same value); lanes
+// differ only in the element they fetch:
+//   * growth: the 8 neighbours of the expanded pixel are loaded and tested by 8 lanes at once; joins are resolved in scan
+//     order with ballots (after a join only the later neighbours are re-tested against the updated region angle);
+//   * rectangle fit / refine statistics: 32 list elements per step are loaded and transformed (sqrt, products) in parallel
+//     and then accumulated by every lane in list order through shuffles, so the floating-point sums are bit-identical to
+//     the sequential loop.
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+
+__device__ void process_seed_coop(const Task& T, const int seed, int* const reg, SeedResult& R) {
+  const int lane = threadIdx.x & 31;
+  const int w = T.w, h = T.h;
+  R.ok = 1; R.n1 = 0; R.n2_orig = 0; R.has_rect = 0; R.foff = 0; R.nf = 0;
+  const int sx = seed % w, sy = seed / w;
+  int bx0 = sx, bx1 = sx, by0 = sy, by1 = sy;
+  int state = 0, n = 0;
+  double prec = T.prec, ra = 0, rad_sq = 0;
+  const double seed_ang = T.px[seed].ang;
+  // neighbour handled by this lane (lanes 0..8 except 4)
+  const int ndx = (lane % 3) - 1, ndy = (lane / 3) - 1;
+  const bool nlane = lane < 9 && lane != 4;
+#pragma unroll 1
+  while (true) {
+    if (state <= 1) {
+      // ---------------- region_grow ----------------
+      if (lane == 0) { T.state[seed] = kUsed; reg[0] = seed; }
+      n = 1;
+      ra = seed_ang;
+      double sn, cs;
+      sincos(ra, &sn, &cs);
+      float sumdx = (float)cs, sumdy = (float)sn;
+      int nxt = seed;
+      __syncwarp();
+#pragma unroll 1
+      for (int i = 0; i < n; i++) {
+        const int p = nxt;
+        const int n_start = n;
+        const int py = p / w, px = p - py * w;
+        const int yy = py + ndy, xx = px + ndx;
+        const bool in = nlane && yy >= 0 && yy < h && xx >= 0 && xx < w;
+        const int q = yy * w + xx;
+        uint32_t st = kUsed;
+        PxA pa; pa.ang = kNotDef; pa.c = 0.f; pa.s = 0.f;
+        if (in) { st = ld_state(T.state + q); pa = T.px[q]; }
+        if (i + 1 < n_start) nxt = reg[i + 1];
+        const bool cand = in && !(st & kUsed) && pa.ang != kNotDef;
+        uint32_t remaining = __ballot_sync(0xffffffffu, cand);
+        while (remaining) {
+          const bool al = ((remaining >> lane) & 1u) && aligned_angle(pa.ang, ra, prec);
+          const uint32_t m = __ballot_sync(0xffffffffu, al);
+          if (!m) break;
+          const int k = __ffs(m) - 1;                     // first aligned neighbour in scan order
+          const int qk = __shfl_sync(0xffffffffu, q, k);
+          const float ck = __shfl_sync(0xffffffffu, pa.c, k), sk = __shfl_sync(0xffffffffu, pa.s, k);
+          if (lane == 0) { T.state[qk] = kUsed; reg[n] = qk; }
+          if (n == i + 1) nxt = qk;
+          n++;
+          const int qy = qk / w, qx = qk - qy * w;
+          bx0 = min(bx0, qx); bx1 = max(bx1, qx); by0 = min(by0, qy); by1 = max(by1, qy);
+          sumdx = __fadd_rn(sumdx, ck);
+          sumdy = __fadd_rn(sumdy, sk);
+          ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
+          remaining &= ~((2u << k) - 1u);                 // earlier neighbours were already decided
+        }
+        __syncwarp();                                      // lane 0's list / state writes before the next loads
+      }
+      if (state == 0) { R.n1 = n; R.nf = n; } else { R.nf = n; }
+      if (state == 0 ? (n < T.min_reg) : (n < 2)) break;
+    } else {
+      // ---------------- one pass of reduce_region_radius (rare; order-dependent swap removal, done uniformly) ----------------
+      rad_sq *= 0.75 * 0.75;
+      for (int i = 0; i < n; ++i) {
+        const int q = reg[i];
+        if (dist_sq((double)sx, (double)sy, (double)(q % w), (double)(q / w)) > rad_sq) {
+          const int last = reg[n - 1];
+          __syncwarp();
+          if (lane == 0) { T.state[q] = 0; reg[i] = last; reg[n - 1] = q; }
+          __syncwarp();
+          --n;
+          --i;
+        }
+      }
+      R.nf = n;
+      if (n < 2) break;
+    }
+    // ---------------- region2rect (with get_theta), 32 elements per step ----------------
+    double x = 0, y = 0, sum = 0;
+    for (int b = 0; b < n; b += 32) {
+      const int e = b + lane;
+      double wgt = 0, qxw = 0, qyw = 0;
+      if (e < n) {
+        const int q = reg[e];
+        const int qy = q / w, qx = q - qy * w;
+        wgt = modgrad_of(T.g2[q]);
+        qxw = (double)qx * wgt; qyw = (double)qy * wgt;
+      }
+      const int m = min(32, n - b);
+      for (int j = 0; j < m; j++) { x += shfl_d(qxw, j); y += shfl_d(qyw, j); sum += shfl_d(wgt, j); }
+    }
+    x /= sum; y /= sum;
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int b = 0; b < n; b += 32) {
+      const int e = b + lane;
+      double t0 = 0, t1 = 0, t2 = 0;
+      if (e < n) {
+        const int q = reg[e];
+        const int qy = q / w, qx = q - qy * w;
+        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[q]);
+        t0 = dy * dy * wgt; t1 = dx * dx * wgt; t2 = dx * dy * wgt;
+      }
+      const int m = min(32, n - b);
+      for (int j = 0; j < m; j++) { Ixx += shfl_d(t0, j); Iyy += shfl_d(t1, j); Ixy -= shfl_d(t2, j); }
+    }
+    const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
+                                           : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+    theta *= kDegToRad;
+    if (angle_diff(theta, ra) > T.prec) theta += kPI;
+    double dy_, dx_;
+    sincos(theta, &dy_, &dx_);
+    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;      // min / max are order-independent: plain warp reductions
+    for (int e = lane; e < n; e += 32) {
+      const int q = reg[e];
+      const int qy = q / w, qx = q - qy * w;
+      const double rdx = (double)qx - x, rdy = (double)qy - y;
+      const double l = rdx * dx_ + rdy * dy_;
+      const double ww = -rdx * dy_ + rdy * dx_;
+      l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+      w_max = fmax(w_max, ww); w_min = fmin(w_min, ww);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      l_max = fmax(l_max, shfl_d(l_max, lane ^ o)); l_min = fmin(l_min, shfl_d(l_min, lane ^ o));
+      w_max = fmax(w_max, shfl_d(w_max, lane ^ o)); w_min = fmin(w_min, shfl_d(w_min, lane ^ o));
+    }
+    {
+      Rect& rec = R.rec;
+      rec.x1 = x + l_min * dx_; rec.y1 = y + l_min * dy_;
+      rec.x2 = x + l_max * dx_; rec.y2 = y + l_max * dy_;
+      rec.width = w_max - w_min;
+      rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx_; rec.dy = dy_; rec.prec = T.prec; rec.p = T.p;
+      if (rec.width < 1.0) rec.width = 1.0;
+    }
+    const double density = (double)n / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
+    if (state == 0) {
+      if (T.refine <= 0 || density >= T.density_th) { R.has_rect = 1; break; }
+      // ---------------- refine: un-mark, tolerance from the angle spread near the seed ----------------
+      double sm = 0, s_sum = 0;
+      int cnt = 0;
+      for (int b = 0; b < n; b += 32) {
+        const int e = b + lane;
+        double d = 0; int use = 0;
+        if (e < n) {
+          const int q = reg[e];
+          T.state[q] = 0;
+          if (dist((double)sx, (double)sy, (double)(q % w), (double)(q / w)) < R.rec.width) { d = angle_diff_signed(T.px[q].ang, seed_ang); use = 1; }
+        }
+        const uint32_t um = __ballot_sync(0xffffffffu, use);
+        const int m = min(32, n - b);
+        for (int j = 0; j < m; j++) {
+          if ((um >> j) & 1u) { const double dj = shfl_d(d, j); sm += dj; s_sum += dj * dj; ++cnt; }
+        }
+      }
+      const double mean_angle = sm / (double)cnt;
+      prec = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sm) / (double)cnt + mean_angle * mean_angle);
+      __syncwarp();
+      state = 1;
+      continue;
+    }
+    if (density >= T.density_th) { R.has_rect = 1; break; }
+    if (state == 1) {
+      const double r1 = dist_sq((double)sx, (double)sy, R.rec.x1, R.rec.y1), r2 = dist_sq((double)sx, (double)sy, R.rec.x2, R.rec.y2);
+      rad_sq = r1 > r2 ? r1 : r2;
+      state = 2;
+    }
+  }
+  R.bx0 = bx0; R.bx1 = bx1; R.by0 = by0; R.by1 = by1;
+  __syncwarp();
+}
+
 __device__ void grow_task_block(const Task& T, BlockShared& S) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NW = blockDim.x >> 5, K = blockDim.x;
@@ -664,16 +850,22 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
       n_round++;
       long long cr = clock64();
       const bool run_spec = kstar < 0 && tid < nsel;
-      bool run_seq = kstar >= 0 && tid == kstar;
-      // the commits of the previous round may have taken kstar's seed: then the sequential algorithm skips it
-      if (run_seq && (ld_state(T.state + my_seed) & kUsed)) { run_seq = false; retired = true; S.rb[0] = 1; S.rb[2] = 0; }
-      if (run_spec || run_seq) {
-        process_seed_u(T, my_seed, run_seq ? T.reg_serial : my_reg, run_seq ? T.npx : cap, stamp, run_spec, R);
-        if (run_seq) {
-          if (R.has_rect) { append_rect(T, S.npend, R.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, R.nf); S.has = 1; }
-          S.rb[0] = R.bx0; S.rb[1] = R.by0; S.rb[2] = R.bx1; S.rb[3] = R.by1;
-          retired = true;
-        }
+      if (run_spec) process_seed_u(T, my_seed, my_reg, cap, stamp, true, R);
+      if (kstar >= 0 && warp == (kstar >> 5)) {
+        // the whole warp of kstar re-runs that seed sequentially (warp-cooperative, exact sequential semantics).  The
+        // commits of the previous round may have taken the seed: then the sequential algorithm skips it
+        const int ks_lane = kstar & 31;
+        const int seed_k = __shfl_sync(0xffffffffu, my_seed, ks_lane);
+        const bool taken = (ld_state(T.state + seed_k) & kUsed) != 0;
+        if (!taken) {
+          SeedResult Q;
+          process_seed_coop(T, seed_k, T.reg_serial, Q);
+          if (lane == ks_lane) {
+            if (Q.has_rect) { append_rect(T, S.npend, Q.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, Q.nf); S.has = 1; }
+            S.rb[0] = Q.bx0; S.rb[1] = Q.by0; S.rb[2] = Q.bx1; S.rb[3] = Q.by1;
+          }
+        } else if (lane == ks_lane) { S.rb[0] = 1; S.rb[2] = 0; }
+        if (lane == ks_lane) retired = true;
       }
       __syncthreads();
       if (kstar < 0) { c2 = clock64(); t_spec += c2 - c1; }
