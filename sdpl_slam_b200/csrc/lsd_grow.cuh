@@ -442,6 +442,46 @@ struct BlockShared {
   int rb[4];                    // bounding box written by the last re-run
 };
 
+
+// The block kernel keeps region lists as packed coordinates (y << 16 | x) instead of linear indices: no integer division
+// by the (run-time) image width anywhere in the per-pixel loops.
+__device__ __forceinline__ int xy_pack(int x, int y) { return (y << 16) | x; }
+__device__ __forceinline__ int xy_x(int v) { return v & 0xffff; }
+__device__ __forceinline__ int xy_y(int v) { return (int)((unsigned)v >> 16); }
+__device__ __forceinline__ int xy_lin(int v, int w) { return xy_y(v) * w + xy_x(v); }
+
+__device__ __forceinline__ bool owns_all_xy(const Task& T, const int* list, int n, uint32_t key) {
+  const int w = T.w;
+  int ok = 1, i = 0;
+  for (; i + 4 <= n && ok; i += 4) {
+    const int q0 = xy_lin(list[i], w), q1 = xy_lin(list[i + 1], w), q2 = xy_lin(list[i + 2], w), q3 = xy_lin(list[i + 3], w);
+    const uint32_t s0 = ld_state(T.state + q0), s1 = ld_state(T.state + q1), s2 = ld_state(T.state + q2), s3 = ld_state(T.state + q3);
+    ok = ((s0 >> 1) == key) & ((s1 >> 1) == key) & ((s2 >> 1) == key) & ((s3 >> 1) == key);
+  }
+  for (; i < n && ok; i++) ok = (ld_state(T.state + xy_lin(list[i], w)) >> 1) == key;
+  return ok != 0;
+}
+__device__ __forceinline__ void mark_used_coop_xy(const Task& T, bool active, const int* list, int n) {
+  const int lane = threadIdx.x & 31, w = T.w;
+  uint32_t longm = __ballot_sync(0xffffffffu, active && n > 32);
+  while (longm) {
+    const int src = __ffs(longm) - 1;
+    longm &= longm - 1;
+    const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(size_t)list, src);
+    const int m = __shfl_sync(0xffffffffu, n, src);
+    const int* l = (const int*)(size_t)p;
+    for (int i = lane; i < m; i += 32) T.state[xy_lin(l[i], w)] = kUsed;
+  }
+  if (active && n <= 32) {
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+      const int q0 = xy_lin(list[i], w), q1 = xy_lin(list[i + 1], w), q2 = xy_lin(list[i + 2], w), q3 = xy_lin(list[i + 3], w);
+      T.state[q0] = kUsed; T.state[q1] = kUsed; T.state[q2] = kUsed; T.state[q3] = kUsed;
+    }
+    for (; i < n; i++) T.state[xy_lin(list[i], w)] = kUsed;
+  }
+}
+
 // Compact single-copy version of the per-seed pipeline for the block kernel: growth, rectangle fit and the refine state
 // machine each appear ONCE in the instruction stream (the templated process_seed<> above expands to two growths and three
 // rectangle fits per instantiation; with both instantiations inlined the kernel was 315 KB of SASS and instruction-fetch
@@ -469,18 +509,18 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
       } else {
         T.state[seed] = kUsed;
       }
-      cur[0] = seed; n = 1;
+      cur[0] = xy_pack(sx, sy); n = 1;
       ra = seed_ang;
       double sn, cs;
       sincos(ra, &sn, &cs);
       float sumdx = (float)cs, sumdy = (float)sn;
-      int nxt = seed;
+      int nxt = xy_pack(sx, sy);
       bool aborted = false;
 #pragma unroll 1
       for (int i = 0; i < n && !aborted; i++) {
         const int p = nxt;
         const int n_start = n;
-        const int py = p / w, px = p - py * w;
+        const int py = xy_y(p), px = xy_x(p);
         uint32_t st[9];
         PxA pa[9];
 #pragma unroll
@@ -506,8 +546,9 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
           } else {
             T.state[q] = kUsed;
           }
-          if (n == i + 1) nxt = q;
-          cur[n++] = q;
+          const int qp = xy_pack(px - 1 + k % 3, py - 1 + k / 3);
+          if (n == i + 1) nxt = qp;
+          cur[n++] = qp;
           R.bx0 = min(R.bx0, px - 1 + k % 3); R.bx1 = max(R.bx1, px - 1 + k % 3);
           R.by0 = min(R.by0, py - 1 + k / 3); R.by1 = max(R.by1, py - 1 + k / 3);
           sumdx = __fadd_rn(sumdx, pa[k].c);
@@ -523,8 +564,8 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
       rad_sq *= 0.75 * 0.75;
       for (int i = 0; i < n; ++i) {
         const int q = cur[i];
-        if (dist_sq((double)sx, (double)sy, (double)(q % w), (double)(q / w)) > rad_sq) {
-          if (!spec) T.state[q] = 0;
+        if (dist_sq((double)sx, (double)sy, (double)xy_x(q), (double)xy_y(q)) > rad_sq) {
+          if (!spec) T.state[xy_lin(q, w)] = 0;
           cur[i] = cur[n - 1];
           cur[n - 1] = q;
           --n;
@@ -539,8 +580,8 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
       double x = 0, y = 0, sum = 0;
       for (int i = 0; i < n; ++i) {
         const int q = cur[i];
-        const int qy = q / w, qx = q - qy * w;
-        const double wgt = modgrad_of(T.g2[q]);
+        const int qy = xy_y(q), qx = xy_x(q);
+        const double wgt = modgrad_of(T.g2[qy * w + qx]);
         x += (double)qx * wgt;
         y += (double)qy * wgt;
         sum += wgt;
@@ -549,8 +590,8 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
       double Ixx = 0, Iyy = 0, Ixy = 0;
       for (int i = 0; i < n; ++i) {
         const int q = cur[i];
-        const int qy = q / w, qx = q - qy * w;
-        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[q]);
+        const int qy = xy_y(q), qx = xy_x(q);
+        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[qy * w + qx]);
         Ixx += dy * dy * wgt;
         Iyy += dx * dx * wgt;
         Ixy -= dx * dy * wgt;
@@ -565,7 +606,7 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
       double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
       for (int i = 0; i < n; ++i) {
         const int q = cur[i];
-        const int qy = q / w, qx = q - qy * w;
+        const int qy = xy_y(q), qx = xy_x(q);
         const double rdx = (double)qx - x, rdy = (double)qy - y;
         const double l = rdx * dx_ + rdy * dy_;
         const double ww = -rdx * dy_ + rdy * dx_;
@@ -586,9 +627,10 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
       double sum = 0, s_sum = 0;
       int cnt = 0;
       for (int i = 0; i < n; ++i) {
-        const int q = cur[i];
+        const int qp = cur[i];
+        const int q = xy_lin(qp, w);
         if (!spec) T.state[q] = 0;
-        if (dist((double)sx, (double)sy, (double)(q % w), (double)(q / w)) < R.rec.width) {
+        if (dist((double)sx, (double)sy, (double)xy_x(qp), (double)xy_y(qp)) < R.rec.width) {
           const double d = angle_diff_signed(T.px[q].ang, seed_ang);
           sum += d;
           s_sum += d * d;
@@ -641,19 +683,19 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
   while (true) {
     if (state <= 1) {
       // ---------------- region_grow ----------------
-      if (lane == 0) { T.state[seed] = kUsed; reg[0] = seed; }
+      if (lane == 0) { T.state[seed] = kUsed; reg[0] = xy_pack(sx, sy); }
       n = 1;
       ra = seed_ang;
       double sn, cs;
       sincos(ra, &sn, &cs);
       float sumdx = (float)cs, sumdy = (float)sn;
-      int nxt = seed;
+      int nxt = xy_pack(sx, sy);
       __syncwarp();
 #pragma unroll 1
       for (int i = 0; i < n; i++) {
         const int p = nxt;
         const int n_start = n;
-        const int py = p / w, px = p - py * w;
+        const int py = xy_y(p), px = xy_x(p);
         const int yy = py + ndy, xx = px + ndx;
         const bool in = nlane && yy >= 0 && yy < h && xx >= 0 && xx < w;
         const int q = yy * w + xx;
@@ -669,11 +711,11 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
           if (!m) break;
           const int k = __ffs(m) - 1;                     // first aligned neighbour in scan order
           const int qk = __shfl_sync(0xffffffffu, q, k);
+          const int qx = __shfl_sync(0xffffffffu, xx, k), qy = __shfl_sync(0xffffffffu, yy, k);
           const float ck = __shfl_sync(0xffffffffu, pa.c, k), sk = __shfl_sync(0xffffffffu, pa.s, k);
-          if (lane == 0) { T.state[qk] = kUsed; reg[n] = qk; }
-          if (n == i + 1) nxt = qk;
+          if (lane == 0) { T.state[qk] = kUsed; reg[n] = xy_pack(qx, qy); }
+          if (n == i + 1) nxt = xy_pack(qx, qy);
           n++;
-          const int qy = qk / w, qx = qk - qy * w;
           bx0 = min(bx0, qx); bx1 = max(bx1, qx); by0 = min(by0, qy); by1 = max(by1, qy);
           sumdx = __fadd_rn(sumdx, ck);
           sumdy = __fadd_rn(sumdy, sk);
@@ -689,10 +731,10 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
       rad_sq *= 0.75 * 0.75;
       for (int i = 0; i < n; ++i) {
         const int q = reg[i];
-        if (dist_sq((double)sx, (double)sy, (double)(q % w), (double)(q / w)) > rad_sq) {
+        if (dist_sq((double)sx, (double)sy, (double)xy_x(q), (double)xy_y(q)) > rad_sq) {
           const int last = reg[n - 1];
           __syncwarp();
-          if (lane == 0) { T.state[q] = 0; reg[i] = last; reg[n - 1] = q; }
+          if (lane == 0) { T.state[xy_lin(q, w)] = 0; reg[i] = last; reg[n - 1] = q; }
           __syncwarp();
           --n;
           --i;
@@ -708,8 +750,8 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
       double wgt = 0, qxw = 0, qyw = 0;
       if (e < n) {
         const int q = reg[e];
-        const int qy = q / w, qx = q - qy * w;
-        wgt = modgrad_of(T.g2[q]);
+        const int qy = xy_y(q), qx = xy_x(q);
+        wgt = modgrad_of(T.g2[qy * w + qx]);
         qxw = (double)qx * wgt; qyw = (double)qy * wgt;
       }
       const int m = min(32, n - b);
@@ -722,8 +764,8 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
       double t0 = 0, t1 = 0, t2 = 0;
       if (e < n) {
         const int q = reg[e];
-        const int qy = q / w, qx = q - qy * w;
-        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[q]);
+        const int qy = xy_y(q), qx = xy_x(q);
+        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[qy * w + qx]);
         t0 = dy * dy * wgt; t1 = dx * dx * wgt; t2 = dx * dy * wgt;
       }
       const int m = min(32, n - b);
@@ -739,7 +781,7 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;      // min / max are order-independent: plain warp reductions
     for (int e = lane; e < n; e += 32) {
       const int q = reg[e];
-      const int qy = q / w, qx = q - qy * w;
+      const int qy = xy_y(q), qx = xy_x(q);
       const double rdx = (double)qx - x, rdy = (double)qy - y;
       const double l = rdx * dx_ + rdy * dy_;
       const double ww = -rdx * dy_ + rdy * dx_;
@@ -769,9 +811,10 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
         const int e = b + lane;
         double d = 0; int use = 0;
         if (e < n) {
-          const int q = reg[e];
+          const int qp = reg[e];
+          const int q = xy_lin(qp, w);
           T.state[q] = 0;
-          if (dist((double)sx, (double)sy, (double)(q % w), (double)(q / w)) < R.rec.width) { d = angle_diff_signed(T.px[q].ang, seed_ang); use = 1; }
+          if (dist((double)sx, (double)sy, (double)xy_x(qp), (double)xy_y(qp)) < R.rec.width) { d = angle_diff_signed(T.px[q].ang, seed_ang); use = 1; }
         }
         const uint32_t um = __ballot_sync(0xffffffffu, use);
         const int m = min(32, n - b);
@@ -883,7 +926,7 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
       if (mine) {
         if (verdict == 0) {
           dead = (ld_state(T.state + my_seed) & kUsed) != 0;
-          if (!dead && R.ok) good = owns_all(T, my_reg, R.n1 + R.n2_orig, stamp >> 1);
+          if (!dead && R.ok) good = owns_all_xy(T, my_reg, R.n1 + R.n2_orig, stamp >> 1);
           verdict = dead ? 2 : (good ? 1 : 3);
         } else if (verdict == 3) {
           // lost a pixel (or never finished): that is permanent; only "my seed was taken meanwhile" can still change
@@ -908,7 +951,7 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
       const bool below = tid < ks;
       const bool do_commit = mine && good && below;
       const bool do_drop = mine && dead && below;
-      mark_used_coop(T, do_commit, my_reg + R.foff, R.nf);
+      mark_used_coop_xy(T, do_commit, my_reg + R.foff, R.nf);
       if (do_commit || do_drop) retired = true;
       const uint32_t rm = __ballot_sync(0xffffffffu, do_commit && R.has_rect);
       if (lane == 0) S.rectm[warp] = rm;
