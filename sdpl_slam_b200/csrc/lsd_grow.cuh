@@ -532,28 +532,45 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
           if (in) pa[k] = T.px[q]; else pa[k].ang = kNotDef;
         }
         if (i + 1 < n_start) nxt = cur[i + 1];
+        // candidates: in bounds, defined, not committed, not already mine.  The reference tests the neighbours one after
+        // the other against the running region angle; a neighbour that fails is not looked at again, one that joins changes
+        // the angle for the LATER neighbours only.  So: test all remaining candidates at once (independent chains), take the
+        // first aligned one in scan order, update the angle, re-test only the neighbours behind it.
+        uint32_t cand = 0;
 #pragma unroll
         for (int k = 0; k < 9; k++) {
-          if (k == 4 || aborted) continue;
-          const uint32_t s = st[k];
-          if (s & kUsed) continue;
-          if (spec && s == stamp) continue;
-          if (!aligned_angle(pa[k].ang, ra, prec)) continue;
-          const int q = (py - 1 + k / 3) * w + (px - 1 + k % 3);
-          if (spec) {
-            if (s > stamp || n >= capc) { aborted = true; continue; }
-            atomicMax(&T.state[q], stamp);
-          } else {
-            T.state[q] = kUsed;
+          if (k == 4) continue;
+          const uint32_t sv = st[k];
+          if (!(sv & kUsed) && !(spec && sv == stamp) && pa[k].ang != kNotDef) cand |= 1u << k;
+        }
+        while (cand) {
+          uint32_t al = 0;
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            if (k == 4) continue;
+            if ((cand >> k) & 1u) al |= (aligned_angle(pa[k].ang, ra, prec) ? 1u : 0u) << k;
           }
-          const int qp = xy_pack(px - 1 + k % 3, py - 1 + k / 3);
+          if (!al) break;
+          const int k = __ffs(al) - 1;
+          uint32_t sk = 0; float ck = 0.f, sn_k = 0.f;
+#pragma unroll
+          for (int j = 0; j < 9; j++) if (j == k) { sk = st[j]; ck = pa[j].c; sn_k = pa[j].s; }
+          const int qx = px - 1 + k % 3, qy = py - 1 + k / 3;
+          if (spec) {
+            if (sk > stamp || n >= capc) { aborted = true; break; }
+            atomicMax(&T.state[qy * w + qx], stamp);
+          } else {
+            T.state[qy * w + qx] = kUsed;
+          }
+          const int qp = xy_pack(qx, qy);
           if (n == i + 1) nxt = qp;
           cur[n++] = qp;
-          R.bx0 = min(R.bx0, px - 1 + k % 3); R.bx1 = max(R.bx1, px - 1 + k % 3);
-          R.by0 = min(R.by0, py - 1 + k / 3); R.by1 = max(R.by1, py - 1 + k / 3);
-          sumdx = __fadd_rn(sumdx, pa[k].c);
-          sumdy = __fadd_rn(sumdy, pa[k].s);
+          R.bx0 = min(R.bx0, qx); R.bx1 = max(R.bx1, qx);
+          R.by0 = min(R.by0, qy); R.by1 = max(R.by1, qy);
+          sumdx = __fadd_rn(sumdx, ck);
+          sumdy = __fadd_rn(sumdy, sn_k);
           ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
+          cand &= ~((2u << k) - 1u);
         }
       }
       if (state == 0) { R.n1 = n; R.nf = n; } else { R.n2_orig = spec ? n : 0; R.nf = n; }
