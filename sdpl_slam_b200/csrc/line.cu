@@ -124,23 +124,25 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineDev D, int o) {
   const int by0 = O.ey_ofs[oy0], by1 = min(O.ey_ofs[oy1] + 1, O.h - 1);
   const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;      // <= 82 x 22
   const int iw = bw + 6, ih = bh + 6;
-  for (int i = threadIdx.x; i < iw * ih; i += 256) {
-    const int yy = i / iw, xx = i - yy * iw;
-    in[yy][xx] = src[(size_t)reflect101(by0 - 3 + yy, O.h) * sstride + reflect101(bx0 - 3 + xx, O.w)];
+  // one warp per row, lanes over columns: no integer division by the (run-time) tile width
+  const int wr = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  for (int yy = wr; yy < ih; yy += 8) {
+    const uint8_t* srow = src + (size_t)reflect101(by0 - 3 + yy, O.h) * sstride;
+    for (int xx = ln; xx < iw; xx += 32) in[yy][xx] = srow[reflect101(bx0 - 3 + xx, O.w)];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < bw * ih; i += 256) {
-    const int yy = i / bw, xx = i - yy * bw;
-    const uint8_t* p = &in[yy][xx];
-    hz[yy][xx] = (unsigned short)(4 * (p[1] + p[5]) + 56 * (p[2] + p[4]) + 136 * p[3]);
-  }
+  for (int yy = wr; yy < ih; yy += 8)
+    for (int xx = ln; xx < bw; xx += 32) {
+      const uint8_t* p = &in[yy][xx];
+      hz[yy][xx] = (unsigned short)(4 * (p[1] + p[5]) + 56 * (p[2] + p[4]) + 136 * p[3]);
+    }
   __syncthreads();
-  for (int i = threadIdx.x; i < bw * bh; i += 256) {
-    const int yy = i / bw, xx = i - yy * bw;
-    const uint32_t v = 4u * ((uint32_t)hz[yy + 1][xx] + hz[yy + 5][xx]) + 56u * ((uint32_t)hz[yy + 2][xx] + hz[yy + 4][xx]) +
-                       136u * (uint32_t)hz[yy + 3][xx];
-    bl[yy][xx] = (uint8_t)min(255u, (v + (1u << 15)) >> 16);
-  }
+  for (int yy = wr; yy < bh; yy += 8)
+    for (int xx = ln; xx < bw; xx += 32) {
+      const uint32_t v = 4u * ((uint32_t)hz[yy + 1][xx] + hz[yy + 5][xx]) + 56u * ((uint32_t)hz[yy + 2][xx] + hz[yy + 4][xx]) +
+                         136u * (uint32_t)hz[yy + 3][xx];
+      bl[yy][xx] = (uint8_t)min(255u, (v + (1u << 15)) >> 16);
+    }
   __syncthreads();
   uint8_t* dst = D.scaled + (size_t)blockIdx.z * D.px_frame + O.px_off;
   for (int i = threadIdx.x; i < kST_W * kST_H; i += 256) {

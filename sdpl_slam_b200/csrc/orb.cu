@@ -242,11 +242,16 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
   const uint8_t* sc = D.score + (size_t)f * D.s_frame + L.s_off;
   uint8_t* s = sm[warp];
   const int aw = iw + 2, ah = ih + 2;
-  for (int i = lane; i < aw * ah; i += 32) {
-    int yy = i / aw, xx = i - yy * aw;
-    uint8_t v = 0;
-    if (yy >= 1 && yy <= ih && xx >= 1 && xx <= iw) v = sc[(size_t)(iy0 + yy - 1) * L.sstride + ix0 + xx - 1];
-    s[i] = v;
+  // (row, column) of the linear index advance incrementally: no integer division by the run-time cell width
+  {
+    int yy = lane / aw, xx = lane - yy * aw;
+    for (int i = lane; i < aw * ah; i += 32) {
+      uint8_t v = 0;
+      if (yy >= 1 && yy <= ih && xx >= 1 && xx <= iw) v = sc[(size_t)(iy0 + yy - 1) * L.sstride + ix0 + xx - 1];
+      s[i] = v;
+      xx += 32;
+      while (xx >= aw) { xx -= aw; yy++; }
+    }
   }
   __syncwarp();
   int th = D.ini_th;
@@ -265,11 +270,11 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
   uint32_t* oxy = D.cand_xy + (size_t)f * D.cand_per_frame + L.cand_off;
   uint8_t* ors = D.cand_resp + (size_t)f * D.cand_per_frame + L.cand_off;
   const int npx = iw * ih;
+  int yy = lane / iw, xx = lane - yy * iw;
   for (int i0 = 0; i0 < npx; i0 += 32) {
     int i = i0 + lane;
-    bool ismax = false; int v = 0, xx = 0, yy = 0;
+    bool ismax = false; int v = 0;
     if (i < npx) {
-      yy = i / iw; xx = i - yy * iw;
       const uint8_t* p = s + (yy + 1) * aw + xx + 1;
       v = p[0];
       ismax = v > 0 && v > p[-1] && v > p[1] && v > p[-aw - 1] && v > p[-aw] && v > p[-aw + 1] && v > p[aw - 1] &&
@@ -294,6 +299,8 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
       }
       base += __popc(m);
     }
+    xx += 32;
+    while (xx >= iw) { xx -= iw; yy++; }
   }
   if (!WRITE && lane == 0) {
     int t = cnt_hi > 0 ? D.ini_th : D.min_th;
