@@ -153,6 +153,9 @@ int sdpl_matcher_last_launches(const sdpl_matcher* h);
  * SDPL_OK, or SDPL_ERR_OVERFLOW when an internal buffer (FAST candidates, quadtree nodes, pending rectangles) overflowed. */
 int sdpl_orb_check(sdpl_orb* h);
 int sdpl_line_check(sdpl_line* h);
+/* the same flag copied to *host_flag (pinned host memory) on `stream` without synchronising or clearing; sticky */
+int sdpl_orb_peek_error_async(sdpl_orb* h, void* stream, int* host_flag);
+int sdpl_line_peek_error_async(sdpl_line* h, void* stream, int* host_flag);
 
 /* ------------------------------------------------------------------------------------------------
  * The whole per-frame front-end in one call: Frame::Frame's ExtractORB + ExtractLines (src/Frame.cc:314,328 -> :927-949)
@@ -175,6 +178,14 @@ int sdpl_frontend_reset(sdpl_frontend* h);
 int sdpl_frontend_process(sdpl_frontend* h, const uint8_t* imgs, int nframes, int w, int h_, int stride, size_t frame_stride,
                           sdpl_keypoint* kps, uint8_t* desc, sdpl_keyline* kls, uint8_t* ldesc, sdpl_dmatch* pt_matches,
                           sdpl_dmatch* ln_matches, sdpl_frame_stats* stats);
+/* Pipelined form: submit enqueues a batch (upload, both pipelines, matching) and returns at once -- `imgs` must stay valid
+ * until that batch is collected; collect waits for the OLDEST submitted batch and copies its results to the host on a
+ * separate stream, overlapping the kernels of a batch submitted after it.  At most two batches in flight.
+ * process == submit + collect. */
+int sdpl_frontend_submit(sdpl_frontend* h, const uint8_t* imgs, int nframes, int w, int h_, int stride, size_t frame_stride);
+int sdpl_frontend_collect(sdpl_frontend* h, sdpl_keypoint* kps, uint8_t* desc, sdpl_keyline* kls, uint8_t* ldesc, sdpl_dmatch* pt_matches,
+                          sdpl_dmatch* ln_matches, sdpl_frame_stats* stats, int* n_frames);
+int sdpl_frontend_pending(const sdpl_frontend* h);
 int sdpl_frontend_last_launches(const sdpl_frontend* h);
 
 /* Per-stage device timing (CUDA events on the handle's stream).  set_profiling(1) makes every following call record

@@ -13,6 +13,15 @@
 
 using namespace sdpl;
 
+struct FeSlot {
+  // device buffers hold nframes+1 descriptor blocks: block 0 = last frame of the previous batch
+  DevBuf imgs, kps, desc, nkp, kls, ldesc, nkl, pbest, psecond, pout, pacc, lbest, lsecond, lout, lacc;
+  cudaEvent_t ev_in = nullptr, ev_orb = nullptr, ev_line = nullptr, ev_pm = nullptr, ev_lm = nullptr;
+  int* hn = nullptr; size_t hn_bytes = 0;     // pinned: [4][n] counts + 2 error flags
+  int n = 0, w = 0, h = 0;
+  bool busy = false;
+};
+
 struct sdpl_frontend {
   int device = 0;
   sdpl_orb* orb = nullptr;
@@ -21,34 +30,39 @@ struct sdpl_frontend {
   sdpl_matcher* lm = nullptr;
   float ratio = 0.8f; int max_dist = 64;
   int kp_cap = 0, kl_cap = 0;
-  cudaStream_t s_io = nullptr, s_orb = nullptr, s_line = nullptr, s_pm = nullptr, s_lm = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_orb = nullptr, ev_line = nullptr, ev_pm = nullptr, ev_lm = nullptr;
-  // device buffers hold nframes+1 descriptor blocks: slot 0 = last frame of the previous call
-  DevBuf d_imgs, d_kps, d_desc, d_nkp, d_kls, d_ldesc, d_nkl, d_pbest, d_psecond, d_pout, d_pacc, d_lbest, d_lsecond, d_lout, d_lacc;
-  void* h_stage = nullptr; size_t h_stage_bytes = 0;
+  cudaStream_t s_io = nullptr, s_orb = nullptr, s_line = nullptr, s_pm = nullptr, s_lm = nullptr, s_out = nullptr;
+  FeSlot slot[2];
+  int head = 0, count = 0, next = 0;     // FIFO of submitted batches
+  int last = -1;                         // slot of the most recently submitted batch (source of the "previous frame")
   int have_prev = 0;
   int launches = 0;
-  int cap_frames = 0;
 };
 
-static int fe_reserve(sdpl_frontend* f, int n, int w, int h) {
+static int fe_reserve(sdpl_frontend* f, FeSlot& S, int n, int w, int h) {
   int rc;
   const size_t N1 = (size_t)n + 1;
-  if ((rc = f->d_imgs.reserve((size_t)w * h * n))) return rc;
-  if ((rc = f->d_kps.reserve(sizeof(sdpl_keypoint) * f->kp_cap * N1))) return rc;
-  if ((rc = f->d_desc.reserve((size_t)32 * f->kp_cap * N1))) return rc;
-  if ((rc = f->d_nkp.reserve(sizeof(int) * N1))) return rc;
-  if ((rc = f->d_kls.reserve(sizeof(sdpl_keyline) * f->kl_cap * N1))) return rc;
-  if ((rc = f->d_ldesc.reserve((size_t)32 * f->kl_cap * N1))) return rc;
-  if ((rc = f->d_nkl.reserve(sizeof(int) * N1))) return rc;
-  if ((rc = f->d_pbest.reserve(sizeof(sdpl_dmatch) * f->kp_cap * N1))) return rc;
-  if ((rc = f->d_psecond.reserve(sizeof(sdpl_dmatch) * f->kp_cap * N1))) return rc;
-  if ((rc = f->d_pout.reserve(sizeof(sdpl_dmatch) * f->kp_cap * N1))) return rc;
-  if ((rc = f->d_pacc.reserve(sizeof(int) * N1))) return rc;
-  if ((rc = f->d_lbest.reserve(sizeof(sdpl_dmatch) * f->kl_cap * N1))) return rc;
-  if ((rc = f->d_lsecond.reserve(sizeof(sdpl_dmatch) * f->kl_cap * N1))) return rc;
-  if ((rc = f->d_lout.reserve(sizeof(sdpl_dmatch) * f->kl_cap * N1))) return rc;
-  if ((rc = f->d_lacc.reserve(sizeof(int) * N1))) return rc;
+  if ((rc = S.imgs.reserve((size_t)w * h * n))) return rc;
+  if ((rc = S.kps.reserve(sizeof(sdpl_keypoint) * f->kp_cap * N1))) return rc;
+  if ((rc = S.desc.reserve((size_t)32 * f->kp_cap * N1))) return rc;
+  if ((rc = S.nkp.reserve(sizeof(int) * N1))) return rc;
+  if ((rc = S.kls.reserve(sizeof(sdpl_keyline) * f->kl_cap * N1))) return rc;
+  if ((rc = S.ldesc.reserve((size_t)32 * f->kl_cap * N1))) return rc;
+  if ((rc = S.nkl.reserve(sizeof(int) * N1))) return rc;
+  if ((rc = S.pbest.reserve(sizeof(sdpl_dmatch) * f->kp_cap * N1))) return rc;
+  if ((rc = S.psecond.reserve(sizeof(sdpl_dmatch) * f->kp_cap * N1))) return rc;
+  if ((rc = S.pout.reserve(sizeof(sdpl_dmatch) * f->kp_cap * N1))) return rc;
+  if ((rc = S.pacc.reserve(sizeof(int) * N1))) return rc;
+  if ((rc = S.lbest.reserve(sizeof(sdpl_dmatch) * f->kl_cap * N1))) return rc;
+  if ((rc = S.lsecond.reserve(sizeof(sdpl_dmatch) * f->kl_cap * N1))) return rc;
+  if ((rc = S.lout.reserve(sizeof(sdpl_dmatch) * f->kl_cap * N1))) return rc;
+  if ((rc = S.lacc.reserve(sizeof(int) * N1))) return rc;
+  const size_t need = sizeof(int) * (4 * (size_t)n + 2);
+  if (S.hn_bytes < need) {
+    if (S.hn) cudaFreeHost(S.hn);
+    S.hn = nullptr; S.hn_bytes = 0;
+    SDPL_CUDA(cudaMallocHost((void**)&S.hn, need));
+    S.hn_bytes = need;
+  }
   return SDPL_OK;
 }
 
@@ -74,10 +88,11 @@ int sdpl_frontend_create(sdpl_frontend** out, int nfeatures, float scale, int nl
     // kernels fill the SMs it leaves idle
     int lo = 0, hi = 0;
     SDPL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    for (cudaStream_t* s : {&f->s_io, &f->s_orb, &f->s_pm, &f->s_lm}) SDPL_CUDA(cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, lo));
+    for (cudaStream_t* s : {&f->s_io, &f->s_orb, &f->s_pm, &f->s_lm, &f->s_out}) SDPL_CUDA(cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, lo));
     SDPL_CUDA(cudaStreamCreateWithPriority(&f->s_line, cudaStreamNonBlocking, hi));
   }
-  for (cudaEvent_t* e : {&f->ev_in, &f->ev_orb, &f->ev_line, &f->ev_pm, &f->ev_lm}) SDPL_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (FeSlot& S : f->slot)
+    for (cudaEvent_t* e : {&S.ev_in, &S.ev_orb, &S.ev_line, &S.ev_pm, &S.ev_lm}) SDPL_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   sdpl_orb_set_stream(f->orb, f->s_orb); sdpl_line_set_stream(f->line, f->s_line);
   sdpl_matcher_set_stream(f->pm, f->s_pm); sdpl_matcher_set_stream(f->lm, f->s_lm);
   *out = f;
@@ -89,12 +104,14 @@ void sdpl_frontend_destroy(sdpl_frontend* f) {
   cudaSetDevice(f->device);
   cudaDeviceSynchronize();
   sdpl_orb_destroy(f->orb); sdpl_line_destroy(f->line); sdpl_matcher_destroy(f->pm); sdpl_matcher_destroy(f->lm);
-  for (DevBuf* b : {&f->d_imgs, &f->d_kps, &f->d_desc, &f->d_nkp, &f->d_kls, &f->d_ldesc, &f->d_nkl, &f->d_pbest, &f->d_psecond, &f->d_pout,
-                    &f->d_pacc, &f->d_lbest, &f->d_lsecond, &f->d_lout, &f->d_lacc})
-    b->release();
-  if (f->h_stage) cudaFreeHost(f->h_stage);
-  for (cudaStream_t s : {f->s_io, f->s_orb, f->s_line, f->s_pm, f->s_lm}) if (s) cudaStreamDestroy(s);
-  for (cudaEvent_t e : {f->ev_in, f->ev_orb, f->ev_line, f->ev_pm, f->ev_lm}) if (e) cudaEventDestroy(e);
+  for (FeSlot& S : f->slot) {
+    for (DevBuf* b : {&S.imgs, &S.kps, &S.desc, &S.nkp, &S.kls, &S.ldesc, &S.nkl, &S.pbest, &S.psecond, &S.pout, &S.pacc, &S.lbest, &S.lsecond,
+                      &S.lout, &S.lacc})
+      b->release();
+    if (S.hn) cudaFreeHost(S.hn);
+    for (cudaEvent_t e : {S.ev_in, S.ev_orb, S.ev_line, S.ev_pm, S.ev_lm}) if (e) cudaEventDestroy(e);
+  }
+  for (cudaStream_t s : {f->s_io, f->s_orb, f->s_line, f->s_pm, f->s_lm, f->s_out}) if (s) cudaStreamDestroy(s);
   delete f;
 }
 
@@ -105,129 +122,168 @@ int sdpl_frontend_capacities(const sdpl_frontend* f, int* kp_capacity, int* kl_c
   return SDPL_OK;
 }
 int sdpl_frontend_last_launches(const sdpl_frontend* f) { return f ? f->launches : 0; }
+int sdpl_frontend_pending(const sdpl_frontend* f) { return f ? f->count : 0; }
 int sdpl_frontend_reset(sdpl_frontend* f) { if (!f) return SDPL_ERR_ARG; f->have_prev = 0; return SDPL_OK; }
 
-int sdpl_frontend_process(sdpl_frontend* f, const uint8_t* imgs, int n, int w, int h, int stride, size_t frame_stride,
-                          sdpl_keypoint* kps, uint8_t* desc, sdpl_keyline* kls, uint8_t* ldesc, sdpl_dmatch* pt_matches,
-                          sdpl_dmatch* ln_matches, sdpl_frame_stats* stats) {
-  if (!f || !imgs || n < 1 || w < 1 || h < 1 || stride < w || !kps || !desc || !kls || !ldesc || !pt_matches || !ln_matches || !stats) {
-    set_last_error("sdpl_frontend_process: bad argument");
-    return SDPL_ERR_ARG;
-  }
+// Enqueue one batch: upload, ORB || lines, matching against the previous frame.  Returns without waiting; `imgs` must stay
+// valid until the batch has been collected.  At most two batches can be in flight.
+int sdpl_frontend_submit(sdpl_frontend* f, const uint8_t* imgs, int n, int w, int h, int stride, size_t frame_stride) {
+  if (!f || !imgs || n < 1 || w < 1 || h < 1 || stride < w) { set_last_error("sdpl_frontend_submit: bad argument"); return SDPL_ERR_ARG; }
+  if (f->count >= 2) { set_last_error("sdpl_frontend_submit: two batches already in flight, collect one first"); return SDPL_ERR_ARG; }
   SDPL_CUDA(cudaSetDevice(f->device));
+  FeSlot& S = f->slot[f->next];
   int rc;
-  if ((rc = fe_reserve(f, std::max(n, f->cap_frames), w, h))) return rc;
-  f->cap_frames = std::max(n, f->cap_frames);
+  if ((rc = fe_reserve(f, S, std::max(n, S.n), w, h))) return rc;
   const int KC = f->kp_cap, LC = f->kl_cap;
-  // slot s = frame s-1 of this call; slot 0 = previous call's last frame
-  sdpl_keypoint* dk = f->d_kps.as<sdpl_keypoint>() + KC;
-  uint8_t* dd = f->d_desc.as<uint8_t>() + (size_t)32 * KC;
-  int* dn = f->d_nkp.as<int>() + 1;
-  sdpl_keyline* dl = f->d_kls.as<sdpl_keyline>() + LC;
-  uint8_t* dld = f->d_ldesc.as<uint8_t>() + (size_t)32 * LC;
-  int* dln = f->d_nkl.as<int>() + 1;
-  if (!f->have_prev) {
-    SDPL_CUDA(cudaMemsetAsync(f->d_nkp.p, 0, sizeof(int), f->s_io));
-    SDPL_CUDA(cudaMemsetAsync(f->d_nkl.p, 0, sizeof(int), f->s_io));
+  sdpl_keypoint* dk = S.kps.as<sdpl_keypoint>() + KC;
+  uint8_t* dd = S.desc.as<uint8_t>() + (size_t)32 * KC;
+  int* dn = S.nkp.as<int>() + 1;
+  sdpl_keyline* dl = S.kls.as<sdpl_keyline>() + LC;
+  uint8_t* dld = S.ldesc.as<uint8_t>() + (size_t)32 * LC;
+  int* dln = S.nkl.as<int>() + 1;
+  // ---- block 0 = last frame of the previous batch (or nothing) ----
+  if (f->have_prev && f->last >= 0) {
+    FeSlot& P = f->slot[f->last];
+    SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_orb, 0));
+    SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_line, 0));
+    if (&P == &S) {
+      // same buffers (single-batch use): the matchers of that batch read block 0, wait for them before overwriting it
+      SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_pm, 0));
+      SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_lm, 0));
+    }
+    const int pl = P.n;   // its last frame sits in block pl
+    SDPL_CUDA(cudaMemcpyAsync(S.desc.p, P.desc.as<uint8_t>() + (size_t)pl * KC * 32, (size_t)32 * KC, cudaMemcpyDeviceToDevice, f->s_io));
+    SDPL_CUDA(cudaMemcpyAsync(S.nkp.p, P.nkp.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_io));
+    SDPL_CUDA(cudaMemcpyAsync(S.ldesc.p, P.ldesc.as<uint8_t>() + (size_t)pl * LC * 32, (size_t)32 * LC, cudaMemcpyDeviceToDevice, f->s_io));
+    SDPL_CUDA(cudaMemcpyAsync(S.nkl.p, P.nkl.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_io));
+  } else {
+    SDPL_CUDA(cudaMemsetAsync(S.nkp.p, 0, sizeof(int), f->s_io));
+    SDPL_CUDA(cudaMemsetAsync(S.nkl.p, 0, sizeof(int), f->s_io));
   }
   // ---- one upload shared by both pipelines ----
   if (stride == w && frame_stride == (size_t)w * h) {
-    SDPL_CUDA(cudaMemcpyAsync(f->d_imgs.p, imgs, (size_t)w * h * n, cudaMemcpyHostToDevice, f->s_io));
+    SDPL_CUDA(cudaMemcpyAsync(S.imgs.p, imgs, (size_t)w * h * n, cudaMemcpyHostToDevice, f->s_io));
   } else {
     for (int i = 0; i < n; i++)
-      SDPL_CUDA(cudaMemcpy2DAsync((char*)f->d_imgs.p + (size_t)i * w * h, w, imgs + (size_t)i * frame_stride, stride, w, h,
+      SDPL_CUDA(cudaMemcpy2DAsync((char*)S.imgs.p + (size_t)i * w * h, w, imgs + (size_t)i * frame_stride, stride, w, h,
                                   cudaMemcpyHostToDevice, f->s_io));
   }
-  SDPL_CUDA(cudaEventRecord(f->ev_in, f->s_io));
+  SDPL_CUDA(cudaEventRecord(S.ev_in, f->s_io));
   int launches = 0;
   // ---- lines (high priority, launched first) and ORB concurrently ----
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_line, f->ev_in, 0));
-  if ((rc = sdpl_line_extract_batch_dev(f->line, f->d_imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dl, dld, LC, dln, 0))) return rc;
+  SDPL_CUDA(cudaStreamWaitEvent(f->s_line, S.ev_in, 0));
+  if ((rc = sdpl_line_extract_batch_dev(f->line, S.imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dl, dld, LC, dln, 0))) return rc;
   launches += sdpl_line_last_launches(f->line);
-  SDPL_CUDA(cudaEventRecord(f->ev_line, f->s_line));
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, f->ev_in, 0));
-  if ((rc = sdpl_orb_extract_batch_dev(f->orb, f->d_imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dk, dd, KC, dn, 0))) return rc;
+  SDPL_CUDA(cudaEventRecord(S.ev_line, f->s_line));
+  SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, S.ev_in, 0));
+  if ((rc = sdpl_orb_extract_batch_dev(f->orb, S.imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dk, dd, KC, dn, 0))) return rc;
   launches += sdpl_orb_last_launches(f->orb);
-  SDPL_CUDA(cudaEventRecord(f->ev_orb, f->s_orb));
-  // ---- frame t against frame t-1 (slot t+1 against slot t), points then lines ----
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_pm, f->ev_orb, 0));
-  if ((rc = sdpl_match_knn2_batch_dev(f->pm, dd, dn, (size_t)32 * KC, f->d_desc.as<uint8_t>(), f->d_nkp.as<int>(), (size_t)32 * KC, n, KC, KC,
-                                      f->d_pbest.as<sdpl_dmatch>(), f->d_psecond.as<sdpl_dmatch>(), 0))) return rc;
+  SDPL_CUDA(cudaEventRecord(S.ev_orb, f->s_orb));
+  // ---- frame t against frame t-1 (block t+1 against block t), points then lines ----
+  SDPL_CUDA(cudaStreamWaitEvent(f->s_pm, S.ev_orb, 0));
+  if ((rc = sdpl_match_knn2_batch_dev(f->pm, dd, dn, (size_t)32 * KC, S.desc.as<uint8_t>(), S.nkp.as<int>(), (size_t)32 * KC, n, KC, KC,
+                                      S.pbest.as<sdpl_dmatch>(), S.psecond.as<sdpl_dmatch>(), 0))) return rc;
   launches += sdpl_matcher_last_launches(f->pm);
-  if ((rc = sdpl_match_ratio_batch_dev(f->pm, f->d_pbest.as<sdpl_dmatch>(), f->d_psecond.as<sdpl_dmatch>(), dn, n, KC, f->ratio, f->max_dist,
-                                       f->d_pout.as<sdpl_dmatch>(), f->d_pacc.as<int>(), 0))) return rc;
+  if ((rc = sdpl_match_ratio_batch_dev(f->pm, S.pbest.as<sdpl_dmatch>(), S.psecond.as<sdpl_dmatch>(), dn, n, KC, f->ratio, f->max_dist,
+                                       S.pout.as<sdpl_dmatch>(), S.pacc.as<int>(), 0))) return rc;
   launches += sdpl_matcher_last_launches(f->pm);
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_lm, f->ev_line, 0));
-  if ((rc = sdpl_match_knn2_batch_dev(f->lm, dld, dln, (size_t)32 * LC, f->d_ldesc.as<uint8_t>(), f->d_nkl.as<int>(), (size_t)32 * LC, n, LC, LC,
-                                      f->d_lbest.as<sdpl_dmatch>(), f->d_lsecond.as<sdpl_dmatch>(), 0))) return rc;
+  SDPL_CUDA(cudaEventRecord(S.ev_pm, f->s_pm));
+  SDPL_CUDA(cudaStreamWaitEvent(f->s_lm, S.ev_line, 0));
+  if ((rc = sdpl_match_knn2_batch_dev(f->lm, dld, dln, (size_t)32 * LC, S.ldesc.as<uint8_t>(), S.nkl.as<int>(), (size_t)32 * LC, n, LC, LC,
+                                      S.lbest.as<sdpl_dmatch>(), S.lsecond.as<sdpl_dmatch>(), 0))) return rc;
   launches += sdpl_matcher_last_launches(f->lm);
-  if ((rc = sdpl_match_ratio_batch_dev(f->lm, f->d_lbest.as<sdpl_dmatch>(), f->d_lsecond.as<sdpl_dmatch>(), dln, n, LC, f->ratio, f->max_dist,
-                                       f->d_lout.as<sdpl_dmatch>(), f->d_lacc.as<int>(), 0))) return rc;
+  if ((rc = sdpl_match_ratio_batch_dev(f->lm, S.lbest.as<sdpl_dmatch>(), S.lsecond.as<sdpl_dmatch>(), dln, n, LC, f->ratio, f->max_dist,
+                                       S.lout.as<sdpl_dmatch>(), S.lacc.as<int>(), 0))) return rc;
   launches += sdpl_matcher_last_launches(f->lm);
+  SDPL_CUDA(cudaEventRecord(S.ev_lm, f->s_lm));
   f->launches = launches;
-  // ---- results back: counts first (they size the row copies), then the valid rows of every frame ----
-  const size_t need = sizeof(int) * 4 * (size_t)n;
-  if (f->h_stage_bytes < need) {
-    if (f->h_stage) cudaFreeHost(f->h_stage);
-    f->h_stage = nullptr; f->h_stage_bytes = 0;
-    SDPL_CUDA(cudaMallocHost(&f->h_stage, need));
-    f->h_stage_bytes = need;
-  }
-  int* hn = (int*)f->h_stage;                    // [4][n]: n_kp, n_lines, point matches, line matches
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, f->ev_orb, 0));
-  SDPL_CUDA(cudaMemcpyAsync(hn, dn, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s_orb));
-  SDPL_CUDA(cudaStreamSynchronize(f->s_orb));
+  S.n = n; S.w = w; S.h = h; S.busy = true;
+  f->last = f->next; f->have_prev = 1;
+  f->next ^= 1; f->count++;
+  return SDPL_OK;
+}
+
+// Wait for the oldest submitted batch and bring its results to the host (on a separate stream, so the copies overlap the
+// kernels of a batch submitted after it).
+int sdpl_frontend_collect(sdpl_frontend* f, sdpl_keypoint* kps, uint8_t* desc, sdpl_keyline* kls, uint8_t* ldesc, sdpl_dmatch* pt_matches,
+                          sdpl_dmatch* ln_matches, sdpl_frame_stats* stats, int* n_frames) {
+  if (!f || !kps || !desc || !kls || !ldesc || !pt_matches || !ln_matches || !stats) { set_last_error("sdpl_frontend_collect: bad argument"); return SDPL_ERR_ARG; }
+  if (f->count < 1) { set_last_error("sdpl_frontend_collect: nothing submitted"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(f->device));
+  FeSlot& S = f->slot[f->head];
+  const int n = S.n, KC = f->kp_cap, LC = f->kl_cap;
+  const sdpl_keypoint* dk = S.kps.as<sdpl_keypoint>() + KC;
+  const uint8_t* dd = S.desc.as<uint8_t>() + (size_t)32 * KC;
+  const int* dn = S.nkp.as<int>() + 1;
+  const sdpl_keyline* dl = S.kls.as<sdpl_keyline>() + LC;
+  const uint8_t* dld = S.ldesc.as<uint8_t>() + (size_t)32 * LC;
+  const int* dln = S.nkl.as<int>() + 1;
+  int* hn = S.hn;                       // [4][n]: n_kp, n_lines, point matches, line matches ; then 2 error flags
+  int* herr = hn + 4 * (size_t)n;
+  cudaStream_t so = f->s_out;
   int status = SDPL_OK;
-  // ORB rows can go while the line pipeline is still running
+  // counts size the row copies: fetch them as soon as their stage is done, then only the valid rows of every frame
+  SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_orb, 0));
+  SDPL_CUDA(cudaMemcpyAsync(hn, dn, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
+  int rc;
+  if ((rc = sdpl_orb_peek_error_async(f->orb, so, herr))) return rc;
+  SDPL_CUDA(cudaStreamSynchronize(so));
   for (int i = 0; i < n; i++) {
     int c = hn[i];
     if (c > KC) { c = KC; status = SDPL_ERR_CAPACITY; }
     if (c > 0) {
-      SDPL_CUDA(cudaMemcpyAsync(kps + (size_t)i * KC, dk + (size_t)i * KC, sizeof(sdpl_keypoint) * c, cudaMemcpyDeviceToHost, f->s_orb));
-      SDPL_CUDA(cudaMemcpyAsync(desc + (size_t)i * KC * 32, dd + (size_t)i * KC * 32, (size_t)32 * c, cudaMemcpyDeviceToHost, f->s_orb));
+      SDPL_CUDA(cudaMemcpyAsync(kps + (size_t)i * KC, dk + (size_t)i * KC, sizeof(sdpl_keypoint) * c, cudaMemcpyDeviceToHost, so));
+      SDPL_CUDA(cudaMemcpyAsync(desc + (size_t)i * KC * 32, dd + (size_t)i * KC * 32, (size_t)32 * c, cudaMemcpyDeviceToHost, so));
     }
   }
-  SDPL_CUDA(cudaMemcpyAsync(hn + 2 * n, f->d_pacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s_pm));
-  SDPL_CUDA(cudaStreamSynchronize(f->s_pm));
+  SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_pm, 0));
+  SDPL_CUDA(cudaMemcpyAsync(hn + 2 * n, S.pacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
   for (int i = 0; i < n; i++) {
     const int c = std::min(hn[i], KC);
-    if (c > 0) SDPL_CUDA(cudaMemcpyAsync(pt_matches + (size_t)i * KC, f->d_pout.as<sdpl_dmatch>() + (size_t)i * KC, sizeof(sdpl_dmatch) * c,
-                                         cudaMemcpyDeviceToHost, f->s_pm));
+    if (c > 0) SDPL_CUDA(cudaMemcpyAsync(pt_matches + (size_t)i * KC, S.pout.as<sdpl_dmatch>() + (size_t)i * KC, sizeof(sdpl_dmatch) * c,
+                                         cudaMemcpyDeviceToHost, so));
   }
-  SDPL_CUDA(cudaMemcpyAsync(hn + n, dln, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s_line));
-  SDPL_CUDA(cudaStreamSynchronize(f->s_line));
+  SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_line, 0));
+  SDPL_CUDA(cudaMemcpyAsync(hn + n, dln, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
+  if ((rc = sdpl_line_peek_error_async(f->line, so, herr + 1))) return rc;
+  SDPL_CUDA(cudaStreamSynchronize(so));
   for (int i = 0; i < n; i++) {
     int c = hn[n + i];
     if (c > LC) { c = LC; status = SDPL_ERR_CAPACITY; }
     if (c > 0) {
-      SDPL_CUDA(cudaMemcpyAsync(kls + (size_t)i * LC, dl + (size_t)i * LC, sizeof(sdpl_keyline) * c, cudaMemcpyDeviceToHost, f->s_line));
-      SDPL_CUDA(cudaMemcpyAsync(ldesc + (size_t)i * LC * 32, dld + (size_t)i * LC * 32, (size_t)32 * c, cudaMemcpyDeviceToHost, f->s_line));
+      SDPL_CUDA(cudaMemcpyAsync(kls + (size_t)i * LC, dl + (size_t)i * LC, sizeof(sdpl_keyline) * c, cudaMemcpyDeviceToHost, so));
+      SDPL_CUDA(cudaMemcpyAsync(ldesc + (size_t)i * LC * 32, dld + (size_t)i * LC * 32, (size_t)32 * c, cudaMemcpyDeviceToHost, so));
     }
   }
-  SDPL_CUDA(cudaMemcpyAsync(hn + 3 * n, f->d_lacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, f->s_lm));
-  SDPL_CUDA(cudaStreamSynchronize(f->s_lm));
+  SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_lm, 0));
+  SDPL_CUDA(cudaMemcpyAsync(hn + 3 * n, S.lacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
   for (int i = 0; i < n; i++) {
     const int c = std::min(hn[n + i], LC);
-    if (c > 0) SDPL_CUDA(cudaMemcpyAsync(ln_matches + (size_t)i * LC, f->d_lout.as<sdpl_dmatch>() + (size_t)i * LC, sizeof(sdpl_dmatch) * c,
-                                         cudaMemcpyDeviceToHost, f->s_lm));
+    if (c > 0) SDPL_CUDA(cudaMemcpyAsync(ln_matches + (size_t)i * LC, S.lout.as<sdpl_dmatch>() + (size_t)i * LC, sizeof(sdpl_dmatch) * c,
+                                         cudaMemcpyDeviceToHost, so));
   }
-  // keep the last frame's descriptors as the "previous frame" of the next call (slot n -> slot 0), after the matchers read slot 0
-  SDPL_CUDA(cudaEventRecord(f->ev_pm, f->s_pm));
-  SDPL_CUDA(cudaEventRecord(f->ev_lm, f->s_lm));
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_io, f->ev_pm, 0));
-  SDPL_CUDA(cudaStreamWaitEvent(f->s_io, f->ev_lm, 0));
-  SDPL_CUDA(cudaMemcpyAsync(f->d_desc.p, dd + (size_t)(n - 1) * KC * 32, (size_t)32 * KC, cudaMemcpyDeviceToDevice, f->s_io));
-  SDPL_CUDA(cudaMemcpyAsync(f->d_nkp.p, dn + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, f->s_io));
-  SDPL_CUDA(cudaMemcpyAsync(f->d_ldesc.p, dld + (size_t)(n - 1) * LC * 32, (size_t)32 * LC, cudaMemcpyDeviceToDevice, f->s_io));
-  SDPL_CUDA(cudaMemcpyAsync(f->d_nkl.p, dln + (n - 1), sizeof(int), cudaMemcpyDeviceToDevice, f->s_io));
-  for (cudaStream_t s : {f->s_orb, f->s_line, f->s_pm, f->s_lm, f->s_io}) SDPL_CUDA(cudaStreamSynchronize(s));
-  f->have_prev = 1;
-  if ((rc = sdpl_orb_check(f->orb)) || (rc = sdpl_line_check(f->line))) return rc;
+  SDPL_CUDA(cudaStreamSynchronize(so));
+  S.busy = false;
+  f->head ^= 1; f->count--;
+  if (n_frames) *n_frames = n;
   for (int i = 0; i < n; i++) {
     stats[i].n_kp = hn[i]; stats[i].n_lines = hn[n + i]; stats[i].n_pt_matches = hn[2 * n + i]; stats[i].n_ln_matches = hn[3 * n + i];
   }
-  if (status == SDPL_ERR_CAPACITY) set_last_error("sdpl_frontend_process: more features than the per-frame capacity");
+  if (herr[0] || herr[1]) {
+    set_last_error("device buffer overflow in the front-end pipeline (FAST candidates / quadtree nodes / pending rectangles)");
+    return SDPL_ERR_OVERFLOW;
+  }
+  if (status == SDPL_ERR_CAPACITY) set_last_error("sdpl_frontend_collect: more features than the per-frame capacity");
   return status;
+}
+
+int sdpl_frontend_process(sdpl_frontend* f, const uint8_t* imgs, int n, int w, int h, int stride, size_t frame_stride,
+                          sdpl_keypoint* kps, uint8_t* desc, sdpl_keyline* kls, uint8_t* ldesc, sdpl_dmatch* pt_matches,
+                          sdpl_dmatch* ln_matches, sdpl_frame_stats* stats) {
+  if (f && f->count > 0) { set_last_error("sdpl_frontend_process: batches are in flight, collect them first"); return SDPL_ERR_ARG; }
+  int rc = sdpl_frontend_submit(f, imgs, n, w, h, stride, frame_stride);
+  if (rc) return rc;
+  return sdpl_frontend_collect(f, kps, desc, kls, ldesc, pt_matches, ln_matches, stats, nullptr);
 }
 
 }  // extern "C"

@@ -1045,6 +1045,12 @@ int sdpl_line_tables(const sdpl_line* o, float* sf, float* isf, float* s2, float
   return SDPL_OK;
 }
 int sdpl_line_last_launches(const sdpl_line* o) { return o ? o->launches : 0; }
+int sdpl_line_peek_error_async(sdpl_line* o, void* stream, int* host_flag) {
+  if (!o || !host_flag) return SDPL_ERR_ARG;
+  if (!o->err.p) { *host_flag = 0; return SDPL_OK; }
+  SDPL_CUDA(cudaMemcpyAsync(host_flag, o->err.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return SDPL_OK;
+}
 int sdpl_line_check(sdpl_line* o) {
   if (!o) return SDPL_ERR_ARG;
   if (!o->err.p) return SDPL_OK;

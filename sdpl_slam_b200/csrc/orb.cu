@@ -1040,6 +1040,12 @@ int sdpl_orb_max_keypoints(const sdpl_orb* o) {
   return t;
 }
 int sdpl_orb_last_launches(const sdpl_orb* o) { return o ? o->launches : 0; }
+int sdpl_orb_peek_error_async(sdpl_orb* o, void* stream, int* host_flag) {
+  if (!o || !host_flag) return SDPL_ERR_ARG;
+  if (!o->err.p) { *host_flag = 0; return SDPL_OK; }
+  SDPL_CUDA(cudaMemcpyAsync(host_flag, o->err.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return SDPL_OK;
+}
 int sdpl_orb_check(sdpl_orb* o) {
   if (!o) return SDPL_ERR_ARG;
   if (!o->err.p) return SDPL_OK;

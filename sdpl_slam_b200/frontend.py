@@ -101,6 +101,9 @@ def load_library(path=None):
     L.sdpl_frontend_reset.argtypes = [vp]
     L.sdpl_frontend_process.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp, vp, vp, vp, vp]
     L.sdpl_frontend_last_launches.argtypes = [vp]
+    L.sdpl_frontend_submit.argtypes = [vp, vp, i, i, i, i, sz]
+    L.sdpl_frontend_collect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ip]
+    L.sdpl_frontend_pending.argtypes = [vp]
     if path is None:
         _lib = L
     return L
@@ -491,26 +494,42 @@ class FrontEnd:
         _check(self._L.sdpl_frontend_reset(self._h))
 
     def _outputs(self, B):
-        if self._bufs is None or self._bufs[0].shape[0] < B:
+        """two output sets, used alternately (a collected result stays valid until the collect after the next one)"""
+        if self._bufs is None or self._bufs[0][0].shape[0] < B:
             KC, LC = self.kp_capacity, self.kl_capacity
-            self._bufs = (np.empty((B, KC), KP_DTYPE), np.empty((B, KC, 32), np.uint8), np.empty((B, LC), KL_DTYPE),
-                          np.empty((B, LC, 32), np.uint8), np.empty((B, KC), DM_DTYPE), np.empty((B, LC), DM_DTYPE),
-                          np.empty(B, FS_DTYPE))
-        return self._bufs
+            self._bufs = [(np.empty((B, KC), KP_DTYPE), np.empty((B, KC, 32), np.uint8), np.empty((B, LC), KL_DTYPE),
+                           np.empty((B, LC, 32), np.uint8), np.empty((B, KC), DM_DTYPE), np.empty((B, LC), DM_DTYPE),
+                           np.empty(B, FS_DTYPE)) for _ in range(2)]
+            self._flip = 0
+        self._flip ^= 1
+        return self._bufs[self._flip]
 
-    def process(self, images):
-        """-> dict(kps, desc, kls, ldesc, pt_matches, ln_matches: padded (B, cap, ...) arrays; stats: per-frame counts).
-        The arrays are reused by the next call."""
+    def submit(self, images):
+        """Enqueue a (B, H, W) uint8 batch (upload, ORB || lines, matching) without waiting.  The array must stay alive and
+        unchanged until the matching collect().  At most two batches in flight."""
         imgs = np.asarray(images)
         if imgs.dtype != np.uint8 or imgs.ndim != 3:
             raise TypeError("images must be a (B, H, W) uint8 array")
         if not imgs.flags["C_CONTIGUOUS"]:
             imgs = np.ascontiguousarray(imgs)
         B, H, W = imgs.shape
+        _check(self._L.sdpl_frontend_submit(self._h, _p(imgs), B, W, H, W, W * H))
+        self._inflight = getattr(self, "_inflight", []) + [imgs]
+
+    def collect(self):
+        """Results of the oldest submitted batch: dict(kps, desc, kls, ldesc, pt_matches, ln_matches: padded (B, cap, ...)
+        arrays; stats: per-frame counts)."""
+        imgs = self._inflight.pop(0)
+        B = imgs.shape[0]
         kps, desc, kls, ldesc, pm, lm, st = self._outputs(B)
-        _check(self._L.sdpl_frontend_process(self._h, _p(imgs), B, W, H, W, W * H, _p(kps), _p(desc), _p(kls), _p(ldesc), _p(pm), _p(lm),
-                                             _p(st)))
-        return dict(kps=kps, desc=desc, kls=kls, ldesc=ldesc, pt_matches=pm, ln_matches=lm, stats=st[:B])
+        n = C.c_int(0)
+        _check(self._L.sdpl_frontend_collect(self._h, _p(kps), _p(desc), _p(kls), _p(ldesc), _p(pm), _p(lm), _p(st), C.byref(n)))
+        return dict(kps=kps, desc=desc, kls=kls, ldesc=ldesc, pt_matches=pm, ln_matches=lm, stats=st[:n.value])
+
+    def process(self, images):
+        """submit + collect of one batch."""
+        self.submit(images)
+        return self.collect()
 
     def last_launches(self):
         return self._L.sdpl_frontend_last_launches(self._h)

@@ -88,3 +88,28 @@ def test_handles_survive_geometry_changes(frontend):
             k, d = fo(imgs[i]); kl, dl = fl(imgs[i])
             assert a[i][0].tobytes() == k.tobytes() and a[i][1].tobytes() == d.tobytes()
             assert b[i][0].tobytes() == kl.tobytes() and b[i][1].tobytes() == dl.tobytes()
+
+
+def test_pipelined_submit_collect_equals_process(frontend):
+    imgs = _seq(6)
+    a = frontend.FrontEnd(500, 1.2, 8, 20, 7)
+    ref = [dict((k, v.copy()) for k, v in a.process(imgs[i:i + 2]).items()) for i in (0, 2, 4)]
+    b = frontend.FrontEnd(500, 1.2, 8, 20, 7)
+    b.submit(imgs[0:2]); b.submit(imgs[2:4])
+    out = [dict((k, v.copy()) for k, v in b.collect().items())]
+    b.submit(imgs[4:6])
+    out.append(dict((k, v.copy()) for k, v in b.collect().items()))
+    out.append(dict((k, v.copy()) for k, v in b.collect().items()))
+    for r, o in zip(ref, out):
+        np.testing.assert_array_equal(r["stats"], o["stats"])
+        for f in range(2):
+            nk, nl = r["stats"]["n_kp"][f], r["stats"]["n_lines"][f]
+            assert r["kps"][f, :nk].tobytes() == o["kps"][f, :nk].tobytes()
+            assert r["desc"][f, :nk].tobytes() == o["desc"][f, :nk].tobytes()
+            assert r["kls"][f, :nl].tobytes() == o["kls"][f, :nl].tobytes()
+            assert r["pt_matches"][f, :nk].tobytes() == o["pt_matches"][f, :nk].tobytes()
+            assert r["ln_matches"][f, :nl].tobytes() == o["ln_matches"][f, :nl].tobytes()
+    # nothing in flight any more: collect must fail loudly
+    b._inflight = [imgs[0:2]]
+    with pytest.raises(frontend.SdplError):
+        b.collect()
