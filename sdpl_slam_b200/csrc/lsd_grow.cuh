@@ -523,13 +523,21 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
         const int py = xy_y(p), px = xy_x(p);
         uint32_t st[9];
         PxA pa[9];
+        // clamped row / column offsets: every load is in bounds and unpredicated; neighbours outside the image are masked
+        // out of the candidate set by four border tests instead of nine bounds checks
+        const int rofs[3] = {max(py - 1, 0) * w, py * w, min(py + 1, h - 1) * w};
+        const int cofs[3] = {max(px - 1, 0), px, min(px + 1, w - 1)};
+        uint32_t vmask = 0x1EFu;                                  // bits 0..8 without the centre
+        if (px == 0) vmask &= ~0x049u;
+        if (px == w - 1) vmask &= ~0x124u;
+        if (py == 0) vmask &= ~0x007u;
+        if (py == h - 1) vmask &= ~0x1C0u;
 #pragma unroll
         for (int k = 0; k < 9; k++) {
-          const int yy = py - 1 + k / 3, xx = px - 1 + k % 3;
-          const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w && k != 4;
-          const int q = yy * w + xx;
-          st[k] = in ? ld_state(T.state + q) : kUsed;
-          if (in) pa[k] = T.px[q]; else pa[k].ang = kNotDef;
+          if (k == 4) continue;
+          const int q = rofs[k / 3] + cofs[k % 3];
+          st[k] = ld_state(T.state + q);
+          pa[k] = T.px[q];
         }
         if (i + 1 < n_start) nxt = cur[i + 1];
         // candidates: in bounds, defined, not committed, not already mine.  The reference tests the neighbours one after
@@ -543,6 +551,7 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
           const uint32_t sv = st[k];
           if (!(sv & kUsed) && !(spec && sv == stamp) && pa[k].ang != kNotDef) cand |= 1u << k;
         }
+        cand &= vmask;
         while (cand) {
           uint32_t al = 0;
 #pragma unroll
