@@ -178,23 +178,47 @@ static const int kG5s1[5] = {14, 62, 104, 62, 14};          // 5x5 sigma 1      
 static const int kG7s075[7] = {0, 4, 56, 136, 56, 4, 0};    // 7x7 sigma 0.75   (LSD: sigma_scale/scale = 0.6/0.8)
 void gaussian_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int kind) {
   const int* k = kind == 0 ? kG7s2 : kind == 1 ? kG5s1 : kG7s075;
-  int n = kind == 1 ? 5 : 7, r = n / 2;
+  const int n = kind == 1 ? 5 : 7, r = n / 2;
+  // horizontal pass into a u16 plane (Q8.8 sums fit 16 bits); each row is first extended by reflect-101 so that the
+  // tap loop has no border logic (same values, same order of additions as the per-tap reflect)
   std::vector<uint16_t> tmp((size_t)w * h);
+  std::vector<uint8_t> ext((size_t)w + 2 * r);
   for (int y = 0; y < h; y++) {
-    const uint8_t* s = src + (size_t)y * sstride;
-    for (int x = 0; x < w; x++) {
-      uint32_t acc = 0;
-      for (int i = 0; i < n; i++) acc += (uint32_t)k[i] * s[reflect101(x + i - r, w)];
-      tmp[(size_t)y * w + x] = (uint16_t)acc;
+    const uint8_t* sr = src + (size_t)y * sstride;
+    for (int i = 0; i < r; i++) { ext[i] = sr[reflect101(i - r, w)]; ext[r + w + i] = sr[reflect101(w + i, w)]; }
+    memcpy(&ext[r], sr, w);
+    uint16_t* t = &tmp[(size_t)y * w];
+    const uint8_t* e = ext.data();
+    if (n == 7) {
+      for (int x = 0; x < w; x++)
+        t[x] = (uint16_t)((uint32_t)k[0] * e[x] + (uint32_t)k[1] * e[x + 1] + (uint32_t)k[2] * e[x + 2] + (uint32_t)k[3] * e[x + 3] +
+                          (uint32_t)k[4] * e[x + 4] + (uint32_t)k[5] * e[x + 5] + (uint32_t)k[6] * e[x + 6]);
+    } else {
+      for (int x = 0; x < w; x++)
+        t[x] = (uint16_t)((uint32_t)k[0] * e[x] + (uint32_t)k[1] * e[x + 1] + (uint32_t)k[2] * e[x + 2] + (uint32_t)k[3] * e[x + 3] +
+                          (uint32_t)k[4] * e[x + 4]);
     }
   }
+  // vertical pass (Q16.16, round half up); rows addressed through reflect-101 row pointers
   std::vector<uint8_t> out((size_t)w * h);
-  for (int y = 0; y < h; y++)
-    for (int x = 0; x < w; x++) {
-      uint32_t acc = 0;
-      for (int i = 0; i < n; i++) acc += (uint32_t)k[i] * tmp[(size_t)reflect101(y + i - r, h) * w + x];
-      out[(size_t)y * w + x] = (uint8_t)std::min(255u, (acc + (1u << 15)) >> 16);
+  for (int y = 0; y < h; y++) {
+    const uint16_t* rows[7];
+    for (int i = 0; i < n; i++) rows[i] = &tmp[(size_t)reflect101(y + i - r, h) * w];
+    uint8_t* o = &out[(size_t)y * w];
+    if (n == 7) {
+      for (int x = 0; x < w; x++) {
+        const uint32_t acc = (uint32_t)k[0] * rows[0][x] + (uint32_t)k[1] * rows[1][x] + (uint32_t)k[2] * rows[2][x] + (uint32_t)k[3] * rows[3][x] +
+                             (uint32_t)k[4] * rows[4][x] + (uint32_t)k[5] * rows[5][x] + (uint32_t)k[6] * rows[6][x];
+        o[x] = (uint8_t)std::min(255u, (acc + (1u << 15)) >> 16);
+      }
+    } else {
+      for (int x = 0; x < w; x++) {
+        const uint32_t acc = (uint32_t)k[0] * rows[0][x] + (uint32_t)k[1] * rows[1][x] + (uint32_t)k[2] * rows[2][x] + (uint32_t)k[3] * rows[3][x] +
+                             (uint32_t)k[4] * rows[4][x];
+        o[x] = (uint8_t)std::min(255u, (acc + (1u << 15)) >> 16);
+      }
     }
+  }
   for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * dstride, &out[(size_t)y * w], w);
 }
 
@@ -286,10 +310,28 @@ int fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std::
   xs.clear(); ys.clear(); sc.clear();
   if (w < 7 || h < 7) return 0;
   std::vector<int> s((size_t)w * h, 0);
+  // An arc of 9 contiguous ring pixels contains at least one pixel of every opposite pair (k, k+8): a corner at `threshold`
+  // needs, for all 8 pairs, one member brighter than centre+threshold (bright arc) or, for all 8 pairs, one member darker
+  // than centre-threshold (dark arc).  Pixels failing this necessary test have score < threshold (stored as 0 either
+  // way), so the full score is only computed for the survivors -- the same early-out cv::FAST uses.
+  int ofs[16];
+  for (int k = 0; k < 16; k++) ofs[k] = kRing[k][1] * stride + kRing[k][0];
   for (int y = 3; y < h - 3; y++)
     for (int x = 3; x < w - 3; x++) {
-      int v = fast_score(img + (size_t)y * stride + x, stride);
-      s[(size_t)y * w + x] = v >= threshold ? v : 0;
+      const uint8_t* p = img + (size_t)y * stride + x;
+      const int hi = p[0] + threshold, lo = p[0] - threshold;
+      bool bright = true, dark = true;
+      for (int k = 0; k < 8 && (bright || dark); k++) {
+        const int a = p[ofs[k]], b = p[ofs[k + 8]];
+        bright = bright && (a > hi || b > hi);
+        dark = dark && (a < lo || b < lo);
+      }
+      int v = 0;
+      if (bright || dark) {
+        v = fast_score(p, stride);
+        if (v < threshold) v = 0;
+      }
+      s[(size_t)y * w + x] = v;
     }
   for (int y = 3; y < h - 3; y++)
     for (int x = 3; x < w - 3; x++) {
