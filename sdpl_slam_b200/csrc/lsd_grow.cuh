@@ -461,6 +461,36 @@ __device__ __forceinline__ bool owns_all_xy(const Task& T, const int* list, int 
   for (; i < n && ok; i++) ok = (ld_state(T.state + xy_lin(list[i], w)) >> 1) == key;
   return ok != 0;
 }
+// warp-cooperative ownership check: lists longer than 64 entries are walked by the whole warp (128 loads in flight per
+// step instead of one lane's dependent chain), short ones by their owner.  `active` lanes get their verdict back.
+__device__ __forceinline__ bool owns_all_coop_xy(const Task& T, bool active, const int* list, int n, uint32_t key) {
+  const int lane = threadIdx.x & 31, w = T.w;
+  bool res = false;
+  uint32_t longm = __ballot_sync(0xffffffffu, active && n > 64);
+  while (longm) {
+    const int src = __ffs(longm) - 1;
+    longm &= longm - 1;
+    const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(size_t)list, src);
+    const int m = __shfl_sync(0xffffffffu, n, src);
+    const uint32_t k = __shfl_sync(0xffffffffu, key, src);
+    const int* l = (const int*)(size_t)p;
+    int ok = 1;
+    for (int i = lane * 4; i < m; i += 128) {
+      const int c = min(4, m - i);
+      int q[4]; uint32_t sv[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) q[j] = j < c ? xy_lin(l[i + j], w) : -1;
+#pragma unroll
+      for (int j = 0; j < 4; j++) sv[j] = j < c ? ld_state(T.state + q[j]) : (k << 1);
+#pragma unroll
+      for (int j = 0; j < 4; j++) ok &= (sv[j] >> 1) == k;
+    }
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == src) res = all_ok;
+  }
+  if (active && n <= 64) res = owns_all_xy(T, list, n, key);
+  return res;
+}
 __device__ __forceinline__ void mark_used_coop_xy(const Task& T, bool active, const int* list, int n) {
   const int lane = threadIdx.x & 31, w = T.w;
   uint32_t longm = __ballot_sync(0xffffffffu, active && n > 32);
@@ -871,7 +901,8 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
   const uint32_t lt = (1u << lane) - 1u;
   const int cap = (32 * T.lane_cap) / K;
   int* my_reg = T.reg_spec + (size_t)tid * cap;
-  if (tid == 0) { S.cursor = 0; S.npend = 0; }
+  if (tid == 0) { S.cursor = 0; }
+  int npend = 0;          // rectangles appended so far (uniform across the CTA)
   uint32_t wave = 0;
   long long t_sel = 0, t_spec = 0, t_commit = 0, t_redo = 0, n_redo = 0, n_round = 0, n_seed = 0;
   __syncthreads();
@@ -905,104 +936,99 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
     SeedResult R;
     R.ok = 0; R.n1 = 0; R.n2_orig = 0; R.nf = 0; R.foff = 0; R.has_rect = 0;
     const uint32_t stamp = (wave << 11) | ((uint32_t)(K - 1 - tid) << 1);   // bit0 = phase, 10 bits of seed priority
-    if (lane == 0) {
-      const int first = warp * 32;
-      S.pend[warp] = nsel >= first + 32 ? 0xffffffffu : (nsel > first ? ((1u << (nsel - first)) - 1u) : 0u);
-    }
-    bool retired = false;
     int verdict = 0;        // cached verdict: 0 unknown, 1 good (invalidated only by a re-run that wrote near me), 2 dead, 3 must re-run
     int kstar = -1;         // -1: the speculative pass of the wave; otherwise the seed that is re-run sequentially this round
+    int settled = 0;        // seeds [0, settled) of the wave are committed, dropped or re-run (uniform across the CTA)
     long long c2 = c1;
-    // every round starts with ONE call site of the per-seed pipeline: all seeds speculatively in the first round, the first
-    // doubtful seed sequentially in the later ones
+    // every round starts with ONE call site of the per-seed pipeline (all seeds speculatively in the first round) or the
+    // warp-cooperative sequential re-run of the first doubtful seed; three CTA barriers per round
     while (true) {
       n_round++;
       long long cr = clock64();
-      const bool run_spec = kstar < 0 && tid < nsel;
-      if (run_spec) process_seed_u(T, my_seed, my_reg, cap, stamp, true, R);
-      if (kstar >= 0 && warp == (kstar >> 5)) {
-        // the whole warp of kstar re-runs that seed sequentially (warp-cooperative, exact sequential semantics).  The
-        // commits of the previous round may have taken the seed: then the sequential algorithm skips it
+      if (kstar < 0) {
+        if (tid < nsel) process_seed_u(T, my_seed, my_reg, cap, stamp, true, R);
+      } else if (warp == (kstar >> 5)) {
+        // the whole warp of kstar re-runs that seed sequentially (exact sequential semantics).  The commits of the previous
+        // round may have taken the seed: then the sequential algorithm skips it
         const int ks_lane = kstar & 31;
         const int seed_k = __shfl_sync(0xffffffffu, my_seed, ks_lane);
         const bool taken = (ld_state(T.state + seed_k) & kUsed) != 0;
+        int has = 0;
         if (!taken) {
           SeedResult Q;
           process_seed_coop(T, seed_k, T.reg_serial, Q);
+          has = Q.has_rect;
           if (lane == ks_lane) {
-            if (Q.has_rect) { append_rect(T, S.npend, Q.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, Q.nf); S.has = 1; }
+            if (has) append_rect(T, npend, Q.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, Q.nf);
             S.rb[0] = Q.bx0; S.rb[1] = Q.by0; S.rb[2] = Q.bx1; S.rb[3] = Q.by1;
           }
         } else if (lane == ks_lane) { S.rb[0] = 1; S.rb[2] = 0; }
-        if (lane == ks_lane) retired = true;
+        if (lane == ks_lane) S.has = has;
       }
-      __syncthreads();
+      __syncthreads();                                                                     // (1) run / re-run finished
       if (kstar < 0) { c2 = clock64(); t_spec += c2 - c1; }
       else {
-        if (tid == 0) S.npend += S.has;
+        npend += S.has;
+        settled = kstar + 1;
         // the re-run wrote `used` inside its bounding box only: cached "good" verdicts elsewhere stay valid
         if (verdict == 1 && !(S.rb[0] > R.bx1 || S.rb[2] < R.bx0 || S.rb[1] > R.by1 || S.rb[3] < R.by0)) verdict = 0;
-        // kstar is settled
-        if (lane == 0 && kstar >= warp * 32 && kstar < warp * 32 + 32) S.pend[warp] &= ~(1u << (kstar - warp * 32));
-        __syncthreads();
         t_redo += clock64() - cr;
       }
-      const bool mine = ((S.pend[warp] >> lane) & 1u) && !retired;
+      if (settled >= nsel) break;
+      const bool mine = tid >= settled && tid < nsel;
       bool dead = false, good = false;
+      {
+        // seeds without a verdict: seed still free?  then the ownership walk (warp-cooperative for long lists)
+        const bool need = mine && verdict == 0;
+        bool d0 = false;
+        if (need) d0 = (ld_state(T.state + my_seed) & kUsed) != 0;
+        const bool own = owns_all_coop_xy(T, need && !d0 && R.ok, my_reg, R.n1 + R.n2_orig, stamp >> 1);
+        if (need) verdict = d0 ? 2 : (own ? 1 : 3);
+      }
       if (mine) {
-        if (verdict == 0) {
-          dead = (ld_state(T.state + my_seed) & kUsed) != 0;
-          if (!dead && R.ok) good = owns_all_xy(T, my_reg, R.n1 + R.n2_orig, stamp >> 1);
-          verdict = dead ? 2 : (good ? 1 : 3);
-        } else if (verdict == 3) {
+        if (verdict == 3) {
           // lost a pixel (or never finished): that is permanent; only "my seed was taken meanwhile" can still change
           dead = (ld_state(T.state + my_seed) & kUsed) != 0;
           if (dead) verdict = 2;
-        } else {
-          dead = verdict == 2; good = verdict == 1;
         }
+        dead = verdict == 2; good = verdict == 1;
       }
       const uint32_t dm = __ballot_sync(0xffffffffu, dead), gm = __ballot_sync(0xffffffffu, good);
-      if (lane == 0) { S.deadm[warp] = dm; S.goodm[warp] = gm; }
-      __syncthreads();
-      // first pending seed of the wave that is neither dead nor provably good
-      int ks = K, any = 0;
+      const uint32_t rm = __ballot_sync(0xffffffffu, good && R.has_rect);
+      if (lane == 0) { S.deadm[warp] = dm; S.goodm[warp] = gm; S.rectm[warp] = rm; }
+      __syncthreads();                                                                     // (2) verdicts published
+      // first unsettled seed that is neither dead nor provably good; rectangles of the good seeds before it, in seed order
+      int ks = nsel, before = 0, total = 0;
       for (int v = 0; v < NW; v++) {
-        const uint32_t pm = S.pend[v];
-        any |= pm != 0;
-        const uint32_t bad = pm & ~S.deadm[v] & ~S.goodm[v];
-        if (bad && ks == K) ks = v * 32 + __ffs(bad) - 1;
+        const int first = v * 32;
+        if (first >= nsel || first + 32 <= settled) continue;
+        uint32_t pm = 0xffffffffu;
+        if (settled > first) pm &= ~((1u << (settled - first)) - 1u);
+        if (nsel < first + 32) pm &= (1u << (nsel - first)) - 1u;
+        if (ks == nsel) {
+          const uint32_t bad = pm & ~S.deadm[v] & ~S.goodm[v];
+          if (bad) { ks = first + __ffs(bad) - 1; pm &= (1u << (ks - first)) - 1u; }
+          const uint32_t rr = S.rectm[v] & pm;
+          total += __popc(rr);
+          if (v < warp) before += __popc(rr);
+          else if (v == warp) before += __popc(rr & lt);
+        }
       }
-      if (!any) break;
       const bool below = tid < ks;
       const bool do_commit = mine && good && below;
-      const bool do_drop = mine && dead && below;
       mark_used_coop_xy(T, do_commit, my_reg + R.foff, R.nf);
-      if (do_commit || do_drop) retired = true;
-      const uint32_t rm = __ballot_sync(0xffffffffu, do_commit && R.has_rect);
-      if (lane == 0) S.rectm[warp] = rm;
-      __syncthreads();
-      int before = S.npend, total = 0;
-      for (int v = 0; v < NW; v++) { const int c = __popc(S.rectm[v]); if (v < warp) before += c; total += c; }
-      if (do_commit && R.has_rect) append_rect(T, before + __popc(rm & lt), R.rec, (int)((wave << 11) | (tid << 1) | 0), my_seed, R.nf);
-      // everything before ks is settled
-      if (lane == 0) {
-        const int first = warp * 32;
-        uint32_t keep = 0xffffffffu;
-        if (ks >= first + 32) keep = 0u;
-        else if (ks > first) keep = ~((1u << (ks - first)) - 1u);
-        S.pend[warp] &= keep;
-      }
-      __syncthreads();
-      if (tid == 0) { S.npend += total; S.has = 0; }
-      if (ks >= K) break;
+      if (do_commit && R.has_rect) append_rect(T, npend + before, R.rec, (int)((wave << 11) | (tid << 1) | 0), my_seed, R.nf);
+      npend += total;
+      settled = ks;
+      if (ks >= nsel) break;
       kstar = ks;
       n_redo++;
-      __syncthreads();
+      __syncthreads();                                                                     // (3) commits visible to the re-run
     }
     t_commit += clock64() - c2;
+    __syncthreads();
   }
-  if (tid == 0) *T.npend = min(S.npend, T.pend_cap);
+  if (tid == 0) *T.npend = min(npend, T.pend_cap);
   if (tid == 0 && T.prof) {
     T.prof[0] = t_sel; T.prof[1] = t_spec; T.prof[2] = t_commit - t_redo; T.prof[3] = t_redo; T.prof[4] = wave; T.prof[5] = n_redo;
     T.prof[6] = n_round; T.prof[7] = n_seed;
