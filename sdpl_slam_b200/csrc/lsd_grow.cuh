@@ -723,6 +723,93 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
+// region2rect (+ get_theta) by a whole warp: list / n / ra are warp-uniform, the result is returned in every lane.
+// 32 elements per step are fetched and transformed in parallel, then accumulated by every lane in list order through
+// shuffles, so the double sums are bit-identical to the sequential loops of the reference.
+__device__ __forceinline__ void coop_region2rect(const Task& T, const int* list, int n, double ra, Rect& rec) {
+  const int lane = threadIdx.x & 31, w = T.w;
+  double x = 0, y = 0, sum = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int e = b + lane;
+    double wgt = 0, qxw = 0, qyw = 0;
+    if (e < n) {
+      const int q = list[e];
+      const int qy = xy_y(q), qx = xy_x(q);
+      wgt = modgrad_of(T.g2[qy * w + qx]);
+      qxw = (double)qx * wgt; qyw = (double)qy * wgt;
+    }
+    const int m = min(32, n - b);
+    for (int j = 0; j < m; j++) { x += shfl_d(qxw, j); y += shfl_d(qyw, j); sum += shfl_d(wgt, j); }
+  }
+  x /= sum; y /= sum;
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int e = b + lane;
+    double t0 = 0, t1 = 0, t2 = 0;
+    if (e < n) {
+      const int q = list[e];
+      const int qy = xy_y(q), qx = xy_x(q);
+      const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[qy * w + qx]);
+      t0 = dy * dy * wgt; t1 = dx * dx * wgt; t2 = dx * dy * wgt;
+    }
+    const int m = min(32, n - b);
+    for (int j = 0; j < m; j++) { Ixx += shfl_d(t0, j); Iyy += shfl_d(t1, j); Ixy -= shfl_d(t2, j); }
+  }
+  const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
+  theta *= kDegToRad;
+  if (angle_diff(theta, ra) > T.prec) theta += kPI;
+  double dy_, dx_;
+  sincos(theta, &dy_, &dx_);
+  double l_min = 0, l_max = 0, w_min = 0, w_max = 0;      // min / max are order-independent: plain warp reductions
+  for (int e = lane; e < n; e += 32) {
+    const int q = list[e];
+    const int qy = xy_y(q), qx = xy_x(q);
+    const double rdx = (double)qx - x, rdy = (double)qy - y;
+    const double l = rdx * dx_ + rdy * dy_;
+    const double ww = -rdx * dy_ + rdy * dx_;
+    l_max = fmax(l_max, l); l_min = fmin(l_min, l);
+    w_max = fmax(w_max, ww); w_min = fmin(w_min, ww);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    l_max = fmax(l_max, shfl_d(l_max, lane ^ o)); l_min = fmin(l_min, shfl_d(l_min, lane ^ o));
+    w_max = fmax(w_max, shfl_d(w_max, lane ^ o)); w_min = fmin(w_min, shfl_d(w_min, lane ^ o));
+  }
+  rec.x1 = x + l_min * dx_; rec.y1 = y + l_min * dy_;
+  rec.x2 = x + l_max * dx_; rec.y2 = y + l_max * dy_;
+  rec.width = w_max - w_min;
+  rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx_; rec.dy = dy_; rec.prec = T.prec; rec.p = T.p;
+  if (rec.width < 1.0) rec.width = 1.0;
+}
+
+// refine: the re-growth tolerance from the angle spread of the region pixels within `width` of the seed (warp-cooperative,
+// sums in list order); UNMARK = sequential semantics (the region's pixels are released before the re-growth)
+template <bool UNMARK>
+__device__ __forceinline__ double coop_refine_tau(const Task& T, const int* list, int n, int sx, int sy, double seed_ang, double width) {
+  const int lane = threadIdx.x & 31, w = T.w;
+  double sm = 0, s_sum = 0;
+  int cnt = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int e = b + lane;
+    double d = 0; int use = 0;
+    if (e < n) {
+      const int qp = list[e];
+      const int q = xy_lin(qp, w);
+      if (UNMARK) T.state[q] = 0;
+      if (dist((double)sx, (double)sy, (double)xy_x(qp), (double)xy_y(qp)) < width) { d = angle_diff_signed(T.px[q].ang, seed_ang); use = 1; }
+    }
+    const uint32_t um = __ballot_sync(0xffffffffu, use);
+    const int m = min(32, n - b);
+    for (int j = 0; j < m; j++) {
+      if ((um >> j) & 1u) { const double dj = shfl_d(d, j); sm += dj; s_sum += dj * dj; ++cnt; }
+    }
+  }
+  const double mean_angle = sm / (double)cnt;
+  return 2.0 * sqrt((s_sum - 2.0 * mean_angle * sm) / (double)cnt + mean_angle * mean_angle);
+}
+
 __device__ void process_seed_coop(const Task& T, const int seed, int* const reg, SeedResult& R) {
   const int lane = threadIdx.x & 31;
   const int w = T.w, h = T.h;
@@ -799,87 +886,11 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
       R.nf = n;
       if (n < 2) break;
     }
-    // ---------------- region2rect (with get_theta), 32 elements per step ----------------
-    double x = 0, y = 0, sum = 0;
-    for (int b = 0; b < n; b += 32) {
-      const int e = b + lane;
-      double wgt = 0, qxw = 0, qyw = 0;
-      if (e < n) {
-        const int q = reg[e];
-        const int qy = xy_y(q), qx = xy_x(q);
-        wgt = modgrad_of(T.g2[qy * w + qx]);
-        qxw = (double)qx * wgt; qyw = (double)qy * wgt;
-      }
-      const int m = min(32, n - b);
-      for (int j = 0; j < m; j++) { x += shfl_d(qxw, j); y += shfl_d(qyw, j); sum += shfl_d(wgt, j); }
-    }
-    x /= sum; y /= sum;
-    double Ixx = 0, Iyy = 0, Ixy = 0;
-    for (int b = 0; b < n; b += 32) {
-      const int e = b + lane;
-      double t0 = 0, t1 = 0, t2 = 0;
-      if (e < n) {
-        const int q = reg[e];
-        const int qy = xy_y(q), qx = xy_x(q);
-        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[qy * w + qx]);
-        t0 = dy * dy * wgt; t1 = dx * dx * wgt; t2 = dx * dy * wgt;
-      }
-      const int m = min(32, n - b);
-      for (int j = 0; j < m; j++) { Ixx += shfl_d(t0, j); Iyy += shfl_d(t1, j); Ixy -= shfl_d(t2, j); }
-    }
-    const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
-    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
-                                           : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
-    theta *= kDegToRad;
-    if (angle_diff(theta, ra) > T.prec) theta += kPI;
-    double dy_, dx_;
-    sincos(theta, &dy_, &dx_);
-    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;      // min / max are order-independent: plain warp reductions
-    for (int e = lane; e < n; e += 32) {
-      const int q = reg[e];
-      const int qy = xy_y(q), qx = xy_x(q);
-      const double rdx = (double)qx - x, rdy = (double)qy - y;
-      const double l = rdx * dx_ + rdy * dy_;
-      const double ww = -rdx * dy_ + rdy * dx_;
-      l_max = fmax(l_max, l); l_min = fmin(l_min, l);
-      w_max = fmax(w_max, ww); w_min = fmin(w_min, ww);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      l_max = fmax(l_max, shfl_d(l_max, lane ^ o)); l_min = fmin(l_min, shfl_d(l_min, lane ^ o));
-      w_max = fmax(w_max, shfl_d(w_max, lane ^ o)); w_min = fmin(w_min, shfl_d(w_min, lane ^ o));
-    }
-    {
-      Rect& rec = R.rec;
-      rec.x1 = x + l_min * dx_; rec.y1 = y + l_min * dy_;
-      rec.x2 = x + l_max * dx_; rec.y2 = y + l_max * dy_;
-      rec.width = w_max - w_min;
-      rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx_; rec.dy = dy_; rec.prec = T.prec; rec.p = T.p;
-      if (rec.width < 1.0) rec.width = 1.0;
-    }
+    coop_region2rect(T, reg, n, ra, R.rec);
     const double density = (double)n / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
     if (state == 0) {
       if (T.refine <= 0 || density >= T.density_th) { R.has_rect = 1; break; }
-      // ---------------- refine: un-mark, tolerance from the angle spread near the seed ----------------
-      double sm = 0, s_sum = 0;
-      int cnt = 0;
-      for (int b = 0; b < n; b += 32) {
-        const int e = b + lane;
-        double d = 0; int use = 0;
-        if (e < n) {
-          const int qp = reg[e];
-          const int q = xy_lin(qp, w);
-          T.state[q] = 0;
-          if (dist((double)sx, (double)sy, (double)xy_x(qp), (double)xy_y(qp)) < R.rec.width) { d = angle_diff_signed(T.px[q].ang, seed_ang); use = 1; }
-        }
-        const uint32_t um = __ballot_sync(0xffffffffu, use);
-        const int m = min(32, n - b);
-        for (int j = 0; j < m; j++) {
-          if ((um >> j) & 1u) { const double dj = shfl_d(d, j); sm += dj; s_sum += dj * dj; ++cnt; }
-        }
-      }
-      const double mean_angle = sm / (double)cnt;
-      prec = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sm) / (double)cnt + mean_angle * mean_angle);
+      prec = coop_refine_tau<true>(T, reg, n, sx, sy, seed_ang, R.rec.width);
       __syncwarp();
       state = 1;
       continue;
@@ -893,6 +904,164 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
   }
   R.bx0 = bx0; R.bx1 = bx1; R.by0 = by0; R.by1 = by1;
   __syncwarp();
+}
+
+// The speculative pass of one wave, warp-synchronous: all 32 lanes of a warp call this together, `active` lanes own a seed.
+// Region growth runs per lane (divergent, each lane its own region); everything that is a loop over a finished region --
+// the rectangle fit and the refine statistics -- is done by the WHOLE warp for one lane's region at a time
+// (coop_region2rect / coop_refine_tau): ncu showed a third of the kernel's active time in those loops with exactly one
+// thread per warp running.  Arithmetic and its order are those of process_seed<true>.
+__device__ void speculate_wave(const Task& T, const bool active, const int seed, int* const reg, const int cap, const uint32_t stamp0,
+                               SeedResult& R) {
+  const int lane = threadIdx.x & 31;
+  const int w = T.w, h = T.h;
+  enum { P_GROW = 0, P_RECT, P_REFSTAT, P_REDUCE, P_DONE };
+  R.ok = 1; R.n1 = 0; R.n2_orig = 0; R.has_rect = 0; R.foff = 0; R.nf = 0;
+  const int sx = active ? seed % w : 0, sy = active ? seed / w : 0;
+  R.bx0 = R.bx1 = sx; R.by0 = R.by1 = sy;
+  int phase = active ? P_GROW : P_DONE;
+  int state = 0;                 // 0: first growth, 1: re-growth with the refined tolerance, 2: radius reduction passes
+  int* cur = reg;
+  int n = 0, capc = cap;
+  double prec = T.prec, ra = 0, rad_sq = 0;
+  uint32_t stamp = stamp0;
+  const double seed_ang = active ? T.px[seed].ang : 0.0;
+#pragma unroll 1
+  while (__any_sync(0xffffffffu, phase != P_DONE)) {
+    if (phase == P_GROW) {
+      // ---------------- region_grow (per lane) ----------------
+      bool aborted = false;
+      if (capc < 1 || ld_state(T.state + seed) > stamp) aborted = true;
+      else {
+        atomicMax(&T.state[seed], stamp);
+        cur[0] = xy_pack(sx, sy); n = 1;
+        ra = seed_ang;
+        double sn, cs;
+        sincos(ra, &sn, &cs);
+        float sumdx = (float)cs, sumdy = (float)sn;
+        int nxt = xy_pack(sx, sy);
+#pragma unroll 1
+        for (int i = 0; i < n && !aborted; i++) {
+          const int p = nxt;
+          const int n_start = n;
+          const int py = xy_y(p), px = xy_x(p);
+          uint32_t st[9];
+          PxA pa[9];
+          const int rofs[3] = {max(py - 1, 0) * w, py * w, min(py + 1, h - 1) * w};
+          const int cofs[3] = {max(px - 1, 0), px, min(px + 1, w - 1)};
+          uint32_t vmask = 0x1EFu;                                  // bits 0..8 without the centre
+          if (px == 0) vmask &= ~0x049u;
+          if (px == w - 1) vmask &= ~0x124u;
+          if (py == 0) vmask &= ~0x007u;
+          if (py == h - 1) vmask &= ~0x1C0u;
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            if (k == 4) continue;
+            const int q = rofs[k / 3] + cofs[k % 3];
+            st[k] = ld_state(T.state + q);
+            pa[k] = T.px[q];
+          }
+          if (i + 1 < n_start) nxt = cur[i + 1];
+          uint32_t cand = 0;
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            if (k == 4) continue;
+            const uint32_t sv = st[k];
+            if (!(sv & kUsed) && sv != stamp && pa[k].ang != kNotDef) cand |= 1u << k;
+          }
+          cand &= vmask;
+          while (cand) {
+            uint32_t al = 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+              if (k == 4) continue;
+              if ((cand >> k) & 1u) al |= (aligned_angle(pa[k].ang, ra, prec) ? 1u : 0u) << k;
+            }
+            if (!al) break;
+            const int k = __ffs(al) - 1;
+            uint32_t sk = 0; float ck = 0.f, sn_k = 0.f;
+#pragma unroll
+            for (int j = 0; j < 9; j++) if (j == k) { sk = st[j]; ck = pa[j].c; sn_k = pa[j].s; }
+            const int qx = px - 1 + k % 3, qy = py - 1 + k / 3;
+            if (sk > stamp || n >= capc) { aborted = true; break; }
+            atomicMax(&T.state[qy * w + qx], stamp);
+            const int qp = xy_pack(qx, qy);
+            if (n == i + 1) nxt = qp;
+            cur[n++] = qp;
+            R.bx0 = min(R.bx0, qx); R.bx1 = max(R.bx1, qx);
+            R.by0 = min(R.by0, qy); R.by1 = max(R.by1, qy);
+            sumdx = __fadd_rn(sumdx, ck);
+            sumdy = __fadd_rn(sumdy, sn_k);
+            ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
+            cand &= ~((2u << k) - 1u);
+          }
+        }
+      }
+      if (state == 0) { R.n1 = n; R.nf = n; } else { R.n2_orig = n; R.nf = n; }
+      if (aborted) { R.ok = 0; phase = P_DONE; }
+      else if (state == 0 ? (n < T.min_reg) : (n < 2)) phase = P_DONE;
+      else phase = P_RECT;
+    } else if (phase == P_REDUCE) {
+      // ---------------- one pass of reduce_region_radius (per lane; order-dependent swap removal) ----------------
+      rad_sq *= 0.75 * 0.75;
+      for (int i = 0; i < n; ++i) {
+        const int q = cur[i];
+        if (dist_sq((double)sx, (double)sy, (double)xy_x(q), (double)xy_y(q)) > rad_sq) {
+          cur[i] = cur[n - 1];
+          cur[n - 1] = q;
+          --n;
+          --i;
+        }
+      }
+      R.nf = n;
+      phase = n < 2 ? P_DONE : P_RECT;
+    }
+    __syncwarp();
+    // ---------------- rectangle fits, one region at a time by the whole warp ----------------
+    uint32_t m = __ballot_sync(0xffffffffu, phase == P_RECT);
+    while (m) {
+      const int L = __ffs(m) - 1;
+      m &= m - 1;
+      const int* lp = (const int*)(size_t)__shfl_sync(0xffffffffu, (unsigned long long)(size_t)cur, L);
+      const int ln = __shfl_sync(0xffffffffu, n, L);
+      const double lra = shfl_d(ra, L);
+      Rect rc;
+      coop_region2rect(T, lp, ln, lra, rc);
+      if (lane == L) R.rec = rc;
+    }
+    if (phase == P_RECT) {
+      const double density = (double)n / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
+      if (state == 0) {
+        if (T.refine <= 0 || density >= T.density_th) { R.has_rect = 1; phase = P_DONE; }
+        else phase = P_REFSTAT;
+      } else if (density >= T.density_th) { R.has_rect = 1; phase = P_DONE; }
+      else {
+        if (state == 1) {
+          const double r1 = dist_sq((double)sx, (double)sy, R.rec.x1, R.rec.y1), r2 = dist_sq((double)sx, (double)sy, R.rec.x2, R.rec.y2);
+          rad_sq = r1 > r2 ? r1 : r2;
+          state = 2;
+        }
+        phase = P_REDUCE;
+      }
+    }
+    // ---------------- refine statistics (speculative: nothing is un-marked), again one region at a time ----------------
+    m = __ballot_sync(0xffffffffu, phase == P_REFSTAT);
+    while (m) {
+      const int L = __ffs(m) - 1;
+      m &= m - 1;
+      const int* lp = (const int*)(size_t)__shfl_sync(0xffffffffu, (unsigned long long)(size_t)cur, L);
+      const int ln = __shfl_sync(0xffffffffu, n, L);
+      const int lsx = __shfl_sync(0xffffffffu, sx, L), lsy = __shfl_sync(0xffffffffu, sy, L);
+      const double lsa = shfl_d(seed_ang, L), lw = shfl_d(R.rec.width, L);
+      const double tau = coop_refine_tau<false>(T, lp, ln, lsx, lsy, lsa, lw);
+      if (lane == L) {
+        prec = tau;
+        cur = reg + n; capc = cap - n; R.foff = n; stamp = stamp0 | 1u;   // keep the first region: it is part of E
+        state = 1;
+        phase = P_GROW;
+      }
+    }
+  }
 }
 
 __device__ void grow_task_block(const Task& T, BlockShared& S) {
@@ -946,7 +1115,7 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
       n_round++;
       long long cr = clock64();
       if (kstar < 0) {
-        if (tid < nsel) process_seed_u(T, my_seed, my_reg, cap, stamp, true, R);
+        if (warp * 32 < nsel) speculate_wave(T, tid < nsel, my_seed, my_reg, cap, stamp, R);
       } else if (warp == (kstar >> 5)) {
         // the whole warp of kstar re-runs that seed sequentially (exact sequential semantics).  The commits of the previous
         // round may have taken the seed: then the sequential algorithm skips it
