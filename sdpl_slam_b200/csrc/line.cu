@@ -50,7 +50,7 @@ struct LineDev {
   unsigned long long lvl_frame, px_frame, lbd_frame, hist_frame, reg_frame;
   uint8_t *lvl, *scaled;
   lsd::PxA* px; int* g2; uint32_t* state; uint32_t* order;
-  uint32_t* hist; int* maxg2; int* ndef;
+  uint32_t* hist; int* maxg2; int* ndef; int* task_order;
   int* reg; lsd::Pending* pend; int pend_cap; int* npend;
   uint8_t* g; short* sdx; short* sdy;
   int* err;
@@ -308,10 +308,24 @@ __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::T
   T.rob_rect = D.rob_rect + (size_t)task * D.rob_w; T.rob = D.rob + (size_t)task * D.rob_w; T.rob_w = D.rob_w_run;
 }
 
+// L5 scheduling.  A task's run time follows its number of candidate seeds, and tasks differ by 2x within a batch; CTAs are
+// handed to the SMs in blockIdx order, so the longest tasks get the lowest indices (longest-processing-time-first) and the
+// short ones fill the tail of the launch.
+__global__ void k_lsd_task_rank(LineDev D, int ntask) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntask) return;
+  const int mine = D.ndef[t];
+  int rank = 0;
+  for (int u = 0; u < ntask; u++) {
+    const int v = D.ndef[u];
+    rank += (v > mine || (v == mine && u < t)) ? 1 : 0;
+  }
+  D.task_order[rank] = t;
+}
+
 __global__ void __launch_bounds__(32) k_lsd_grow(LineDev D) {
   __shared__ lsd::RobShared S;
-  // big octave-0 tasks first: blockIdx.x enumerates (octave-major, frame-minor)
-  const int o = blockIdx.x / D.B, f = blockIdx.x % D.B;
+  const int task = D.task_order[blockIdx.x], f = task / D.nl, o = task % D.nl;
   lsd::Task T;
   make_task(D, f, o, T);
   if (D.serial_mode == 2) lsd::grow_task_rob(T, S);               // 2: dynamic lane scheduling + re-order buffer (experimental)
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LineDev D) {
 template <int NW, int MINB>
 __global__ void __launch_bounds__(32 * NW, MINB) k_lsd_grow_block(LineDev D) {
   __shared__ lsd::BlockShared S;
-  const int o = blockIdx.x / D.B, f = blockIdx.x % D.B;
+  const int task = D.task_order[blockIdx.x], f = task / D.nl, o = task % D.nl;
   lsd::Task T;
   make_task(D, f, o, T);
   lsd::grow_task_block(T, S);
@@ -675,7 +689,7 @@ struct sdpl_line {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
-  DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
+  DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -817,6 +831,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->hist.reserve(sizeof(uint32_t) * D.hist_frame * B))) return rc;
   if ((rc = o->maxg2.reserve(sizeof(int) * nl * B))) return rc;
   if ((rc = o->ndef.reserve(sizeof(int) * nl * B))) return rc;
+  if ((rc = o->torder.reserve(sizeof(int) * nl * B))) return rc;
   if ((rc = o->reg.reserve(sizeof(int) * D.reg_frame * B))) return rc;
   if ((rc = o->pend.reserve(sizeof(lsd::Pending) * (size_t)D.pend_cap * nl * B))) return rc;
   if ((rc = o->npend.reserve(sizeof(int) * nl * B))) return rc;
@@ -857,7 +872,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   }
   D.lvl = o->lvl.as<uint8_t>(); D.scaled = o->scaled.as<uint8_t>(); D.px = o->px.as<lsd::PxA>(); D.g2 = o->g2.as<int>();
   D.state = o->state.as<uint32_t>(); D.order = o->order.as<uint32_t>(); D.hist = o->hist.as<uint32_t>();
-  D.maxg2 = o->maxg2.as<int>(); D.ndef = o->ndef.as<int>(); D.reg = o->reg.as<int>(); D.pend = o->pend.as<lsd::Pending>();
+  D.maxg2 = o->maxg2.as<int>(); D.ndef = o->ndef.as<int>(); D.task_order = o->torder.as<int>(); D.reg = o->reg.as<int>(); D.pend = o->pend.as<lsd::Pending>();
   D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sdx = o->sdx.as<short>(); D.sdy = o->sdy.as<short>();
   D.err = o->err.as<int>(); D.prof = o->prof.as<long long>(); D.lgam = o->lgam.as<double>(); D.lgam_n = kLgamN;
   D.rob_rect = o->robrect.as<lsd::Rect>(); D.rob = o->rob.as<lsd::RobEntry>(); D.rob_w = o->rob_w;
@@ -903,6 +918,8 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     k_lsd_sort<true><<<dim3(div_up(D.O[l].nchunks, kSortWarps), B), kSortWarps * 32, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
+  k_lsd_task_rank<<<div_up(nl * B, 128), 128, 0, st>>>(D, nl * B);
+  SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_sort");
   if (o->serial_mode == 0) {
     // warps per task / CTAs per SM: 8 warps and one CTA per SM (256-seed waves, shortest latency) while every task gets an
@@ -1021,7 +1038,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   if (!o) return;
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
-  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->reg, &o->pend, &o->npend,
+  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
                     &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);

@@ -1080,18 +1080,31 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
     // ---- warp 0 selects the next (up to) K free seeds in order ----
     if (warp == 0) {
       int cursor = S.cursor, nsel = 0;
+      // four blocks of 32 list entries per trip: the two dependent loads (list entry, its state word) of all four are in
+      // flight together; the blocks are then consumed in order exactly as one at a time
       while (nsel < K && cursor < T.ndef) {
-        const int idx = cursor + lane;
-        const int p = idx < T.ndef ? (int)T.order[idx] : -1;
-        const bool fr = p >= 0 && !(ld_state(T.state + (p >= 0 ? p : 0)) & kUsed);
-        const uint32_t m = __ballot_sync(0xffffffffu, fr);
-        const int c = __popc(m);
-        const int take = min(c, K - nsel);
-        const int rank = __popc(m & lt);
-        if (fr && rank < take) S.sel[nsel + rank] = p;
-        if (c > take) cursor += (int)__fns(m, 0, take) + 1;
-        else cursor += 32;
-        nsel += take;
+        int p[4];
+        bool fr[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int idx = cursor + j * 32 + lane;
+          p[j] = idx < T.ndef ? (int)T.order[idx] : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) fr[j] = !(ld_state(T.state + (p[j] >= 0 ? p[j] : 0)) & kUsed) && p[j] >= 0;
+        bool stop = false;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (stop) continue;
+          const uint32_t m = __ballot_sync(0xffffffffu, fr[j]);
+          const int c = __popc(m);
+          const int take = min(c, K - nsel);
+          const int rank = __popc(m & lt);
+          if (fr[j] && rank < take) S.sel[nsel + rank] = p[j];
+          nsel += take;
+          if (c > take) { cursor += (int)__fns(m, 0, take) + 1; stop = true; }
+          else { cursor += 32; stop = nsel >= K || cursor >= T.ndef; }
+        }
       }
       if (lane == 0) { S.cursor = cursor; S.nsel = nsel; }
     }
