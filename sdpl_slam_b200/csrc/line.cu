@@ -368,16 +368,20 @@ __global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
   }
 }
 
-// second pass over the small rectangles whose first evaluation failed (compacted: uniform work per thread)
-__global__ void __launch_bounds__(64) k_lsd_nfa_rest(LineDev D) {
+// second pass over the small rectangles whose first evaluation failed: up to 25 more evaluations each, five at a time
+// (lsd::validate_rest_warp).  A warp wants a dozen rectangles to keep its six groups busy: the number of warps that work on a
+// task follows the length of its list
+constexpr int kRestBlocks = 16;
+__global__ void __launch_bounds__(128) k_lsd_nfa_rest(LineDev D) {
   const int task = blockIdx.y;
   const int f = task / D.nl, o = task % D.nl;
   const int nf = D.nbig[(size_t)D.nl * D.B + task];
-  if ((int)(blockIdx.x * blockDim.x) >= nf) return;
+  const int nwarps = min(max((nf + 11) / 12, 1), (int)gridDim.x * 4);
+  const int wg = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (nf == 0 || (int)blockIdx.x * 4 >= nwarps) return;
   lsd::Task T;
   make_task(D, f, o, T);
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nf; k += gridDim.x * blockDim.x)
-    lsd::validate_rest(T, D.bigidx[(size_t)task * D.pend_cap + D.pend_cap - 1 - k]);
+  if (wg < nwarps) lsd::validate_rest_warp(T, D.bigidx + (size_t)task * D.pend_cap + D.pend_cap - 1, nf, wg, nwarps);
 }
 
 __global__ void __launch_bounds__(128) k_lsd_nfa_big(LineDev D) {
@@ -948,7 +952,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   SDPL_LAUNCH_CHECK();
   k_lsd_nfa_big<<<dim3(64, nl * B), 128, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
-  k_lsd_nfa_rest<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
+  k_lsd_nfa_rest<<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_nfa");
   k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());

@@ -1763,11 +1763,84 @@ __device__ bool validate_first(const Task& T, int i) {
   *reinterpret_cast<double*>(T.pend[i].seg) = v;
   return false;
 }
-__device__ void validate_rest(const Task& T, int i) {
-  Rect rec = T.pend[i].rec;
-  const double v0 = *reinterpret_cast<const double*>(T.pend[i].seg);
-  const double v = rect_improve_rest<false>(T, rec, v0);
-  write_segment(T, i, rec, v > T.log_eps);
+// Variation `n` (0..4) of refinement stage `stage` (0..4) of rect_improve, built from the stage's starting rectangle with the
+// same repeated operations as the sequential loops (so the doubles are identical).  Inside a stage the rectangle tried at
+// iteration n does not depend on the outcome of iterations 0..n-1 -- only `rec`/`log_nfa` do -- which is what lets five lanes
+// evaluate a stage at once.  Returns false when the reference loop skips that iteration (width cannot shrink further).
+__device__ __forceinline__ bool rect_variation(int stage, int n, Rect& r) {
+  const double delta = 0.5, delta_2 = delta / 2.0;
+  if (stage == 0) {
+    for (int j = 0; j <= n; j++) r.p /= 2;
+    r.prec = r.p * kPI;
+    return true;
+  }
+  if (stage == 4) {
+    if (!((r.width - delta) >= 0.5)) return false;
+    for (int j = 0; j <= n; j++) r.p /= 2;
+    r.prec = r.p * kPI;
+    return true;
+  }
+  for (int j = 0; j <= n; j++) {
+    if (!((r.width - delta) >= 0.5)) return false;
+    if (stage == 2) { r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2; r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2; }
+    if (stage == 3) { r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2; r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2; }
+    r.width -= delta;
+  }
+  return true;
+}
+
+// Pass 2 by one warp: six rectangles at a time, five lanes each (lanes 30/31 idle).  Every trip of the loop is one stage of
+// rect_improve for the six rectangles: lane (g, n) evaluates variation n, the five values are folded in iteration order
+// (strict >, first maximum wins), the group moves to the next stage or settles the rectangle and takes the next one of the
+// warp's share (positions first, first + stride, ... of the failed list, counted from the back of `back`).
+__device__ void validate_rest_warp(const Task& T, const int* back, int nf, int first, int stride) {
+  const int lane = threadIdx.x & 31, grp = lane / 5, var = lane - grp * 5;
+  const bool worker = grp < 6;
+  const int gl0 = worker ? grp * 5 : 25;
+  int next = first, idx = -1, stage = 0;
+  Rect rec;
+  double log_nfa = 0;
+#pragma unroll 1
+  while (true) {
+#pragma unroll 1
+    for (int g = 0; g < 6; g++) {
+      const bool idle = __shfl_sync(0xffffffffu, idx, g * 5) < 0;
+      if (idle && next < nf) {
+        if (grp == g) {
+          idx = back[-next];
+          rec = T.pend[idx].rec;
+          log_nfa = *reinterpret_cast<const double*>(T.pend[idx].seg);
+          stage = 0;
+        }
+        next += stride;
+      }
+    }
+    const bool busy = worker && idx >= 0;
+    if (!__any_sync(0xffffffffu, busy)) break;
+    double v = 0;
+    int have = 0;
+    if (busy) {
+      Rect r = rec;
+      have = rect_variation(stage, var, r) ? 1 : 0;
+      if (have) v = rect_nfa<false>(T, r);
+    }
+    int best = -1;
+    double bv = log_nfa;
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+      const double vn = shfl_d(v, gl0 + n);
+      const int hn = __shfl_sync(0xffffffffu, have, gl0 + n);
+      if (hn && vn > bv) { bv = vn; best = n; }
+    }
+    if (busy) {
+      if (best >= 0) { rect_variation(stage, best, rec); log_nfa = bv; }
+      ++stage;
+      if (log_nfa > T.log_eps || stage == 5) {
+        if (var == 0) write_segment(T, idx, rec, log_nfa > T.log_eps);
+        idx = -1;
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ void write_segment(const Task& T, int i, const Rect& rec, bool acc) {
