@@ -4,7 +4,7 @@
 // frames (and, where possible, all pyramid levels) of a chunk.  Device data layout per chunk of B frames:
 //   pyr   [B][sum_l (h_l+38)*pstride_l]   u8   padded pyramid planes (19 px reflect-101 border)      (K1)
 //   score [B][sum_l h_l*sstride_l]        u8   FAST-9/16 corner score, 0 where < minThFAST           (K2)
-//   blur  [B][sum_l h_l*sstride_l]        u8   7x7 sigma-2 blurred level interiors                    (K6)
+//   blur  [B][sum_l (h_l+38)*pstride_l]   u8   7x7 sigma-2 blurred levels, same padded geometry as pyr (K6)
 //   cell  [B][ncells]                     u32  per 30-px cell: (threshold<<16) | keypoint count       (K3a)
 //   cand  [B][sum_l cand_cap_l]           u32 (y<<16|x) + u8 response, cell-major/row-major order     (K3b)
 //   kp    [B][sum_l kp_cap_l]             u32 (y<<16|x) + u8 response in quadtree list order          (K4)
@@ -36,6 +36,7 @@ struct CellDev { short level, x0, y0, x1, y1, sx, sy, pad; };  // window [x0,x1)
 struct OrbDev {
   int nl, B, ini_th, min_th;
   unsigned long long pyr_frame, s_frame;
+  int blur_tiles;
   int cells_per_frame, cand_per_frame, kp_per_frame;
   uint8_t *pyr, *score, *blur;
   uint32_t* cellinfo;
@@ -602,39 +603,63 @@ __global__ void __launch_bounds__(kQT) k_quadtree(OrbDev D, int cap) {
 // K6: GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 on the un-padded level (ORBextractor.cc:1083-1084).
 //     Fixed point: Q8.8 kernel [18,34,48,56,48,34,18], horizontal Q8.8, vertical Q16.16, (v + 2^15) >> 16.
 // ------------------------------------------------------------------------------------------------
-constexpr int kBT_W = 64, kBT_H = 16;
-__global__ void __launch_bounds__(256) k_blur7(OrbDev D) {
-  __shared__ uint8_t in[kBT_H + 6][kBT_W + 8];
-  __shared__ unsigned short hz[kBT_H + 6][kBT_W];
-  int t = blockIdx.x, l = 0;
+//     The padded pyramid plane already holds the reflect-101 border the blur needs (19 >= 3 px), so the kernel reads it as
+//     aligned 32-bit words with no border arithmetic, and the blurred plane uses the same padded geometry (aligned word
+//     stores).  A thread owns one word = four columns and walks down kBlurRows rows: the seven taps of the horizontal pass
+//     are two dp4a on byte windows cut from (previous | own | next) word -- the neighbours' words come by shuffle --, the
+//     seven horizontal results of each column slide through registers for the vertical pass.  One warp = 128 columns.
+constexpr int kBlurRows = 32;
+__global__ void __launch_bounds__(128) k_blur7(OrbDev D) {
+  const int lane = threadIdx.x & 31;
+  int t = blockIdx.x * 4 + (threadIdx.x >> 5), l = 0;
+  if (t >= D.blur_tiles) return;
 #pragma unroll 1
   for (int i = 1; i < D.nl; i++) if (t >= D.L[i].blur_tile_base) l = i;
   const LvlDev& L = D.L[l];
   t -= L.blur_tile_base;
-  int tx = t % L.blur_tiles_x, ty = t / L.blur_tiles_x;
-  int x0 = tx * kBT_W, y0 = ty * kBT_H;
-  const uint8_t* img = D.pyr + (size_t)blockIdx.y * D.pyr_frame + L.pyr_off + (size_t)kBorder * L.pstride + kBorder;
-  for (int i = threadIdx.x; i < (kBT_H + 6) * (kBT_W + 6); i += 256) {
-    int yy = i / (kBT_W + 6), xx = i - yy * (kBT_W + 6);
-    int gy = reflect101(min(y0 - 3 + yy, L.h + 2), L.h), gx = reflect101(min(x0 - 3 + xx, L.w + 2), L.w);
-    in[yy][xx] = img[(size_t)gy * L.pstride + gx];
-  }
-  __syncthreads();
-  const int k0 = 18, k1 = 34, k2 = 48, k3 = 56;
-  for (int i = threadIdx.x; i < (kBT_H + 6) * kBT_W; i += 256) {
-    int yy = i / kBT_W, xx = i % kBT_W;
-    const uint8_t* p = &in[yy][xx];
-    hz[yy][xx] = (unsigned short)(k0 * (p[0] + p[6]) + k1 * (p[1] + p[5]) + k2 * (p[2] + p[4]) + k3 * p[3]);
-  }
-  __syncthreads();
-  uint8_t* out = D.blur + (size_t)blockIdx.y * D.s_frame + L.s_off;
-  for (int i = threadIdx.x; i < kBT_H * kBT_W; i += 256) {
-    int yy = i / kBT_W, xx = i % kBT_W;
-    int gx = x0 + xx, gy = y0 + yy;
-    if (gx >= L.w || gy >= L.h) continue;
-    uint32_t v = k0 * ((uint32_t)hz[yy][xx] + hz[yy + 6][xx]) + k1 * ((uint32_t)hz[yy + 1][xx] + hz[yy + 5][xx]) +
-                 k2 * ((uint32_t)hz[yy + 2][xx] + hz[yy + 4][xx]) + k3 * (uint32_t)hz[yy + 3][xx];
-    out[(size_t)gy * L.sstride + gx] = (uint8_t)min(255u, (v + (1u << 15)) >> 16);
+  const int tx = t % L.blur_tiles_x, ty = t / L.blur_tiles_x;
+  // words of a padded row that overlap the interior: px 16.. (word 4) to px kBorder + w - 1
+  const int w_first = kBorder / 4, w_last = (kBorder + L.w - 1) / 4;
+  const int word = min(w_first + tx * 32 + lane, w_last + 1);              // lanes past the end feed their left neighbour only
+  const bool store = w_first + tx * 32 + lane <= w_last;
+  const int y0 = ty * kBlurRows, nrows = min(kBlurRows, L.h - y0);
+  const size_t plane = (size_t)blockIdx.y * D.pyr_frame + L.pyr_off;
+  const int ws = L.pstride / 4;                                            // words per row
+  const uint32_t* in = (const uint32_t*)(D.pyr + plane) + (size_t)(kBorder + y0 - 3) * ws + word;
+  uint32_t* out = (uint32_t*)(D.blur + plane) + (size_t)(kBorder + y0) * ws + word;
+  const uint32_t K_lo = 18u | (34u << 8) | (48u << 16) | (56u << 24), K_hi = 48u | (34u << 8) | (18u << 16);
+  uint32_t hz[7][4];
+#pragma unroll
+  for (int k = 0; k < 7; k++) { hz[k][0] = hz[k][1] = hz[k][2] = hz[k][3] = 0; }
+#pragma unroll 1
+  for (int i0 = 0; i0 < nrows + 6; i0 += 7) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      const int i = i0 + k;
+      if (i < nrows + 6) {                                                 // warp-uniform
+        const uint32_t cur = in[(size_t)i * ws];
+        uint32_t prev = __shfl_up_sync(0xffffffffu, cur, 1), next = __shfl_down_sync(0xffffffffu, cur, 1);
+        if (lane == 0) prev = in[(size_t)i * ws - 1];
+        if (lane == 31) next = in[(size_t)i * ws + 1];
+        hz[k][0] = __dp4a(__funnelshift_r(prev, cur, 8), K_lo, __dp4a(__funnelshift_r(cur, next, 8), K_hi, 0u));
+        hz[k][1] = __dp4a(__funnelshift_r(prev, cur, 16), K_lo, __dp4a(__funnelshift_r(cur, next, 16), K_hi, 0u));
+        hz[k][2] = __dp4a(__funnelshift_r(prev, cur, 24), K_lo, __dp4a(__funnelshift_r(cur, next, 24), K_hi, 0u));
+        hz[k][3] = __dp4a(cur, K_lo, __dp4a(next, K_hi, 0u));
+        if (i >= 6) {
+          uint32_t v[4];
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            v[c] = 56u * hz[(k + 4) % 7][c] + (1u << 15);
+            v[c] += 18u * (hz[(k + 1) % 7][c] + hz[k][c]);
+            v[c] += 34u * (hz[(k + 2) % 7][c] + hz[(k + 6) % 7][c]);
+            v[c] += 48u * (hz[(k + 3) % 7][c] + hz[(k + 5) % 7][c]);
+          }
+          // byte 2 of every sum (sum of the weights is 2^16: the result cannot exceed 255)
+          const uint32_t lo = __byte_perm(v[0], v[1], 0x0062), hi = __byte_perm(v[2], v[3], 0x0062);
+          if (store) out[(size_t)(i - 6) * ws] = __byte_perm(lo, hi, 0x5410);
+        }
+      }
+    }
   }
 }
 
@@ -688,7 +713,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(OrbDev D, sdpl_keypoint
   const float factorPI = (float)(3.14159265358979323846 / 180.f);
   const float ar = __fmul_rn(angle, factorPI);
   const float a = (float)cos((double)ar), b = (float)sin((double)ar);
-  const uint8_t* cb = D.blur + (size_t)f * D.s_frame + L.s_off + (size_t)ky * L.sstride + kx;
+  const uint8_t* cb = D.blur + (size_t)f * D.pyr_frame + L.pyr_off + (size_t)(kBorder + ky) * L.pstride + kBorder + kx;
   const signed char* pat = g_pattern + lane * 32;
   int val = 0;
 #pragma unroll
@@ -698,7 +723,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(OrbDev D, sdpl_keypoint
     int c0 = cv_round_f(__fsub_rn(__fmul_rn((float)px0, a), __fmul_rn((float)py0, b)));
     int r1 = cv_round_f(__fadd_rn(__fmul_rn((float)px1, b), __fmul_rn((float)py1, a)));
     int c1 = cv_round_f(__fsub_rn(__fmul_rn((float)px1, a), __fmul_rn((float)py1, b)));
-    int t0 = cb[(ptrdiff_t)r0 * L.sstride + c0], t1 = cb[(ptrdiff_t)r1 * L.sstride + c1];
+    int t0 = cb[(ptrdiff_t)r0 * L.pstride + c0], t1 = cb[(ptrdiff_t)r1 * L.pstride + c1];
     val |= (t0 < t1) << t;
   }
   desc[((size_t)f * capacity + o) * 32 + lane] = (uint8_t)val;
@@ -807,8 +832,8 @@ static int orb_setup(sdpl_orb* o, int w, int h, int B) {
     L.fast_tiles_x = dw > 0 ? div_up(dw, kFT_W) : 0;
     int fty = dh > 0 ? div_up(dh, kFT_H) : 0;
     L.fast_tile_base = ft; ft += L.fast_tiles_x * fty;
-    L.blur_tiles_x = div_up(L.w, kBT_W);
-    L.blur_tile_base = bt; bt += L.blur_tiles_x * div_up(L.h, kBT_H);
+    L.blur_tiles_x = div_up((kBorder + L.w - 1) / 4 - kBorder / 4 + 1, 32);
+    L.blur_tile_base = bt; bt += L.blur_tiles_x * div_up(L.h, kBlurRows);
     // resize tables for level l from level l-1 (cv::resize INTER_LINEAR, fixed-point Q11)
     L.area_fast = 0;
     if (l > 0) {
@@ -843,13 +868,13 @@ static int orb_setup(sdpl_orb* o, int w, int h, int B) {
   }
   D.pyr_frame = align_up(pyr_off, 256); D.s_frame = align_up(s_off, 256);
   D.cells_per_frame = cell_base; D.cand_per_frame = cand_off; D.kp_per_frame = kp_off;
-  o->fast_tiles = ft; o->blur_tiles = bt; o->kp_cap_total = kp_off;
+  o->fast_tiles = ft; o->blur_tiles = bt; D.blur_tiles = bt; o->kp_cap_total = kp_off;
   o->qt_cap = 64;
   for (int l = 0; l < nl; l++) o->qt_cap = std::max(o->qt_cap, D.L[l].kp_cap + 8);
   int rc;
   if ((rc = o->pyr.reserve(D.pyr_frame * B))) return rc;
   if ((rc = o->score.reserve(D.s_frame * B))) return rc;
-  if ((rc = o->blur.reserve(D.s_frame * B))) return rc;
+  if ((rc = o->blur.reserve(D.pyr_frame * B))) return rc;
   if ((rc = o->cellinfo.reserve(sizeof(uint32_t) * (size_t)std::max(1, cell_base) * B))) return rc;
   if ((rc = o->cand_xy.reserve(sizeof(uint32_t) * (size_t)cand_off * B))) return rc;
   if ((rc = o->cand_resp.reserve((size_t)cand_off * B))) return rc;
@@ -935,7 +960,7 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "quadtree");
-  k_blur7<<<dim3(o->blur_tiles, B), 256, 0, st>>>(D);
+  k_blur7<<<dim3(div_up(o->blur_tiles, 4), B), 128, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "blur7");
   k_orient_describe<<<dim3(div_up(D.kp_per_frame, 8), B), 256, 0, st>>>(D, d_kps, d_desc, capacity, d_n_out);
@@ -1156,7 +1181,7 @@ int sdpl_orb_blurred_level(sdpl_orb* o, int frame, int level, uint8_t* out, int 
   if (out_stride < L.w) return SDPL_ERR_ARG;
   SDPL_CUDA(cudaSetDevice(o->device));
   SDPL_CUDA(cudaStreamSynchronize(o->stream));
-  SDPL_CUDA(cudaMemcpy2D(out, out_stride, o->D.blur + (size_t)frame * o->D.s_frame + L.s_off, L.sstride, L.w, L.h,
+  SDPL_CUDA(cudaMemcpy2D(out, out_stride, o->D.blur + (size_t)frame * o->D.pyr_frame + L.pyr_off + (size_t)kBorder * L.pstride + kBorder, L.pstride, L.w, L.h,
                          cudaMemcpyDeviceToHost));
   return SDPL_OK;
 }
