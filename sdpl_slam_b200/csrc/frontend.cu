@@ -89,7 +89,8 @@ int sdpl_frontend_create(sdpl_frontend** out, int nfeatures, float scale, int nl
     int lo = 0, hi = 0;
     SDPL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     for (cudaStream_t* s : {&f->s_io, &f->s_orb, &f->s_pm, &f->s_lm, &f->s_out}) SDPL_CUDA(cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, lo));
-    SDPL_CUDA(cudaStreamCreateWithPriority(&f->s_line, cudaStreamNonBlocking, hi));
+    const char* lp = getenv("SDPL_FE_LINE_PRIO");
+    SDPL_CUDA(cudaStreamCreateWithPriority(&f->s_line, cudaStreamNonBlocking, (lp && !strcmp(lp, "high")) ? hi : lo));
   }
   for (FeSlot& S : f->slot)
     for (cudaEvent_t* e : {&S.ev_in, &S.ev_orb, &S.ev_line, &S.ev_pm, &S.ev_lm}) SDPL_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));

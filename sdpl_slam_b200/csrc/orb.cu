@@ -40,6 +40,7 @@ struct OrbDev {
   int cells_per_frame, cand_per_frame, kp_per_frame;
   uint8_t *pyr, *score, *blur;
   uint32_t* cellinfo;
+  uint2* cellmask; int mask_words;     // per cell: (maximum, maximum >= iniThFAST) bit masks, 32 pixels per entry
   uint32_t* cand_xy; uint8_t* cand_resp; unsigned short* cand_node;
   int* n_cand; int* n_kp;
   uint32_t* kp_xy; uint8_t* kp_resp;
@@ -228,7 +229,9 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
 //     Keypoint at threshold t  <=>  score >= t and score > all 8 neighbours inside the cell interior.
 //     Cell uses iniThFAST unless that yields zero keypoints, then minThFAST.
 // ------------------------------------------------------------------------------------------------
-template <bool WRITE>
+//     Two launches: k_cell_nms evaluates the maxima once and keeps them as bit masks (32 pixels per word, one word for
+//     "local maximum", one for "local maximum with score >= iniThFAST"); k_cell_emit turns the masks of the threshold the
+//     cell ended up with into the ordered candidate list.
 __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
   __shared__ uint8_t sm[8][kCellApron * kCellApron];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
   const LvlDev& L = D.L[cd.level];
   int ix0 = cd.x0 + 3, iy0 = cd.y0 + 3, iw = cd.x1 - cd.x0 - 6, ih = cd.y1 - cd.y0 - 6;
   uint32_t* info = D.cellinfo + (size_t)f * D.cells_per_frame + c;
-  if (iw <= 0 || ih <= 0) { if (!WRITE && lane == 0) *info = (uint32_t)D.ini_th << 16; return; }
+  if (iw <= 0 || ih <= 0) { if (lane == 0) *info = (uint32_t)D.ini_th << 16; return; }
   const uint8_t* sc = D.score + (size_t)f * D.s_frame + L.s_off;
   uint8_t* s = sm[warp];
   const int aw = iw + 2, ah = ih + 2;
@@ -255,21 +258,8 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
     }
   }
   __syncwarp();
-  int th = D.ini_th;
-  uint32_t base = 0;
-  if (WRITE) {
-    th = (int)(*info >> 16);
-    // offset of this cell = sum of the counts of the preceding cells of the same level
-    int acc = 0;
-    const uint32_t* lv = D.cellinfo + (size_t)f * D.cells_per_frame + L.cell_base;
-    for (int i = lane; i < c - L.cell_base; i += 32) acc += (int)(lv[i] & 0xFFFF);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    base = (uint32_t)acc;
-  }
   int cnt_hi = 0, cnt_lo = 0;
-  uint32_t* oxy = D.cand_xy + (size_t)f * D.cand_per_frame + L.cand_off;
-  uint8_t* ors = D.cand_resp + (size_t)f * D.cand_per_frame + L.cand_off;
+  uint2* masks = D.cellmask + ((size_t)f * D.cells_per_frame + c) * D.mask_words;
   const int npx = iw * ih;
   int yy = lane / iw, xx = lane - yy * iw;
   for (int i0 = 0; i0 < npx; i0 += 32) {
@@ -281,33 +271,70 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
       ismax = v > 0 && v > p[-1] && v > p[1] && v > p[-aw - 1] && v > p[-aw] && v > p[-aw + 1] && v > p[aw - 1] &&
               v > p[aw] && v > p[aw + 1];
     }
-    if (!WRITE) {
-      cnt_lo += __popc(__ballot_sync(0xffffffffu, ismax));
-      cnt_hi += __popc(__ballot_sync(0xffffffffu, ismax && v >= D.ini_th));
-    } else {
-      bool keep = ismax && v >= th;
-      uint32_t m = __ballot_sync(0xffffffffu, keep);
-      if (keep) {
-        uint32_t o = base + __popc(m & ((1u << lane) - 1));
-        if (o < (uint32_t)L.cand_cap) {
-          // cell-local FAST coordinate + cell shift (j*wCell, i*hCell): border-relative coordinates
-          int kx = (xx + 3) + cd.sx, ky = (yy + 3) + cd.sy;
-          oxy[o] = ((uint32_t)ky << 16) | (uint32_t)kx;
-          ors[o] = (uint8_t)v;
-        } else {
-          atomicExch(D.err, SDPL_ERR_OVERFLOW);
-        }
-      }
-      base += __popc(m);
-    }
+    const uint32_t m_lo = __ballot_sync(0xffffffffu, ismax), m_hi = __ballot_sync(0xffffffffu, ismax && v >= D.ini_th);
+    cnt_lo += __popc(m_lo);
+    cnt_hi += __popc(m_hi);
+    if (lane == 0) masks[i0 >> 5] = make_uint2(m_lo, m_hi);
     xx += 32;
     while (xx >= iw) { xx -= iw; yy++; }
   }
-  if (!WRITE && lane == 0) {
+  if (lane == 0) {
     int t = cnt_hi > 0 ? D.ini_th : D.min_th;
     int n = cnt_hi > 0 ? cnt_hi : cnt_lo;
     if (n > 0xFFFF) { n = 0xFFFF; atomicExch(D.err, SDPL_ERR_OVERFLOW); }
     *info = ((uint32_t)t << 16) | (uint32_t)n;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cell_emit(OrbDev D) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int c = blockIdx.x * 8 + warp;
+  int f = blockIdx.y;
+  if (c >= D.cells_per_frame) return;
+  CellDev cd = D.cells[c];
+  const LvlDev& L = D.L[cd.level];
+  const int ix0 = cd.x0 + 3, iy0 = cd.y0 + 3, iw = cd.x1 - cd.x0 - 6, ih = cd.y1 - cd.y0 - 6;
+  if (iw <= 0 || ih <= 0) return;
+  const uint32_t info = D.cellinfo[(size_t)f * D.cells_per_frame + c];
+  if ((info & 0xFFFFu) == 0) return;
+  const bool hi = (int)(info >> 16) == D.ini_th;
+  // offset of this cell = sum of the counts of the preceding cells of the same level
+  int acc = 0;
+  const uint32_t* lv = D.cellinfo + (size_t)f * D.cells_per_frame + L.cell_base;
+  for (int i = lane; i < c - L.cell_base; i += 32) acc += (int)(lv[i] & 0xFFFF);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  uint32_t base = (uint32_t)acc;
+  const uint8_t* sc = D.score + (size_t)f * D.s_frame + L.s_off;
+  uint32_t* oxy = D.cand_xy + (size_t)f * D.cand_per_frame + L.cand_off;
+  uint8_t* ors = D.cand_resp + (size_t)f * D.cand_per_frame + L.cand_off;
+  const uint2* masks = D.cellmask + ((size_t)f * D.cells_per_frame + c) * D.mask_words;
+  const int nwords = (iw * ih + 31) >> 5;
+  for (int g0 = 0; g0 < nwords; g0 += 32) {
+    const int g = g0 + lane;
+    uint32_t m = 0;
+    if (g < nwords) { const uint2 mm = masks[g]; m = hi ? mm.y : mm.x; }
+    // exclusive prefix of the set bits over the 32 words of this trip
+    const int n = __popc(m);
+    int pre = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+    uint32_t o = base + (uint32_t)(pre - n);
+    base += (uint32_t)__shfl_sync(0xffffffffu, pre, 31);
+    while (m) {
+      const int bit = __ffs(m) - 1;
+      m &= m - 1;
+      const int i = g * 32 + bit;
+      const int yy = i / iw, xx = i - yy * iw;
+      if (o < (uint32_t)L.cand_cap) {
+        // cell-local FAST coordinate + cell shift (j*wCell, i*hCell): border-relative coordinates
+        oxy[o] = ((uint32_t)((yy + 3) + cd.sy) << 16) | (uint32_t)((xx + 3) + cd.sx);
+        ors[o] = sc[(size_t)(iy0 + yy) * L.sstride + ix0 + xx];
+      } else {
+        atomicExch(D.err, SDPL_ERR_OVERFLOW);
+      }
+      ++o;
+    }
   }
 }
 
@@ -756,7 +783,7 @@ struct sdpl_orb {
   int gw = 0, gh = 0, gB = 0;
   OrbDev D;
   std::vector<CellDev> cells;
-  DevBuf pyr, score, blur, cellinfo, cand_xy, cand_resp, cand_node, n_cand, n_kp, kp_xy, kp_resp, cellsdev, tables, err;
+  DevBuf pyr, score, blur, cellinfo, cellmask, cand_xy, cand_resp, cand_node, n_cand, n_kp, kp_xy, kp_resp, cellsdev, tables, err;
   DevBuf in_stage, out_kps, out_desc, out_n;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;   // pinned
   int fast_tiles = 0, blur_tiles = 0, max_quota = 0, kp_cap_total = 0, qt_cap = 64;
@@ -775,7 +802,7 @@ static int orb_setup(sdpl_orb* o, int w, int h, int B) {
   memcpy(D.umax, o->umax, sizeof(D.umax));
   for (int l = 0; l < nl; l++) D.sf[l] = o->sf[l];
   size_t pyr_off = 0, s_off = 0;
-  int cell_base = 0, cand_off = 0, kp_off = 0, ft = 0, bt = 0;
+  int cell_base = 0, cand_off = 0, kp_off = 0, ft = 0, bt = 0, mask_words = 1;
   o->cells.clear();
   std::vector<unsigned short> tab_u16;   // all resize tables packed: per level xofs,yofs (u16) then xa,ya (short2)
   std::vector<short> tab_s16;
@@ -815,6 +842,7 @@ static int orb_setup(sdpl_orb* o, int w, int h, int B) {
           c.level = (short)l; c.x0 = (short)(int)iniX; c.y0 = (short)(int)iniY; c.x1 = (short)(int)maxX; c.y1 = (short)(int)maxY;
           c.sx = (short)(j * wCell); c.sy = (short)(i * hCell); c.pad = 0;
           o->cells.push_back(c);
+          mask_words = std::max(mask_words, (((int)maxX - (int)iniX - 6) * ((int)maxY - (int)iniY - 6) + 31) / 32);
           L.ncells++;
         }
       }
@@ -867,7 +895,7 @@ static int orb_setup(sdpl_orb* o, int w, int h, int B) {
     }
   }
   D.pyr_frame = align_up(pyr_off, 256); D.s_frame = align_up(s_off, 256);
-  D.cells_per_frame = cell_base; D.cand_per_frame = cand_off; D.kp_per_frame = kp_off;
+  D.cells_per_frame = cell_base; D.cand_per_frame = cand_off; D.kp_per_frame = kp_off; D.mask_words = mask_words;
   o->fast_tiles = ft; o->blur_tiles = bt; D.blur_tiles = bt; o->kp_cap_total = kp_off;
   o->qt_cap = 64;
   for (int l = 0; l < nl; l++) o->qt_cap = std::max(o->qt_cap, D.L[l].kp_cap + 8);
@@ -876,6 +904,7 @@ static int orb_setup(sdpl_orb* o, int w, int h, int B) {
   if ((rc = o->score.reserve(D.s_frame * B))) return rc;
   if ((rc = o->blur.reserve(D.pyr_frame * B))) return rc;
   if ((rc = o->cellinfo.reserve(sizeof(uint32_t) * (size_t)std::max(1, cell_base) * B))) return rc;
+  if ((rc = o->cellmask.reserve(sizeof(uint2) * (size_t)std::max(1, cell_base) * std::max(1, D.mask_words) * B))) return rc;
   if ((rc = o->cand_xy.reserve(sizeof(uint32_t) * (size_t)cand_off * B))) return rc;
   if ((rc = o->cand_resp.reserve((size_t)cand_off * B))) return rc;
   if ((rc = o->cand_node.reserve(sizeof(unsigned short) * (size_t)cand_off * B))) return rc;
@@ -901,7 +930,7 @@ static int orb_setup(sdpl_orb* o, int w, int h, int B) {
     L.ya = (const short2*)((char*)o->tables.p + u16_bytes + ya_at[l] * 2);
   }
   D.pyr = o->pyr.as<uint8_t>(); D.score = o->score.as<uint8_t>(); D.blur = o->blur.as<uint8_t>();
-  D.cellinfo = o->cellinfo.as<uint32_t>(); D.cand_xy = o->cand_xy.as<uint32_t>(); D.cand_resp = o->cand_resp.as<uint8_t>();
+  D.cellinfo = o->cellinfo.as<uint32_t>(); D.cellmask = o->cellmask.as<uint2>(); D.cand_xy = o->cand_xy.as<uint32_t>(); D.cand_resp = o->cand_resp.as<uint8_t>();
   D.cand_node = o->cand_node.as<unsigned short>(); D.n_cand = o->n_cand.as<int>(); D.n_kp = o->n_kp.as<int>();
   D.kp_xy = o->kp_xy.as<uint32_t>(); D.kp_resp = o->kp_resp.as<uint8_t>(); D.cells = o->cellsdev.as<CellDev>();
   D.err = o->err.as<int>();
@@ -945,9 +974,9 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
   o->timer.mark(st, "fast_score");
   if (D.cells_per_frame > 0) {
     dim3 g(div_up(D.cells_per_frame, 8), B);
-    k_cell_nms<false><<<g, 256, 0, st>>>(D);
+    k_cell_nms<<<g, 256, 0, st>>>(D);
     SDPL_LAUNCH_CHECK();
-    k_cell_nms<true><<<g, 256, 0, st>>>(D);
+    k_cell_emit<<<g, 256, 0, st>>>(D);
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "cell_nms");
@@ -1031,7 +1060,7 @@ void sdpl_orb_destroy(sdpl_orb* o) {
   if (!o) return;
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
-  for (DevBuf* b : {&o->pyr, &o->score, &o->blur, &o->cellinfo, &o->cand_xy, &o->cand_resp, &o->cand_node, &o->n_cand, &o->n_kp,
+  for (DevBuf* b : {&o->pyr, &o->score, &o->blur, &o->cellinfo, &o->cellmask, &o->cand_xy, &o->cand_resp, &o->cand_node, &o->n_cand, &o->n_kp,
                     &o->kp_xy, &o->kp_resp, &o->cellsdev, &o->tables, &o->err, &o->in_stage, &o->out_kps, &o->out_desc, &o->out_n})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
