@@ -279,9 +279,6 @@ def run_gpu(args, stages):
     orb.set_stream(s_orb.cuda_stream); mat.set_stream(s_match.cuda_stream)
     if use_line:
         line.set_stream(s_line.cuda_stream); lmat.set_stream(s_lmatch.cuda_stream)
-    for hdl in (orb, mat, line, lmat):
-        if hdl is not None:
-            hdl.set_profiling(True)
     launches = [0]
 
     def match_prev(m, stream, d, n, rows, best, second, nacc):
@@ -354,6 +351,9 @@ def run_gpu(args, stages):
     # ---- per-stage kernel times, each pipeline alone on the device (no cross-stream overlap) ----
     stage_ms, stage_launch = {}, {}
     reps = 3
+    for hdl in (orb, mat, line, lmat):
+        if hdl is not None:
+            hdl.set_profiling(True)      # stage marks on the handle's stream (and no internal stream fork: stages run one after another)
     for hdl, fn in ((orb, lambda: orb.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kps.data_ptr(), d_desc.data_ptr() + cap * 32, cap,
                                                         d_nkp.data_ptr() + 4)),
                     (line, (lambda: line.extract_batch_dev(d_imgs.data_ptr(), F, W, H, d_kls.data_ptr(), d_ldesc.data_ptr() + LINE_CAP * 32,
