@@ -155,7 +155,7 @@ __device__ __forceinline__ bool has_arc9(uint32_t m16) {
 __device__ __forceinline__ unsigned expand2(unsigned v16) { return __byte_perm(v16, 0u, 0x4140); }   // (b0, b1) -> s16x2
 
 __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
-  constexpr int S = kFT_W + 8;                                  // row stride (even)
+  constexpr int S = kFT_W + 12;                                 // row stride: 19 words
   __shared__ __align__(4) uint8_t tileA[(kFT_H + 6) * S];
   __shared__ __align__(4) uint8_t tileB[(kFT_H + 6) * S];       // tileB[i] == tileA[i + 1]
   int t = blockIdx.x;
@@ -166,15 +166,26 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
   t -= L.fast_tile_base;
   const int tx = t % L.fast_tiles_x, ty = t / L.fast_tiles_x;
   const int x0 = kBorder + tx * kFT_W, y0 = kBorder + ty * kFT_H;   // level (interior) coordinates of the tile
-  const uint8_t* img = D.pyr + (size_t)blockIdx.y * D.pyr_frame + L.pyr_off + (size_t)kBorder * L.pstride + kBorder;
-  // stage tile + 3 px halo (always inside the padded plane), plus one extra column for the shifted copy
-  for (int i = threadIdx.x; i < (kFT_H + 6) * (kFT_W + 7); i += 256) {
-    const int yy = i / (kFT_W + 7), xx = i - yy * (kFT_W + 7);
-    const int gy = y0 - 3 + yy, gx = x0 - 3 + xx;
-    uint8_t v = 0;
-    if (gy < L.h + kBorder && gx < L.w + kBorder) v = img[(ptrdiff_t)gy * L.pstride + gx];
-    tileA[yy * S + xx] = v;
-    if (xx > 0) tileB[yy * S + xx - 1] = v;
+  // stage tile + 3 px halo as aligned 32-bit words of the padded plane.  The tile starts at padded column 2 * kBorder - 3 + 64 tx
+  // = 35 + 64 tx: the word-aligned copy starts 3 bytes earlier (kShift), so tile column xx sits at byte xx + kShift of a
+  // staged row.  Words past the end of a padded row / rows past the plane are clamped: they only feed pixels that are
+  // not written (a written pixel's ring stays inside the plane).  tileB = tileA shifted by one byte (funnel shift).
+  constexpr int kShift = (2 * kBorder - 3) & 3;
+  static_assert(kShift == 3 && (kFT_W & 3) == 0, "tile origin alignment");
+  constexpr int kWords = (kFT_W + 6 + kShift + 1 + 3) / 4;      // words per staged row (the byte after the last one feeds tileB)
+  static_assert(kWords * 4 <= S, "staged row fits the tile stride");
+  {
+    const uint32_t* plane = (const uint32_t*)(D.pyr + (size_t)blockIdx.y * D.pyr_frame + L.pyr_off);
+    const int ws = L.pstride / 4, last_row = L.h + 2 * kBorder - 1;
+    const int w0 = (2 * kBorder - 3 + tx * kFT_W) / 4;          // first word (exact: the byte offset is 32 + 64 tx)
+    const int r0 = kBorder - 3 + y0;                             // padded row of the tile's first staged row
+    for (int i = threadIdx.x; i < (kFT_H + 6) * kWords; i += 256) {
+      const int yy = i / kWords, j = i - yy * kWords;
+      const uint32_t* row = plane + (size_t)min(r0 + yy, last_row) * ws;
+      const uint32_t a = row[min(w0 + j, ws - 1)], b = row[min(w0 + j + 1, ws - 1)];
+      *(uint32_t*)(tileA + yy * S + 4 * j) = a;
+      *(uint32_t*)(tileB + yy * S + 4 * j) = __funnelshift_r(a, b, 8);
+    }
   }
   __syncthreads();
   uint8_t* sc = D.score + (size_t)blockIdx.y * D.s_frame + L.s_off;
@@ -188,13 +199,13 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
     const int yy = i / (kFT_W / 2), xx = (i % (kFT_W / 2)) * 2;   // even column inside the tile
     const int gx = x0 + xx, gy = y0 + yy;
     if (gx >= xe || gy >= ye) continue;
-    const int base = (yy + 3) * S + xx + 3;                        // odd byte offset of the centre pair
-    const unsigned c2 = expand2(*(const unsigned short*)(tileB + base - 1));
+    const int base = (yy + 3) * S + xx + 3 + kShift;               // even byte offset of the centre pair (tile column xx + 3)
+    const unsigned c2 = expand2(*(const unsigned short*)(tileA + base));
     unsigned d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      const int off = base + RY[k] * S + RX[k];                    // parity known at compile time: RX odd -> even offset
-      const unsigned short v = (RX[k] & 1) ? *(const unsigned short*)(tileA + off) : *(const unsigned short*)(tileB + off - 1);
+      const int off = base + RY[k] * S + RX[k];                    // parity known at compile time: RX odd -> odd offset
+      const unsigned short v = (RX[k] & 1) ? *(const unsigned short*)(tileB + off - 1) : *(const unsigned short*)(tileA + off);
       d[k] = __vsub2(expand2(v), c2);
     }
     unsigned m3[16], M3[16];
