@@ -142,25 +142,6 @@ int sdpl_frontend_submit(sdpl_frontend* f, const uint8_t* imgs, int n, int w, in
   sdpl_keyline* dl = S.kls.as<sdpl_keyline>() + LC;
   uint8_t* dld = S.ldesc.as<uint8_t>() + (size_t)32 * LC;
   int* dln = S.nkl.as<int>() + 1;
-  // ---- block 0 = last frame of the previous batch (or nothing) ----
-  if (f->have_prev && f->last >= 0) {
-    FeSlot& P = f->slot[f->last];
-    SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_orb, 0));
-    SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_line, 0));
-    if (&P == &S) {
-      // same buffers (single-batch use): the matchers of that batch read block 0, wait for them before overwriting it
-      SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_pm, 0));
-      SDPL_CUDA(cudaStreamWaitEvent(f->s_io, P.ev_lm, 0));
-    }
-    const int pl = P.n;   // its last frame sits in block pl
-    SDPL_CUDA(cudaMemcpyAsync(S.desc.p, P.desc.as<uint8_t>() + (size_t)pl * KC * 32, (size_t)32 * KC, cudaMemcpyDeviceToDevice, f->s_io));
-    SDPL_CUDA(cudaMemcpyAsync(S.nkp.p, P.nkp.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_io));
-    SDPL_CUDA(cudaMemcpyAsync(S.ldesc.p, P.ldesc.as<uint8_t>() + (size_t)pl * LC * 32, (size_t)32 * LC, cudaMemcpyDeviceToDevice, f->s_io));
-    SDPL_CUDA(cudaMemcpyAsync(S.nkl.p, P.nkl.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_io));
-  } else {
-    SDPL_CUDA(cudaMemsetAsync(S.nkp.p, 0, sizeof(int), f->s_io));
-    SDPL_CUDA(cudaMemsetAsync(S.nkl.p, 0, sizeof(int), f->s_io));
-  }
   // ---- one upload shared by both pipelines ----
   if (stride == w && frame_stride == (size_t)w * h) {
     SDPL_CUDA(cudaMemcpyAsync(S.imgs.p, imgs, (size_t)w * h * n, cudaMemcpyHostToDevice, f->s_io));
@@ -171,6 +152,28 @@ int sdpl_frontend_submit(sdpl_frontend* f, const uint8_t* imgs, int n, int w, in
   }
   SDPL_CUDA(cudaEventRecord(S.ev_in, f->s_io));
   int launches = 0;
+  // ---- block 0 = last frame of the previous batch (or nothing).  The copies ride on the matcher streams, behind the
+  //      previous batch's extraction: the upload above and the extraction below do not wait for the previous batch ----
+  if (f->have_prev && f->last >= 0) {
+    FeSlot& P = f->slot[f->last];
+    const int pl = P.n;   // its last frame sits in block pl
+    SDPL_CUDA(cudaStreamWaitEvent(f->s_pm, P.ev_orb, 0));
+    SDPL_CUDA(cudaStreamWaitEvent(f->s_lm, P.ev_line, 0));
+    SDPL_CUDA(cudaMemcpyAsync(S.desc.p, P.desc.as<uint8_t>() + (size_t)pl * KC * 32, (size_t)32 * KC, cudaMemcpyDeviceToDevice, f->s_pm));
+    SDPL_CUDA(cudaMemcpyAsync(S.nkp.p, P.nkp.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_pm));
+    SDPL_CUDA(cudaMemcpyAsync(S.ldesc.p, P.ldesc.as<uint8_t>() + (size_t)pl * LC * 32, (size_t)32 * LC, cudaMemcpyDeviceToDevice, f->s_lm));
+    SDPL_CUDA(cudaMemcpyAsync(S.nkl.p, P.nkl.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_lm));
+    if (&P == &S) {
+      // same buffers (cannot happen while the slots alternate): the extraction below overwrites the block just copied from
+      SDPL_CUDA(cudaEventRecord(S.ev_pm, f->s_pm));
+      SDPL_CUDA(cudaEventRecord(S.ev_lm, f->s_lm));
+      SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, S.ev_pm, 0));
+      SDPL_CUDA(cudaStreamWaitEvent(f->s_line, S.ev_lm, 0));
+    }
+  } else {
+    SDPL_CUDA(cudaMemsetAsync(S.nkp.p, 0, sizeof(int), f->s_pm));
+    SDPL_CUDA(cudaMemsetAsync(S.nkl.p, 0, sizeof(int), f->s_lm));
+  }
   // ---- lines (high priority, launched first) and ORB concurrently ----
   SDPL_CUDA(cudaStreamWaitEvent(f->s_line, S.ev_in, 0));
   if ((rc = sdpl_line_extract_batch_dev(f->line, S.imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dl, dld, LC, dln, 0))) return rc;
