@@ -38,6 +38,24 @@ __device__ __forceinline__ Top2 top2_warp_merge(Top2 t) {
   return t;
 }
 
+// 256-bit Hamming distance.  popc is the scarce unit (a quarter of the logic rate), so seven of the eight XOR words go
+// through a carry-save adder tree first (Harley-Seal: sum = a^b^c, carry = maj(a,b,c), one LOP3 each) and only the ones /
+// twos / fours words and the eighth word are counted: 4 popc instead of 8 per pair.
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+  sum = a ^ b ^ c;
+  carry = (a & b) | (c & (a | b));
+}
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint4& a, const uint4& b) {
+  const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+  const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+  uint32_t s1, c1, s2, c2, ones, c3, twos, fours;
+  csa(x0, x1, x2, s1, c1);
+  csa(x3, x4, x5, s2, c2);
+  csa(s1, s2, x6, ones, c3);
+  csa(c1, c2, c3, twos, fours);
+  return __popc(ones) + __popc(x7) + 2u * __popc(twos) + 4u * __popc(fours);
+}
+
 // partial[(p*max_q + q)*nsplit + s]
 __global__ void __launch_bounds__(kWarps * 32) k_match_partial(const uint8_t* __restrict__ q, const int* __restrict__ nq_arr,
                                                                size_t q_stride, const uint8_t* __restrict__ t,
@@ -70,8 +88,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_partial(const uint8_t* __
     uint4 a = __ldg(src), b = __ldg(src + 1);
 #pragma unroll
     for (int k = 0; k < kQW; k++) {
-      uint32_t d = __popc(qw[k][0] ^ a.x) + __popc(qw[k][1] ^ a.y) + __popc(qw[k][2] ^ a.z) + __popc(qw[k][3] ^ a.w) +
-                   __popc(qw[k][4] ^ b.x) + __popc(qw[k][5] ^ b.y) + __popc(qw[k][6] ^ b.z) + __popc(qw[k][7] ^ b.w);
+      const uint32_t d = hamming256(qw[k], a, b);
       // ascending j inside a lane: strict '<' keeps the lowest index on ties
       if (d < best[k].d1) { best[k].d2 = best[k].d1; best[k].i2 = best[k].i1; best[k].d1 = d; best[k].i1 = j; }
       else if (d < best[k].d2) { best[k].d2 = d; best[k].i2 = j; }
