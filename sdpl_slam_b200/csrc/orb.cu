@@ -244,7 +244,6 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
 //     "local maximum", one for "local maximum with score >= iniThFAST"); k_cell_emit turns the masks of the threshold the
 //     cell ended up with into the ordered candidate list.
 __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
-  __shared__ uint8_t sm[8][kCellApron * kCellApron];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int c = blockIdx.x * 8 + warp;
   int f = blockIdx.y;
@@ -254,21 +253,11 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
   int ix0 = cd.x0 + 3, iy0 = cd.y0 + 3, iw = cd.x1 - cd.x0 - 6, ih = cd.y1 - cd.y0 - 6;
   uint32_t* info = D.cellinfo + (size_t)f * D.cells_per_frame + c;
   if (iw <= 0 || ih <= 0) { if (lane == 0) *info = (uint32_t)D.ini_th << 16; return; }
-  const uint8_t* sc = D.score + (size_t)f * D.s_frame + L.s_off;
-  uint8_t* s = sm[warp];
-  const int aw = iw + 2, ah = ih + 2;
+  // The score plane is sparse (0 below minThFAST): every lane reads its own pixel, and only the few non-zero ones look at
+  // their eight neighbours (straight from the plane; neighbours outside the cell interior count as 0).
   // (row, column) of the linear index advance incrementally: no integer division by the run-time cell width
-  {
-    int yy = lane / aw, xx = lane - yy * aw;
-    for (int i = lane; i < aw * ah; i += 32) {
-      uint8_t v = 0;
-      if (yy >= 1 && yy <= ih && xx >= 1 && xx <= iw) v = sc[(size_t)(iy0 + yy - 1) * L.sstride + ix0 + xx - 1];
-      s[i] = v;
-      xx += 32;
-      while (xx >= aw) { xx -= aw; yy++; }
-    }
-  }
-  __syncwarp();
+  const uint8_t* sc = D.score + (size_t)f * D.s_frame + L.s_off + (size_t)iy0 * L.sstride + ix0;
+  const int ss = L.sstride;
   int cnt_hi = 0, cnt_lo = 0;
   uint2* masks = D.cellmask + ((size_t)f * D.cells_per_frame + c) * D.mask_words;
   const int npx = iw * ih;
@@ -277,10 +266,25 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
     int i = i0 + lane;
     bool ismax = false; int v = 0;
     if (i < npx) {
-      const uint8_t* p = s + (yy + 1) * aw + xx + 1;
+      const uint8_t* p = sc + (size_t)yy * ss + xx;
       v = p[0];
-      ismax = v > 0 && v > p[-1] && v > p[1] && v > p[-aw - 1] && v > p[-aw] && v > p[-aw + 1] && v > p[aw - 1] &&
-              v > p[aw] && v > p[aw + 1];
+      if (v > 0) {
+        const bool l = xx > 0, r = xx < iw - 1, u = yy > 0, d = yy < ih - 1;
+        int m = 0;
+        if (l) m = max(m, (int)p[-1]);
+        if (r) m = max(m, (int)p[1]);
+        if (u) {
+          m = max(m, (int)p[-ss]);
+          if (l) m = max(m, (int)p[-ss - 1]);
+          if (r) m = max(m, (int)p[-ss + 1]);
+        }
+        if (d) {
+          m = max(m, (int)p[ss]);
+          if (l) m = max(m, (int)p[ss - 1]);
+          if (r) m = max(m, (int)p[ss + 1]);
+        }
+        ismax = v > m;
+      }
     }
     const uint32_t m_lo = __ballot_sync(0xffffffffu, ismax), m_hi = __ballot_sync(0xffffffffu, ismax && v >= D.ini_th);
     cnt_lo += __popc(m_lo);
