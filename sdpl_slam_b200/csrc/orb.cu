@@ -70,54 +70,65 @@ __global__ void __launch_bounds__(128) k_pyr_base(const uint8_t* __restrict__ in
   *(uint32_t*)(out + (size_t)blockIdx.z * out_frame + (size_t)y * pstride + x4) = v;
 }
 
-// level l from level l-1: cv::resize INTER_LINEAR (Q11 fixed point) + reflect-101 border in one pass.
+// level l from level l-1: cv::resize INTER_LINEAR (Q11 fixed point) + reflect-101 border in one pass.  A thread owns four
+// output columns (one aligned word) and kPyrRows consecutive rows: the column part of the bilinear set-up (reflected
+// column, source offset, Q11 weights from the tables) is done once and reused down the rows.
+constexpr int kPyrRows = 4;
 __global__ void __launch_bounds__(128) k_pyr_resize(OrbDev D, int l) {
   const LvlDev& Ld = D.L[l];
   const LvlDev& Ls = D.L[l - 1];
-  int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  int y = blockIdx.y;
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (x4 >= Ld.pstride) return;
   uint8_t* frame = D.pyr + (size_t)blockIdx.z * D.pyr_frame;
   const uint8_t* src = frame + Ls.pyr_off + (size_t)kBorder * Ls.pstride + kBorder;
-  int iy = reflect101(y - kBorder, Ld.h);
-  uint32_t v = 0;
-  if (Ld.area_fast) {
-    const uint8_t* s0 = src + (size_t)(2 * iy) * Ls.pstride;
-    const uint8_t* s1 = s0 + Ls.pstride;
+  const int rows = Ld.h + 2 * kBorder;
+  const int y_first = blockIdx.y * kPyrRows;
+  int sx0[4], sx1[4];
+  short2 aa[4];
+  bool in[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int x = x4 + k;
-      uint32_t b = 0;
-      if (x < Ld.w + 2 * kBorder) {
-        int ix = reflect101(x - kBorder, Ld.w);
-        b = (s0[2 * ix] + s0[2 * ix + 1] + s1[2 * ix] + s1[2 * ix + 1] + 2) >> 2;
-      }
-      v |= b << (8 * k);
-    }
-  } else {
-    int sy = (short)Ld.yofs[iy];
-    short2 bb = Ld.ya[iy];
-    int sy0 = min(max(sy, 0), Ls.h - 1), sy1 = min(max(sy + 1, 0), Ls.h - 1);
-    const uint8_t* s0 = src + (size_t)sy0 * Ls.pstride;
-    const uint8_t* s1 = src + (size_t)sy1 * Ls.pstride;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int x = x4 + k;
-      uint32_t b = 0;
-      if (x < Ld.w + 2 * kBorder) {
-        int ix = reflect101(x - kBorder, Ld.w);
-        int sx = Ld.xofs[ix];
-        short2 aa = Ld.xa[ix];
-        int sx1 = min(sx + 1, Ls.w - 1);
-        int r0 = s0[sx] * aa.x + s0[sx1] * aa.y;
-        int r1 = s1[sx] * aa.x + s1[sx1] * aa.y;
-        int o = (((bb.x * (r0 >> 4)) >> 16) + ((bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
-        b = (uint32_t)min(max(o, 0), 255);
-      }
-      v |= b << (8 * k);
-    }
+  for (int k = 0; k < 4; k++) {
+    const int x = x4 + k;
+    in[k] = x < Ld.w + 2 * kBorder;
+    const int ix = reflect101(min(x, Ld.w + 2 * kBorder - 1) - kBorder, Ld.w);
+    if (Ld.area_fast) { sx0[k] = 2 * ix; sx1[k] = 2 * ix + 1; aa[k] = make_short2(0, 0); }
+    else { sx0[k] = Ld.xofs[ix]; sx1[k] = min(sx0[k] + 1, Ls.w - 1); aa[k] = Ld.xa[ix]; }
   }
-  *(uint32_t*)(frame + Ld.pyr_off + (size_t)y * Ld.pstride + x4) = v;
+#pragma unroll 1
+  for (int r = 0; r < kPyrRows; r++) {
+    const int y = y_first + r;
+    if (y >= rows) break;
+    const int iy = reflect101(y - kBorder, Ld.h);
+    uint32_t v = 0;
+    if (Ld.area_fast) {
+      const uint8_t* s0 = src + (size_t)(2 * iy) * Ls.pstride;
+      const uint8_t* s1 = s0 + Ls.pstride;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t b = 0;
+        if (in[k]) b = (s0[sx0[k]] + s0[sx1[k]] + s1[sx0[k]] + s1[sx1[k]] + 2) >> 2;
+        v |= b << (8 * k);
+      }
+    } else {
+      const int sy = (short)Ld.yofs[iy];
+      const short2 bb = Ld.ya[iy];
+      const int sy0 = min(max(sy, 0), Ls.h - 1), sy1 = min(max(sy + 1, 0), Ls.h - 1);
+      const uint8_t* s0 = src + (size_t)sy0 * Ls.pstride;
+      const uint8_t* s1 = src + (size_t)sy1 * Ls.pstride;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t b = 0;
+        if (in[k]) {
+          const int r0 = s0[sx0[k]] * aa[k].x + s0[sx1[k]] * aa[k].y;
+          const int r1 = s1[sx0[k]] * aa[k].x + s1[sx1[k]] * aa[k].y;
+          const int o = (((bb.x * (r0 >> 4)) >> 16) + ((bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
+          b = (uint32_t)min(max(o, 0), 255);
+        }
+        v |= b << (8 * k);
+      }
+    }
+    *(uint32_t*)(frame + Ld.pyr_off + (size_t)y * Ld.pstride + x4) = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -977,7 +988,7 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
   }
   for (int l = 1; l < nl; l++) {
     const LvlDev& L = D.L[l];
-    dim3 g(div_up(L.pstride / 4, 128), L.h + 2 * kBorder, B);
+    dim3 g(div_up(L.pstride / 4, 128), div_up(L.h + 2 * kBorder, kPyrRows), B);
     k_pyr_resize<<<g, 128, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
