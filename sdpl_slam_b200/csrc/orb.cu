@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(128) k_blur7(OrbDev D) {
 // K5 + K7: IC_Angle orientation (ORBextractor.cc:66-93) and rotated-BRIEF descriptor (:97-136), one warp per
 //          keypoint; writes the final cv::KeyPoint record (ORBextractor.cc:826-836, 1099-1105).
 // ------------------------------------------------------------------------------------------------
-__device__ const signed char g_pattern[1024] = {
+__device__ __align__(16) const signed char g_pattern[1024] = {
 #include "../../include/sdpl_orb_pattern.inc"
 };
 
@@ -752,12 +752,16 @@ __global__ void __launch_bounds__(256) k_orient_describe(OrbDev D, sdpl_keypoint
   const uint8_t* c = D.pyr + (size_t)f * D.pyr_frame + L.pyr_off + (size_t)(kBorder + ky) * L.pstride + kBorder + kx;
   int m10 = 0, m01 = 0;
   if (lane < 31) {
-    int v = lane - 15;
-    int d = D.umax[v < 0 ? -v : v];
-    const uint8_t* row = c + (ptrdiff_t)v * L.pstride;
-    int s = 0;
-    for (int u = -d; u <= d; u++) { int p = row[u]; m10 += u * p; s += p; }
-    m01 = v * s;
+    // lanes over the 31 columns of the patch, rows in sequence: every load of the warp is one contiguous 31-byte segment
+    // (integer moments: any summation order gives the reference's m10 / m01)
+    const int u = lane - 15, au = u < 0 ? -u : u;
+#pragma unroll
+    for (int v = -15; v <= 15; v++) {
+      if (au <= D.umax[v < 0 ? -v : v]) {
+        const int p = c[(ptrdiff_t)v * L.pstride + u];
+        m10 += u * p; m01 += v * p;
+      }
+    }
   }
 #pragma unroll
   for (int o2 = 16; o2; o2 >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o2); m01 += __shfl_xor_sync(0xffffffffu, m01, o2); }
@@ -767,11 +771,18 @@ __global__ void __launch_bounds__(256) k_orient_describe(OrbDev D, sdpl_keypoint
   const float ar = __fmul_rn(angle, factorPI);
   const float a = (float)cos((double)ar), b = (float)sin((double)ar);
   const uint8_t* cb = D.blur + (size_t)f * D.pyr_frame + L.pyr_off + (size_t)(kBorder + ky) * L.pstride + kBorder + kx;
-  const signed char* pat = g_pattern + lane * 32;
+  // the lane's eight tests = 32 signed bytes of the pattern, fetched as two 16-byte loads
+  uint32_t pw[8];
+  {
+    const uint4* p4 = (const uint4*)(g_pattern + lane * 32);
+    const uint4 p0 = p4[0], p1 = p4[1];
+    pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w; pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
+  }
   int val = 0;
 #pragma unroll
   for (int t = 0; t < 8; t++) {
-    int px0 = pat[4 * t], py0 = pat[4 * t + 1], px1 = pat[4 * t + 2], py1 = pat[4 * t + 3];
+    const int px0 = (int)(signed char)(pw[t] & 0xffu), py0 = (int)(signed char)((pw[t] >> 8) & 0xffu);
+    const int px1 = (int)(signed char)((pw[t] >> 16) & 0xffu), py1 = (int)(signed char)(pw[t] >> 24);
     int r0 = cv_round_f(__fadd_rn(__fmul_rn((float)px0, b), __fmul_rn((float)py0, a)));
     int c0 = cv_round_f(__fsub_rn(__fmul_rn((float)px0, a), __fmul_rn((float)py0, b)));
     int r1 = cv_round_f(__fadd_rn(__fmul_rn((float)px1, b), __fmul_rn((float)py1, a)));
