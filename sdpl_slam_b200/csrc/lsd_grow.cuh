@@ -946,7 +946,6 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
           const int n_start = n;
           const int py = xy_y(p), px = xy_x(p);
           uint32_t st[9];
-          PxA pa[9];
           const int rofs[3] = {max(py - 1, 0) * w, py * w, min(py + 1, h - 1) * w};
           const int cofs[3] = {max(px - 1, 0), px, min(px + 1, w - 1)};
           uint32_t vmask = 0x1EFu;                                  // bits 0..8 without the centre
@@ -954,44 +953,53 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
           if (px == w - 1) vmask &= ~0x124u;
           if (py == 0) vmask &= ~0x007u;
           if (py == h - 1) vmask &= ~0x1C0u;
+          // only the angle of the eight neighbours is fetched up front; cos / sin are read for the one that joins
+          double ang[9];
 #pragma unroll
           for (int k = 0; k < 9; k++) {
             if (k == 4) continue;
             const int q = rofs[k / 3] + cofs[k % 3];
             st[k] = ld_state(T.state + q);
-            pa[k] = T.px[q];
+            ang[k] = T.px[q].ang;
           }
           if (i + 1 < n_start) nxt = cur[i + 1];
-          uint32_t cand = 0;
+          // candidates: free, not mine yet, gradient defined; `foreign` = carries the stamp of an earlier seed of the wave
+          uint32_t cand = 0, foreign = 0;
 #pragma unroll
           for (int k = 0; k < 9; k++) {
             if (k == 4) continue;
             const uint32_t sv = st[k];
-            if (!(sv & kUsed) && sv != stamp && pa[k].ang != kNotDef) cand |= 1u << k;
+            if (!(sv & kUsed) && sv != stamp && ang[k] != kNotDef) cand |= 1u << k;
+            if (sv > stamp) foreign |= 1u << k;
           }
           cand &= vmask;
           while (cand) {
+            // alignment of all eight slots against the running angle, branch-free (aligned_angle without the undefined test:
+            // cand excludes those pixels; |t| <= prec, or past 3/2 pi and 2 pi - |t| <= prec -- the same doubles)
             uint32_t al = 0;
 #pragma unroll
             for (int k = 0; k < 9; k++) {
               if (k == 4) continue;
-              if ((cand >> k) & 1u) al |= (aligned_angle(pa[k].ang, ra, prec) ? 1u : 0u) << k;
+              const double t = fabs(ra - ang[k]);
+              const double u = fabs(t - k2PI);
+              const bool ok = (t <= prec) | ((t > k3_2PI) & (u <= prec));
+              al |= (ok ? 1u : 0u) << k;
             }
+            al &= cand;
             if (!al) break;
             const int k = __ffs(al) - 1;
-            uint32_t sk = 0; float ck = 0.f, sn_k = 0.f;
-#pragma unroll
-            for (int j = 0; j < 9; j++) if (j == k) { sk = st[j]; ck = pa[j].c; sn_k = pa[j].s; }
             const int qx = px - 1 + k % 3, qy = py - 1 + k / 3;
-            if (sk > stamp || n >= capc) { aborted = true; break; }
-            atomicMax(&T.state[qy * w + qx], stamp);
+            if (((foreign >> k) & 1u) || n >= capc) { aborted = true; break; }
+            const int q = qy * w + qx;
+            atomicMax(&T.state[q], stamp);
+            const float2 cs = *reinterpret_cast<const float2*>(&T.px[q].c);
             const int qp = xy_pack(qx, qy);
             if (n == i + 1) nxt = qp;
             cur[n++] = qp;
             R.bx0 = min(R.bx0, qx); R.bx1 = max(R.bx1, qx);
             R.by0 = min(R.by0, qy); R.by1 = max(R.by1, qy);
-            sumdx = __fadd_rn(sumdx, ck);
-            sumdy = __fadd_rn(sumdy, sn_k);
+            sumdx = __fadd_rn(sumdx, cs.x);
+            sumdy = __fadd_rn(sumdy, cs.y);
             ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
             cand &= ~((2u << k) - 1u);
           }

@@ -14,6 +14,7 @@ CONFIGS = [
     (375, 1242, 2500, 8, 1.2, 20, 7),
     (480, 640, 1000, 8, 1.2, 20, 7),
     (211, 333, 500, 5, 1.3, 20, 7),
+    (101, 149, 60, 3, 1.2, 20, 7),       # levels narrower than one blur warp / one FAST tile, ragged last cells
 ]
 
 
