@@ -84,7 +84,17 @@ __device__ __forceinline__ bool aligned_angle(double a, double theta, double pre
   return n <= prec;
 }
 __device__ __forceinline__ double modgrad_of(int g2) { return sqrt((double)g2 / 4.0); }
-__device__ __forceinline__ uint32_t ld_state(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+// The state words of a task are only ever touched by the ONE CTA that grows that task, so CTA scope is all the coherence the
+// speculative stamps need: relaxed.cta loads may be served by the SM's L1 (a volatile / .sys load goes to L2 every time, and
+// the neighbourhood loads are the latency chain of the whole kernel), relaxed.cta RED.MAX claims a pixel.
+__device__ __forceinline__ uint32_t ld_state(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void claim_max(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.cta.global.max.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // region_grow.  SPEC=false: exact sequential semantics, marks `used` (state = kUsed).
@@ -101,7 +111,7 @@ __device__ bool region_grow(const Task& T, int seed, int* reg, int cap, int& n_o
   float sumdx = (float)cos(ra), sumdy = (float)sin(ra);
   if (SPEC) {
     if (ld_state(T.state + seed) > stamp) { n_out = n; return false; }
-    atomicMax(&T.state[seed], stamp);
+    claim_max(&T.state[seed], stamp);
   } else {
     T.state[seed] = kUsed;
   }
@@ -134,7 +144,7 @@ __device__ bool region_grow(const Task& T, int seed, int* reg, int cap, int& n_o
         // if an earlier seed claims the same pixel concurrently its stamp wins and the commit-time ownership check sees it.
         if (s > stamp) { n_out = n; return false; }
         if (n >= cap) { n_out = n; return false; }
-        atomicMax(&T.state[q], stamp);
+        claim_max(&T.state[q], stamp);
       } else {
         T.state[q] = kUsed;
       }
@@ -535,7 +545,7 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
       // ---------------- region_grow ----------------
       if (spec) {
         if (capc < 1 || ld_state(T.state + seed) > stamp) { R.ok = 0; return; }
-        atomicMax(&T.state[seed], stamp);
+        claim_max(&T.state[seed], stamp);
       } else {
         T.state[seed] = kUsed;
       }
@@ -597,7 +607,7 @@ __device__ __forceinline__ void process_seed_u(const Task& T, const int seed, in
           const int qx = px - 1 + k % 3, qy = py - 1 + k / 3;
           if (spec) {
             if (sk > stamp || n >= capc) { aborted = true; break; }
-            atomicMax(&T.state[qy * w + qx], stamp);
+            claim_max(&T.state[qy * w + qx], stamp);
           } else {
             T.state[qy * w + qx] = kUsed;
           }
@@ -933,7 +943,7 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
       bool aborted = false;
       if (capc < 1 || ld_state(T.state + seed) > stamp) aborted = true;
       else {
-        atomicMax(&T.state[seed], stamp);
+        claim_max(&T.state[seed], stamp);
         cur[0] = xy_pack(sx, sy); n = 1;
         ra = seed_ang;
         double sn, cs;
@@ -991,7 +1001,7 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
             const int qx = px - 1 + k % 3, qy = py - 1 + k / 3;
             if (((foreign >> k) & 1u) || n >= capc) { aborted = true; break; }
             const int q = qy * w + qx;
-            atomicMax(&T.state[q], stamp);
+            claim_max(&T.state[q], stamp);
             const float2 cs = *reinterpret_cast<const float2*>(&T.px[q].c);
             const int qp = xy_pack(qx, qy);
             if (n == i + 1) nxt = qp;
@@ -1348,7 +1358,7 @@ __device__ void grow_task_rob(const Task& T, RobShared& S) {
         // start of region_grow: the seed itself (first growth: stamp phase 0, re-growth: phase 1)
         if (st[4] > stamp || (alloc - S.freed[lane]) + (cb - base) + 64u > (unsigned int)T.lane_cap) { phase = PH_ABORT; n = 0; }
         else {
-          atomicMax(&T.state[seed], stamp);
+          claim_max(&T.state[seed], stamp);
           SEG(cb) = seed; n = 1; i = 0; nxt = seed;
           ra = pa[4].ang;
           sumdx = (float)cos(ra); sumdy = (float)sin(ra);
@@ -1367,7 +1377,7 @@ __device__ void grow_task_rob(const Task& T, RobShared& S) {
             if (!aligned_angle(pa[k].ang, ra, prec_cur)) continue;
             if (s > stamp || (unsigned int)n + 1u >= room) { phase = PH_ABORT; continue; }
             const int q = (py - 1 + k / 3) * w + (px - 1 + k % 3);
-            atomicMax(&T.state[q], stamp);
+            claim_max(&T.state[q], stamp);
             if (first < 0) first = q;
             SEG(cb + n) = q; n++;
             sumdx = __fadd_rn(sumdx, pa[k].c);
