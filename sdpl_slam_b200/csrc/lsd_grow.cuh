@@ -461,14 +461,19 @@ __device__ __forceinline__ int xy_y(int v) { return (int)((unsigned)v >> 16); }
 __device__ __forceinline__ int xy_lin(int v, int w) { return xy_y(v) * w + xy_x(v); }
 
 __device__ __forceinline__ bool owns_all_xy(const Task& T, const int* list, int n, uint32_t key) {
+  // eight list entries, then their eight state words, in flight per trip: the walk is two dependent round trips per trip
   const int w = T.w;
-  int ok = 1, i = 0;
-  for (; i + 4 <= n && ok; i += 4) {
-    const int q0 = xy_lin(list[i], w), q1 = xy_lin(list[i + 1], w), q2 = xy_lin(list[i + 2], w), q3 = xy_lin(list[i + 3], w);
-    const uint32_t s0 = ld_state(T.state + q0), s1 = ld_state(T.state + q1), s2 = ld_state(T.state + q2), s3 = ld_state(T.state + q3);
-    ok = ((s0 >> 1) == key) & ((s1 >> 1) == key) & ((s2 >> 1) == key) & ((s3 >> 1) == key);
+  int ok = 1;
+  for (int i = 0; i < n && ok; i += 8) {
+    int q[8];
+    uint32_t sv[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) q[j] = i + j < n ? xy_lin(list[i + j], w) : -1;
+#pragma unroll
+    for (int j = 0; j < 8; j++) sv[j] = q[j] >= 0 ? ld_state(T.state + q[j]) : (key << 1);
+#pragma unroll
+    for (int j = 0; j < 8; j++) ok &= (sv[j] >> 1) == key;
   }
-  for (; i < n && ok; i++) ok = (ld_state(T.state + xy_lin(list[i], w)) >> 1) == key;
   return ok != 0;
 }
 // warp-cooperative ownership check: lists longer than 64 entries are walked by the whole warp (128 loads in flight per
@@ -510,15 +515,23 @@ __device__ __forceinline__ void mark_used_coop_xy(const Task& T, bool active, co
     const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(size_t)list, src);
     const int m = __shfl_sync(0xffffffffu, n, src);
     const int* l = (const int*)(size_t)p;
-    for (int i = lane; i < m; i += 32) T.state[xy_lin(l[i], w)] = kUsed;
+    // four list blocks in flight per trip (a plain loop waits for every load before it issues the next one)
+    for (int i = lane; i < m; i += 128) {
+      int q[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) q[j] = i + 32 * j < m ? l[i + 32 * j] : -1;
+#pragma unroll
+      for (int j = 0; j < 4; j++) if (q[j] >= 0) T.state[xy_lin(q[j], w)] = kUsed;
+    }
   }
   if (active && n <= 32) {
-    int i = 0;
-    for (; i + 4 <= n; i += 4) {
-      const int q0 = xy_lin(list[i], w), q1 = xy_lin(list[i + 1], w), q2 = xy_lin(list[i + 2], w), q3 = xy_lin(list[i + 3], w);
-      T.state[q0] = kUsed; T.state[q1] = kUsed; T.state[q2] = kUsed; T.state[q3] = kUsed;
+    for (int i = 0; i < n; i += 8) {
+      int q[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) q[j] = i + j < n ? list[i + j] : -1;
+#pragma unroll
+      for (int j = 0; j < 8; j++) if (q[j] >= 0) T.state[xy_lin(q[j], w)] = kUsed;
     }
-    for (; i < n; i++) T.state[xy_lin(list[i], w)] = kUsed;
   }
 }
 
