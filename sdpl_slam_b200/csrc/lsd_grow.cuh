@@ -74,14 +74,12 @@ __device__ __forceinline__ double angle_diff_signed(double a, double b) {
 }
 __device__ __forceinline__ double angle_diff(double a, double b) { return fabs(angle_diff_signed(a, b)); }
 __device__ __forceinline__ bool aligned_angle(double a, double theta, double prec) {
-  if (a == kNotDef) return false;
-  double n = theta - a;
-  if (n < 0) n = -n;
-  if (n > k3_2PI) {
-    n -= k2PI;
-    if (n < 0) n = -n;
-  }
-  return n <= prec;
+  // isAligned of the reference, branch-free: |theta - a| <= prec, or past 3/2 pi and |(|theta - a|) - 2 pi| <= prec -- the same
+  // doubles as the if-chain.  An undefined angle (kNotDef = -1024) fails both tests for any tolerance below 1000 rad, so the
+  // reference's explicit test for it is implied.
+  const double t = fabs(theta - a);
+  const double u = fabs(t - k2PI);
+  return (t <= prec) | ((t > k3_2PI) & (u <= prec));
 }
 __device__ __forceinline__ double modgrad_of(int g2) { return sqrt((double)g2 / 4.0); }
 // The state words of a task are only ever touched by the ONE CTA that grows that task, so CTA scope is all the coherence the
