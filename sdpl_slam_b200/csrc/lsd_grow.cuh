@@ -1109,21 +1109,22 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
     // ---- warp 0 selects the next (up to) K free seeds in order ----
     if (warp == 0) {
       int cursor = S.cursor, nsel = 0;
-      // four blocks of 32 list entries per trip: the two dependent loads (list entry, its state word) of all four are in
+      // eight blocks of 32 list entries per trip: the two dependent loads (list entry, its state word) of all eight are in
       // flight together; the blocks are then consumed in order exactly as one at a time
+      constexpr int kSelBlocks = 8;
       while (nsel < K && cursor < T.ndef) {
-        int p[4];
-        bool fr[4];
+        int p[kSelBlocks];
+        bool fr[kSelBlocks];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < kSelBlocks; j++) {
           const int idx = cursor + j * 32 + lane;
           p[j] = idx < T.ndef ? (int)T.order[idx] : -1;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) fr[j] = !(ld_state(T.state + (p[j] >= 0 ? p[j] : 0)) & kUsed) && p[j] >= 0;
+        for (int j = 0; j < kSelBlocks; j++) fr[j] = !(ld_state(T.state + (p[j] >= 0 ? p[j] : 0)) & kUsed) && p[j] >= 0;
         bool stop = false;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < kSelBlocks; j++) {
           if (stop) continue;
           const uint32_t m = __ballot_sync(0xffffffffu, fr[j]);
           const int c = __popc(m);
