@@ -30,8 +30,8 @@ LINE_CFG = dict(nfeatures=0, refine=2, lsd_scale=0.8, nlevels=2, scale=2.0, extr
 RATIO, MAX_DIST = 0.8, 64
 LINE_CAP = 2048
 # DRAM bytes per frame of the dominant kernel from one `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum of
-# k_lsd_grow_block<4,4> over 128 frames: 3.066 GB + 0.310 GB, profiles/r1_lsd_grow_wave_ncu_full_summary.csv)
-NCU_TRAFFIC_PER_FRAME = {"lsd_grow": (3066408000 + 309583616) / 128.0}
+# k_lsd_grow_block<4,4> over 128 frames: 2.893 GB + 0.294 GB, profiles/r1_lsd_kernels_final_ncu_full_summary.csv)
+NCU_TRAFFIC_PER_FRAME = {"lsd_grow": (2892995000 + 294136064) / 128.0}
 METRIC = "front-end frames/sec (ORB+LSD/LBD+match) at 1242x375"
 UNIT = "frames/s"
 
@@ -388,8 +388,8 @@ def run_gpu(args, stages):
                     "traffic": int(tpf * F / nl) if tpf else None, "peak_source": peak_src, "launches_per_step": nl, "avg_launch_ms": dom["ms"] / nl,
                     "alg_bytes_per_launch": dom["alg_bytes"] // nl,
                     "note": "stage time by CUDA events on the handle's stream, pipeline run alone, mean of %d calls; the kernel is a dependent-"
-                            "instruction chain (ncu: 10 of 32 threads active per instruction, issue slots 10 %% busy, 58 %% of the stalls at the CTA "
-                            "barrier), bounded by latency and by the 4 resident CTAs per SM, not by bandwidth; traffic = "
+                            "instruction chain (ncu: 12 of 32 threads active per instruction, issue slots 13 %% busy, half of the stall cycles at the "
+                            "CTA barrier), bounded by latency and by the 4 resident CTAs per SM, not by bandwidth; traffic = "
                             "ncu DRAM bytes per frame x frames per launch" % reps}
 
     # ---- end to end through the host-buffer C ABI (`e2e`): pinned host frames in, results back on the host ----
