@@ -533,202 +533,6 @@ __device__ __forceinline__ void mark_used_coop_xy(const Task& T, bool active, co
   }
 }
 
-// Compact single-copy version of the per-seed pipeline for the block kernel: growth, rectangle fit and the refine state
-// machine each appear ONCE in the instruction stream (the templated process_seed<> above expands to two growths and three
-// rectangle fits per instantiation; with both instantiations inlined the kernel was 315 KB of SASS and instruction-fetch
-// bound).  `spec` selects speculative (stamps, no writes to `used`) or sequential (writes `used`) semantics at run time.
-// Arithmetic and its order are identical to process_seed<>.
-__device__ __forceinline__ void process_seed_u(const Task& T, const int seed, int* const reg, const int cap, const uint32_t stamp0,
-                                               const bool spec, SeedResult& R) {
-  const int w = T.w, h = T.h;
-  R.ok = 1; R.n1 = 0; R.n2_orig = 0; R.has_rect = 0; R.foff = 0; R.nf = 0;
-  const int sx = seed % w, sy = seed / w;
-  R.bx0 = R.bx1 = sx; R.by0 = R.by1 = sy;
-  int state = 0;                 // 0: first growth, 1: re-growth with the refined tolerance, 2: radius reduction passes
-  int* cur = reg;
-  int n = 0, capc = cap;
-  double prec = T.prec, ra = 0, rad_sq = 0;
-  uint32_t stamp = stamp0;
-  const double seed_ang = T.px[seed].ang;
-#pragma unroll 1
-  while (true) {
-    if (state <= 1) {
-      // ---------------- region_grow ----------------
-      if (spec) {
-        if (capc < 1 || ld_state(T.state + seed) > stamp) { R.ok = 0; return; }
-        claim_max(&T.state[seed], stamp);
-      } else {
-        T.state[seed] = kUsed;
-      }
-      cur[0] = xy_pack(sx, sy); n = 1;
-      ra = seed_ang;
-      double sn, cs;
-      sincos(ra, &sn, &cs);
-      float sumdx = (float)cs, sumdy = (float)sn;
-      int nxt = xy_pack(sx, sy);
-      bool aborted = false;
-#pragma unroll 1
-      for (int i = 0; i < n && !aborted; i++) {
-        const int p = nxt;
-        const int n_start = n;
-        const int py = xy_y(p), px = xy_x(p);
-        uint32_t st[9];
-        PxA pa[9];
-        // clamped row / column offsets: every load is in bounds and unpredicated; neighbours outside the image are masked
-        // out of the candidate set by four border tests instead of nine bounds checks
-        const int rofs[3] = {max(py - 1, 0) * w, py * w, min(py + 1, h - 1) * w};
-        const int cofs[3] = {max(px - 1, 0), px, min(px + 1, w - 1)};
-        uint32_t vmask = 0x1EFu;                                  // bits 0..8 without the centre
-        if (px == 0) vmask &= ~0x049u;
-        if (px == w - 1) vmask &= ~0x124u;
-        if (py == 0) vmask &= ~0x007u;
-        if (py == h - 1) vmask &= ~0x1C0u;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-          if (k == 4) continue;
-          const int q = rofs[k / 3] + cofs[k % 3];
-          st[k] = ld_state(T.state + q);
-          pa[k] = T.px[q];
-        }
-        if (i + 1 < n_start) nxt = cur[i + 1];
-        // candidates: in bounds, defined, not committed, not already mine.  The reference tests the neighbours one after
-        // the other against the running region angle; a neighbour that fails is not looked at again, one that joins changes
-        // the angle for the LATER neighbours only.  So: test all remaining candidates at once (independent chains), take the
-        // first aligned one in scan order, update the angle, re-test only the neighbours behind it.
-        uint32_t cand = 0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-          if (k == 4) continue;
-          const uint32_t sv = st[k];
-          if (!(sv & kUsed) && !(spec && sv == stamp) && pa[k].ang != kNotDef) cand |= 1u << k;
-        }
-        cand &= vmask;
-        while (cand) {
-          uint32_t al = 0;
-#pragma unroll
-          for (int k = 0; k < 9; k++) {
-            if (k == 4) continue;
-            if ((cand >> k) & 1u) al |= (aligned_angle(pa[k].ang, ra, prec) ? 1u : 0u) << k;
-          }
-          if (!al) break;
-          const int k = __ffs(al) - 1;
-          uint32_t sk = 0; float ck = 0.f, sn_k = 0.f;
-#pragma unroll
-          for (int j = 0; j < 9; j++) if (j == k) { sk = st[j]; ck = pa[j].c; sn_k = pa[j].s; }
-          const int qx = px - 1 + k % 3, qy = py - 1 + k / 3;
-          if (spec) {
-            if (sk > stamp || n >= capc) { aborted = true; break; }
-            claim_max(&T.state[qy * w + qx], stamp);
-          } else {
-            T.state[qy * w + qx] = kUsed;
-          }
-          const int qp = xy_pack(qx, qy);
-          if (n == i + 1) nxt = qp;
-          cur[n++] = qp;
-          R.bx0 = min(R.bx0, qx); R.bx1 = max(R.bx1, qx);
-          R.by0 = min(R.by0, qy); R.by1 = max(R.by1, qy);
-          sumdx = __fadd_rn(sumdx, ck);
-          sumdy = __fadd_rn(sumdy, sn_k);
-          ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
-          cand &= ~((2u << k) - 1u);
-        }
-      }
-      if (state == 0) { R.n1 = n; R.nf = n; } else { R.n2_orig = spec ? n : 0; R.nf = n; }
-      if (aborted) { R.ok = 0; return; }
-      if (state == 0 ? (n < T.min_reg) : (n < 2)) return;
-    } else {
-      // ---------------- one pass of reduce_region_radius ----------------
-      rad_sq *= 0.75 * 0.75;
-      for (int i = 0; i < n; ++i) {
-        const int q = cur[i];
-        if (dist_sq((double)sx, (double)sy, (double)xy_x(q), (double)xy_y(q)) > rad_sq) {
-          if (!spec) T.state[xy_lin(q, w)] = 0;
-          cur[i] = cur[n - 1];
-          cur[n - 1] = q;
-          --n;
-          --i;
-        }
-      }
-      R.nf = n;
-      if (n < 2) return;
-    }
-    // ---------------- region2rect (with get_theta) ----------------
-    {
-      double x = 0, y = 0, sum = 0;
-      for (int i = 0; i < n; ++i) {
-        const int q = cur[i];
-        const int qy = xy_y(q), qx = xy_x(q);
-        const double wgt = modgrad_of(T.g2[qy * w + qx]);
-        x += (double)qx * wgt;
-        y += (double)qy * wgt;
-        sum += wgt;
-      }
-      x /= sum; y /= sum;
-      double Ixx = 0, Iyy = 0, Ixy = 0;
-      for (int i = 0; i < n; ++i) {
-        const int q = cur[i];
-        const int qy = xy_y(q), qx = xy_x(q);
-        const double dx = (double)qx - x, dy = (double)qy - y, wgt = modgrad_of(T.g2[qy * w + qx]);
-        Ixx += dy * dy * wgt;
-        Iyy += dx * dx * wgt;
-        Ixy -= dx * dy * wgt;
-      }
-      const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
-      double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
-                                             : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
-      theta *= kDegToRad;
-      if (angle_diff(theta, ra) > T.prec) theta += kPI;
-      double dy_, dx_;
-      sincos(theta, &dy_, &dx_);
-      double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
-      for (int i = 0; i < n; ++i) {
-        const int q = cur[i];
-        const int qy = xy_y(q), qx = xy_x(q);
-        const double rdx = (double)qx - x, rdy = (double)qy - y;
-        const double l = rdx * dx_ + rdy * dy_;
-        const double ww = -rdx * dy_ + rdy * dx_;
-        if (l > l_max) l_max = l; else if (l < l_min) l_min = l;
-        if (ww > w_max) w_max = ww; else if (ww < w_min) w_min = ww;
-      }
-      Rect& rec = R.rec;
-      rec.x1 = x + l_min * dx_; rec.y1 = y + l_min * dy_;
-      rec.x2 = x + l_max * dx_; rec.y2 = y + l_max * dy_;
-      rec.width = w_max - w_min;
-      rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx_; rec.dy = dy_; rec.prec = T.prec; rec.p = T.p;
-      if (rec.width < 1.0) rec.width = 1.0;
-    }
-    const double density = (double)n / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
-    if (state == 0) {
-      if (T.refine <= 0 || density >= T.density_th) { R.has_rect = 1; return; }
-      // ---------------- refine: tolerance from the angle spread near the seed ----------------
-      double sum = 0, s_sum = 0;
-      int cnt = 0;
-      for (int i = 0; i < n; ++i) {
-        const int qp = cur[i];
-        const int q = xy_lin(qp, w);
-        if (!spec) T.state[q] = 0;
-        if (dist((double)sx, (double)sy, (double)xy_x(qp), (double)xy_y(qp)) < R.rec.width) {
-          const double d = angle_diff_signed(T.px[q].ang, seed_ang);
-          sum += d;
-          s_sum += d * d;
-          ++cnt;
-        }
-      }
-      const double mean_angle = sum / (double)cnt;
-      prec = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-      if (spec) { cur = reg + n; capc = cap - n; R.foff = n; stamp = stamp0 | 1u; }   // keep the first region: it is part of E
-      state = 1;
-      continue;
-    }
-    if (density >= T.density_th) { R.has_rect = 1; return; }
-    if (state == 1) {
-      const double r1 = dist_sq((double)sx, (double)sy, R.rec.x1, R.rec.y1), r2 = dist_sq((double)sx, (double)sy, R.rec.x2, R.rec.y2);
-      rad_sq = r1 > r2 ? r1 : r2;
-      state = 2;
-    }
-  }
-}
-
 // Warp-cooperative version of the SEQUENTIAL per-seed pipeline (exactly the semantics and arithmetic order of
 // process_seed<false>): the whole warp works on ONE seed.  Used for the re-runs, which otherwise leave 127 of 128 threads
 // idle behind one dependent-instruction chain.  All scalar state is warp-uniform (every lane holds the same value); lanes
