@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
 // (lsd::validate_rest_warp).  A warp wants a dozen rectangles to keep its six groups busy: the number of warps that work on a
 // task follows the length of its list
 constexpr int kRestBlocks = 16;
-__global__ void __launch_bounds__(128) k_lsd_nfa_rest(LineDev D) {
+__global__ void __launch_bounds__(128, 16) k_lsd_nfa_rest(LineDev D) {
   const int task = blockIdx.y;
   const int f = task / D.nl, o = task % D.nl;
   const int nf = D.nbig[(size_t)D.nl * D.B + task];
