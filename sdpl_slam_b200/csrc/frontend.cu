@@ -84,8 +84,8 @@ int sdpl_frontend_create(sdpl_frontend** out, int nfeatures, float scale, int nl
   f->kl_cap = lsd_nfeatures > 0 ? lsd_nfeatures : 2048;
   SDPL_CUDA(cudaSetDevice(device));
   {
-    // the latency-bound line pipeline runs on the high-priority stream: its CTAs are placed first and the ORB / matching
-    // kernels fill the SMs it leaves idle
+    // all streams share one priority by default: a high-priority line stream (SDPL_FE_LINE_PRIO=high) measured 1-5 % slower on
+    // B200 -- the region-growing kernel holds every register of an SM while it is resident, so the pipelines take turns anyway
     int lo = 0, hi = 0;
     SDPL_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     for (cudaStream_t* s : {&f->s_io, &f->s_orb, &f->s_pm, &f->s_lm, &f->s_out}) SDPL_CUDA(cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, lo));
@@ -174,7 +174,7 @@ int sdpl_frontend_submit(sdpl_frontend* f, const uint8_t* imgs, int n, int w, in
     SDPL_CUDA(cudaMemsetAsync(S.nkp.p, 0, sizeof(int), f->s_pm));
     SDPL_CUDA(cudaMemsetAsync(S.nkl.p, 0, sizeof(int), f->s_lm));
   }
-  // ---- lines (high priority, launched first) and ORB concurrently ----
+  // ---- lines (launched first) and ORB concurrently ----
   SDPL_CUDA(cudaStreamWaitEvent(f->s_line, S.ev_in, 0));
   if ((rc = sdpl_line_extract_batch_dev(f->line, S.imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dl, dld, LC, dln, 0))) return rc;
   launches += sdpl_line_last_launches(f->line);
