@@ -49,7 +49,7 @@ struct LineDev {
   const uint8_t* in;
   unsigned long long lvl_frame, px_frame, lbd_frame, hist_frame, reg_frame;
   uint8_t *lvl, *scaled;
-  lsd::PxA* px; int* g2; uint32_t* state; uint32_t* order;
+  lsd::PxA* px; double* ang; int* g2; uint32_t* state; uint32_t* order;
   uint32_t* hist; int* maxg2; int* ndef; int* task_order;
   int* reg; lsd::Pending* pend; int pend_cap; int* npend;
   uint8_t* g; short* sdx; short* sdy;
@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
       g2 = -1;
     }
     D.px[q] = a;
+    D.ang[q] = a.ang;
     D.g2[q] = g2;
     D.state[q] = 0u;
   }
@@ -295,7 +296,7 @@ __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::T
   const size_t pb = (size_t)f * D.px_frame + O.px_off;
   const int task = f * D.nl + o;
   T.w = O.sw; T.h = O.sh; T.npx = O.npx;
-  T.px = D.px + pb; T.g2 = D.g2 + pb; T.state = D.state + pb; T.order = D.order + pb;
+  T.px = D.px + pb; T.ang = D.ang + pb; T.g2 = D.g2 + pb; T.state = D.state + pb; T.order = D.order + pb;
   T.ndef = D.ndef[task];
   T.reg_spec = D.reg + (size_t)f * D.reg_frame + O.reg_off;
   T.lane_cap = O.lane_cap;
@@ -693,7 +694,7 @@ struct sdpl_line {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
-  DevBuf lvl, scaled, px, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
+  DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -829,6 +830,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->lvl.reserve(D.lvl_frame * B))) return rc;
   if ((rc = o->scaled.reserve(D.px_frame * B))) return rc;
   if ((rc = o->px.reserve(sizeof(lsd::PxA) * D.px_frame * B))) return rc;
+  if ((rc = o->ang.reserve(sizeof(double) * D.px_frame * B))) return rc;
   if ((rc = o->g2.reserve(sizeof(int) * D.px_frame * B))) return rc;
   if ((rc = o->state.reserve(sizeof(uint32_t) * D.px_frame * B))) return rc;
   if ((rc = o->order.reserve(sizeof(uint32_t) * D.px_frame * B))) return rc;
@@ -874,7 +876,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
     O.ex_ofs = i32 + exo_at[l]; O.ey_ofs = i32 + eyo_at[l];
     O.ex_c1 = u16 + exc_at[l]; O.ey_c1 = u16 + eyc_at[l];
   }
-  D.lvl = o->lvl.as<uint8_t>(); D.scaled = o->scaled.as<uint8_t>(); D.px = o->px.as<lsd::PxA>(); D.g2 = o->g2.as<int>();
+  D.lvl = o->lvl.as<uint8_t>(); D.scaled = o->scaled.as<uint8_t>(); D.px = o->px.as<lsd::PxA>(); D.ang = o->ang.as<double>(); D.g2 = o->g2.as<int>();
   D.state = o->state.as<uint32_t>(); D.order = o->order.as<uint32_t>(); D.hist = o->hist.as<uint32_t>();
   D.maxg2 = o->maxg2.as<int>(); D.ndef = o->ndef.as<int>(); D.task_order = o->torder.as<int>(); D.reg = o->reg.as<int>(); D.pend = o->pend.as<lsd::Pending>();
   D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sdx = o->sdx.as<short>(); D.sdy = o->sdy.as<short>();
@@ -1042,7 +1044,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   if (!o) return;
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
-  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
+  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
                     &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);

@@ -49,6 +49,7 @@ struct RobEntry;
 struct Task {                      // one (frame, level)
   int w, h, npx;
   const PxA* px;
+  const double* ang;               // the angles alone, densely packed: what the neighbourhood loads and the NFA scans read
   const int* g2;                   // gx^2+gy^2 ; modgrad = sqrt(g2/4.0)
   uint32_t* state;                 // bit31 = used (committed) ; low bits = speculative stamp
   const uint32_t* order;           // defined pixels by descending bin, row-major inside a bin
@@ -785,7 +786,7 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
             if (k == 4) continue;
             const int q = rofs[k / 3] + cofs[k % 3];
             st[k] = ld_state(T.state + q);
-            ang[k] = T.px[q].ang;
+            ang[k] = T.px[q].ang;            // (not the dense T.ang: this load also brings the cos/sin of the neighbour into L1)
           }
           if (i + 1 < n_start) nxt = cur[i + 1];
           // candidates: free, not mine yet, gradient defined; `foreign` = carries the stamp of an earlier seed of the wave
@@ -1508,10 +1509,10 @@ __device__ __noinline__ double rect_nfa(const Task& T, const Rect& rec) {
     const double right = (yy < c3) ? px[0] + ((double)yy - py[0]) * frstep : px[3] + ((double)yy - py[3]) * srstep;
     if (!(right >= 0) || !(left <= (double)(T.w - 1))) continue;
     const int xb = (int)ceil(left > 0 ? left : 0.0), xe = (int)(right < (double)(T.w - 1) ? right : (double)(T.w - 1));
-    const PxA* row = T.px + (size_t)yy * T.w;
+    const double* row = T.ang + (size_t)yy * T.w;
     for (int x = xb + ((COOP && !by_rows) ? lane : 0); x <= xe; x += xstep) {
       ++total;
-      if (aligned_angle(row[x].ang, rec.theta, rec.prec)) ++alg;
+      if (aligned_angle(row[x], rec.theta, rec.prec)) ++alg;
     }
   }
   if (!COOP) return nfa(T, total, alg, rec.p);
