@@ -25,7 +25,7 @@ namespace sdpl {
 
 constexpr int kMaxOct = 4;
 constexpr int kBins = 1024;
-constexpr int kSortChunk = 1024;        // pixels per warp in the counting sort
+constexpr int kSortChunk = 4096;        // pixels per warp in the counting sort
 constexpr int kSortWarps = 4;           // warps per block in the counting sort
 
 struct OctDev {
