@@ -12,6 +12,7 @@
 //   pyrDown / Sobel          binary_descriptor_custom.cpp:366,395-396
 //   resize INTER_LINEAR_EXACT (inside cv::LineSegmentDetector, LSDDetector_custom.cpp:307)
 #include "oracle_internal.h"
+#include "../include/sdpl_trig.h"
 #include <cmath>
 #include <cfloat>
 #include <cstring>
@@ -377,4 +378,5 @@ int orc_fast9_nms(const uint8_t* img, int w, int h, int stride, int th, int* xs,
 }
 int orc_cv_round_f(float v) { return orc::cv_round(v); }
 int orc_cv_round_d(double v) { return orc::cv_round(v); }
+void orc_sdpl_sincos(double x, double* s, double* c) { sdpl_sincos(x, s, c); }
 }

@@ -6,6 +6,7 @@
 // Oracle decisions: no FMA; cos/sin/atan2 evaluated in double and rounded to float; sqrt in float
 // (cv::sqrt == std::sqrt(float) inside namespace cv); LBD with more than 2 octaves ignores the fictitious entries.
 #include "oracle_internal.h"
+#include "../include/sdpl_trig.h"
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -28,8 +29,8 @@ static void lbd_one(const int16_t* dxImg, const int16_t* dyImg, int realWidth, i
   const short halfHeight = (short)((heightOfLSP - 1) / 2), halfWidth = (short)((lengthOfLSP - 1) / 2);
   const float midX = (float)(0.5 * (kl.sx_oct + kl.ex_oct)), midY = (float)(0.5 * (kl.sy_oct + kl.ey_oct));
   float dL[2], dO[2];
-  dL[0] = (float)std::cos((double)kl.angle);
-  dL[1] = (float)std::sin((double)kl.angle);
+  dL[0] = (float)sdpl_cos((double)kl.angle);   // include/sdpl_trig.h, shared with the CUDA kernel (oracle decision ix)
+  dL[1] = (float)sdpl_sin((double)kl.angle);
   dO[0] = -dL[1];
   dO[1] = dL[0];
   volatile float t0, t1;

@@ -11,10 +11,16 @@
 //       produces), kept only to quantify the difference against cv2.
 //  trig in region growing: OpenCV calls sincosf; the oracle evaluates cos/sin in double on the float-rounded angle,
 //       rounds to float and accumulates in float (identical except where glibc's sincosf is not correctly rounded).
+//  (ix) every double cos / sin of the LSD path (region2rect's rectangle axes, the per-pixel unit vectors) is
+//       include/sdpl_trig.h -- strict-IEEE, < 0.6 ulp, the SAME source the CUDA kernels compile -- instead of the C
+//       library's: glibc and CUDA differ in the last bit for ~0.1 % of the arguments (glibc's own FMA / non-FMA builds
+//       differ as well), and one flipped edge pixel of a rotated rectangle changes an NFA verdict about once per 3000
+//       rectangles.  The cv2 pin (tests/test_oracle_vs_cv2.py) holds with either.
 //  rect_nfa: follows the OpenCV 4.x implementation (double vertices, ceil/int column limits), recovered from the
 //       cv2 4.13 binary and verified bit-exact against it; the OpenCV 3.4-era integer-division scan is kept behind
 //       orc_lsd_set_nfa_variant(4) only to document the difference (the reference README pins "OpenCV 3.4").
 #include "oracle_internal.h"
+#include "../include/sdpl_trig.h"
 #include <cmath>
 #include <cfloat>
 #include <cstring>
@@ -36,6 +42,10 @@ std::vector<double> g_dbg;  // per output line: width, p, log_nfa, n, k
 int g_last_n = 0, g_last_k = 0;
 std::vector<uint8_t> g_last_scaled;
 int g_last_w = 0, g_last_h = 0;
+std::vector<double> g_cand;  // per rectangle handed to rect_improve: x1,y1,x2,y2,width, first rect_nfa value, final log_nfa
+std::vector<int> g_trace;   // per processed seed: position in the seed order, pixels expanded (all growths), first region size
+int g_trace_on = 0, g_expanded = 0;
+std::vector<int> g_trace_n;  // list length after every expansion, -1 between growths (frontier model for the GPU batch size)
 
 struct RegPoint { int x, y; double angle, modgrad; };
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
@@ -126,9 +136,10 @@ struct Lsd {
     reg.clear();
     reg_angle = angles[(size_t)sy * w + sx];
     reg.push_back(RegPoint{sx, sy, reg_angle, modgrad[(size_t)sy * w + sx]});
-    float sumdx = float(std::cos(reg_angle)), sumdy = float(std::sin(reg_angle));
+    float sumdx = float(sdpl_cos(reg_angle)), sumdy = float(sdpl_sin(reg_angle));
     used[(size_t)sy * w + sx] = 1;
     for (size_t i = 0; i < reg.size(); i++) {
+      ++g_expanded;
       const int px = reg[i].x, py = reg[i].y;
       int xx_min = std::max(px - 1, 0), xx_max = std::min(px + 1, w - 1);
       int yy_min = std::max(py - 1, 0), yy_max = std::min(py + 1, h - 1);
@@ -140,7 +151,7 @@ struct Lsd {
             u = 1;
             reg.push_back(RegPoint{xx, yy, angle, modgrad[(size_t)yy * w + xx]});
             if (g_trig_mode == 0) {          // double cos of the float-rounded angle, rounded to float, float accumulate
-              volatile float c = (float)std::cos((double)(float)angle), s = (float)std::sin((double)(float)angle);
+              volatile float c = (float)sdpl_cos((double)(float)angle), s = (float)sdpl_sin((double)(float)angle);
               sumdx = sumdx + c; sumdy = sumdy + s;
             } else if (g_trig_mode == 1) {   // cosf / sinf, float accumulate
               volatile float c = cosf((float)angle), s = sinf((float)angle);
@@ -152,7 +163,9 @@ struct Lsd {
             reg_angle = fast_atan2(sumdy, sumdx) * kDegToRad;
           }
         }
+      if (g_trace_on == 2) g_trace_n.push_back((int)reg.size());
     }
+    if (g_trace_on == 2) g_trace_n.push_back(-1);
   }
 
   double get_theta(const std::vector<RegPoint>& reg, double x, double y, double reg_angle, double prec) const {
@@ -181,7 +194,7 @@ struct Lsd {
     }
     x /= sum; y /= sum;
     double theta = get_theta(reg, x, y, reg_angle, prec);
-    double dx = std::cos(theta), dy = std::sin(theta);
+    double dx = sdpl_cos(theta), dy = sdpl_sin(theta);
     double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
     for (size_t i = 0; i < reg.size(); ++i) {
       double rdx = double(reg[i].x) - x, rdy = double(reg[i].y) - y;
@@ -417,6 +430,8 @@ int lsd_detect(const uint8_t* src, int sw, int sh, int sstride, int refine_mode,
                double ang_th, double log_eps, double density_th, int n_bins, int tie_mode, std::vector<float>& lines) {
   lines.clear();
   g_dbg.clear();
+  g_trace.clear();
+  g_cand.clear();
   Lsd L;
   const double prec = kPI * ang_th / 180, p = ang_th / 180;
   const double rho = quant / std::sin(prec);
@@ -444,7 +459,10 @@ int lsd_detect(const uint8_t* src, int sw, int sh, int sstride, int refine_mode,
     const int px = L.ordered[i].x, py = L.ordered[i].y;
     if (L.used[(size_t)py * L.w + px] == 0 && L.angles[(size_t)py * L.w + px] != kNotDef) {
       double reg_angle;
+      g_expanded = 0;
       L.region_grow(px, py, reg, reg_angle, prec);
+      const int n_first = (int)reg.size();
+      struct Tr { int i, n1; ~Tr() { if (g_trace_on) { g_trace.push_back(i); g_trace.push_back(g_expanded); g_trace.push_back(n1); } } } tr{(int)i, n_first};
       if (reg.size() < min_reg_size) continue;
       Rect rec;
       L.region2rect(reg, reg_angle, prec, p, rec);
@@ -452,7 +470,10 @@ int lsd_detect(const uint8_t* src, int sw, int sh, int sstride, int refine_mode,
       if (refine_mode > 0) {
         if (!L.refine(reg, reg_angle, prec, p, rec, density_th)) continue;
         if (refine_mode >= 2) {
+          const double v_first = L.rect_nfa(rec);
+          const Rect rin = rec;
           log_nfa = L.rect_improve(rec, log_eps);
+          if (g_trace_on) { g_cand.push_back(rin.x1); g_cand.push_back(rin.y1); g_cand.push_back(rin.x2); g_cand.push_back(rin.y2); g_cand.push_back(rin.width); g_cand.push_back(v_first); g_cand.push_back(log_nfa); g_cand.push_back((double)g_last_n); g_cand.push_back((double)g_last_k); }
           if (log_nfa <= log_eps) continue;
         }
       }
@@ -471,6 +492,10 @@ int lsd_detect(const uint8_t* src, int sw, int sh, int sstride, int refine_mode,
 extern "C" {
 void orc_lsd_set_trig_mode(int m) { orc::g_trig_mode = m; }
 void orc_lsd_set_nfa_variant(int m) { orc::g_nfa_variant = m; }
+void orc_lsd_trace(int on) { orc::g_trace_on = on; orc::g_trace.clear(); orc::g_trace_n.clear(); orc::g_cand.clear(); }
+int orc_lsd_trace_cand(double* out, int cap) { int n = (int)orc::g_cand.size(); for (int i = 0; i < n && i < cap; i++) out[i] = orc::g_cand[i]; return n; }
+int orc_lsd_trace_n(int* out, int cap) { int n = (int)orc::g_trace_n.size(); for (int i = 0; i < n && i < cap; i++) out[i] = orc::g_trace_n[i]; return n; }
+int orc_lsd_trace_get(int* out, int cap) { int n = (int)orc::g_trace.size(); for (int i = 0; i < n && i < cap; i++) out[i] = orc::g_trace[i]; return n; }
 int orc_lsd_debug(double* out, int cap) { int n = (int)orc::g_dbg.size(); for (int i = 0; i < n && i < cap; i++) out[i] = orc::g_dbg[i]; return n; }
 int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int refine, double scale, double sigma_scale, double quant,
                    double ang_th, double log_eps, double density_th, int n_bins, int tie_mode, float* lines, int cap) {

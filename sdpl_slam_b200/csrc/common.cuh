@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "../../include/sdpl_frontend.h"
+#include "../../include/sdpl_trig.h"   // strict-IEEE double sin / cos, the same source the CPU oracle compiles
 
 namespace sdpl {
 

@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
       if (norm > D.rho) {
         a.ang = (double)fast_atan2_deg((float)gx, (float)-gy) * lsd::kDegToRad;
         const double af = (double)(float)a.ang;
-        a.c = (float)cos(af); a.s = (float)sin(af);
+        double sn_, cs_; sdpl_sincos(af, &sn_, &cs_);
+        a.c = (float)cs_; a.s = (float)sn_;
       } else {
         g2 = -g2 - 1;           // undefined pixels carry a negative code: excluded from max / bins, modgrad unused
       }
@@ -344,9 +345,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lsd_grow_block(LineDev D) {
 }
 
 constexpr int kLgamN = 32768;
-__global__ void k_lgam_table(double* t, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) t[i] = i > 0 ? lsd::log_gamma((double)i) : 0.0;
+static double host_log_gamma(double x) {
+  if (x > 15.0) return 0.918938533204673 + (x - 0.5) * std::log(x) - x + 0.5 * x * std::log(x * std::sinh(1 / x) + 1 / (810.0 * std::pow(x, 6.0)));
+  static const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+  double a = (x + 0.5) * std::log(x + 5.5) - (x + 5.5), b = 0;
+  for (int n = 0; n < 7; ++n) { a -= std::log(x + (double)n); b += q[n] * std::pow(x, (double)n); }
+  return a + std::log(b);
 }
 
 // small rectangles: one thread each; rectangles whose scan visits more than kBigRect pixels are queued for the warp kernel
@@ -588,7 +592,8 @@ __global__ void __launch_bounds__(64) k_lbd(LineDev D, const sdpl_keyline* __res
   const short lengthOfLSP = (short)kl.num_pixels;
   const short halfHeight = (short)((WB * NB - 1) / 2), halfWidth = (short)((lengthOfLSP - 1) / 2);
   const float midX = (float)(0.5 * (double)__fadd_rn(kl.sx_oct, kl.ex_oct)), midY = (float)(0.5 * (double)__fadd_rn(kl.sy_oct, kl.ey_oct));
-  const float dL0 = (float)cos((double)kl.angle), dL1 = (float)sin((double)kl.angle);
+  double dsn_, dcs_; sdpl_sincos((double)kl.angle, &dsn_, &dcs_);
+  const float dL0 = (float)dcs_, dL1 = (float)dsn_;
   const float dO0 = -dL1, dO1 = dL0;
   if (tid < 63) {
     float t0 = __fmul_rn(-dL0, (float)halfWidth), t1 = __fmul_rn(dL1, (float)halfHeight);
@@ -853,9 +858,12 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->bigidx.reserve(sizeof(int) * (size_t)D.pend_cap * nl * B))) return rc;
   if (!o->lgam.p) {
     if ((rc = o->lgam.reserve(sizeof(double) * kLgamN))) return rc;
-    k_lgam_table<<<div_up(kLgamN, 256), 256, 0, o->stream>>>(o->lgam.as<double>(), kLgamN);
-    SDPL_CUDA(cudaGetLastError());
-    SDPL_CUDA(cudaStreamSynchronize(o->stream));
+    // log_gamma(i) as the reference's NFA evaluates it (Lanczos / Windschitl formulas, descriptor_custom.hpp:687-760 show the
+    // same ones), tabulated once per handle ON THE HOST: the table then holds exactly the doubles the C library gives the CPU
+    // path (CUDA's log / pow / sinh differ from glibc's in the last bit for some arguments)
+    std::vector<double> tab(kLgamN, 0.0);
+    for (int i = 1; i < kLgamN; i++) tab[i] = host_log_gamma((double)i);
+    SDPL_CUDA(cudaMemcpy(o->lgam.p, tab.data(), sizeof(double) * kLgamN, cudaMemcpyHostToDevice));
   }
   const size_t u16_bytes = align_up(t_u16.size() * 2 + 2, 16), s16_bytes = align_up(t_s16.size() * 2 + 2, 16);
   if ((rc = o->tables.reserve(u16_bytes + s16_bytes + t_i32.size() * 4 + 16))) return rc;
@@ -1236,8 +1244,8 @@ int sdpl_line_debug_pending(sdpl_line* o, int frame, int octave, double* out, in
   if (np) SDPL_CUDA(cudaMemcpy(P.data(), o->D.pend + (size_t)task * o->D.pend_cap, sizeof(lsd::Pending) * np, cudaMemcpyDeviceToHost));
   for (int i = 0; i < np && i < capacity && out; i++) {
     double* d = out + 8 * i;
-    d[0] = P[i].rec.x1; d[1] = P[i].rec.y1; d[2] = P[i].rec.x2; d[3] = P[i].rec.y2; d[4] = P[i].rec.width; d[5] = P[i].seed;
-    d[6] = P[i].npix; d[7] = P[i].tag;
+    d[0] = P[i].rec.x1; d[1] = P[i].rec.y1; d[2] = P[i].rec.x2; d[3] = P[i].rec.y2; d[4] = P[i].rec.width; d[5] = P[i].rec.p;
+    d[6] = P[i].accepted; d[7] = P[i].tag;
   }
   *n_out = np;
   return SDPL_OK;

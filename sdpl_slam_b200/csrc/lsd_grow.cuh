@@ -107,7 +107,7 @@ __device__ bool region_grow(const Task& T, int seed, int* reg, int cap, int& n_o
   int n = 1;
   reg[0] = seed;
   double ra = T.px[seed].ang;
-  float sumdx = (float)cos(ra), sumdy = (float)sin(ra);
+  float sumdx = (float)sdpl_cos(ra), sumdy = (float)sdpl_sin(ra);
   if (SPEC) {
     if (ld_state(T.state + seed) > stamp) { n_out = n; return false; }
     claim_max(&T.state[seed], stamp);
@@ -189,7 +189,7 @@ __device__ void region2rect(const Task& T, const int* reg, int n, double reg_ang
   }
   x /= sum; y /= sum;
   const double theta = get_theta(T, reg, n, x, y, reg_angle, prec);
-  const double dx = cos(theta), dy = sin(theta);
+  const double dx = sdpl_cos(theta), dy = sdpl_sin(theta);
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
   for (int i = 0; i < n; ++i) {
     const int q = reg[i];
@@ -587,7 +587,7 @@ __device__ __forceinline__ void coop_region2rect(const Task& T, const int* list,
   theta *= kDegToRad;
   if (angle_diff(theta, ra) > T.prec) theta += kPI;
   double dy_, dx_;
-  sincos(theta, &dy_, &dx_);
+  sdpl_sincos(theta, &dy_, &dx_);
   double l_min = 0, l_max = 0, w_min = 0, w_max = 0;      // min / max are order-independent: plain warp reductions
   for (int e = lane; e < n; e += 32) {
     const int q = list[e];
@@ -656,7 +656,7 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
       n = 1;
       ra = seed_ang;
       double sn, cs;
-      sincos(ra, &sn, &cs);
+      sdpl_sincos(ra, &sn, &cs);
       float sumdx = (float)cs, sumdy = (float)sn;
       int nxt = xy_pack(sx, sy);
       __syncwarp();
@@ -763,7 +763,7 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
         cur[0] = xy_pack(sx, sy); n = 1;
         ra = seed_ang;
         double sn, cs;
-        sincos(ra, &sn, &cs);
+        sdpl_sincos(ra, &sn, &cs);
         float sumdx = (float)cs, sumdy = (float)sn;
         int nxt = xy_pack(sx, sy);
 #pragma unroll 1
@@ -1178,7 +1178,7 @@ __device__ void grow_task_rob(const Task& T, RobShared& S) {
           claim_max(&T.state[seed], stamp);
           SEG(cb) = seed; n = 1; i = 0; nxt = seed;
           ra = pa[4].ang;
-          sumdx = (float)cos(ra); sumdy = (float)sin(ra);
+          sumdx = (float)sdpl_cos(ra); sumdy = (float)sdpl_sin(ra);
           phase = PH_GROW;
         }
       } else if (phase == PH_GROW) {
@@ -1230,7 +1230,7 @@ __device__ void grow_task_rob(const Task& T, RobShared& S) {
                                                  : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
           theta *= kDegToRad;
           if (angle_diff(theta, ra) > T.prec) theta += kPI;
-          rec.theta = theta; rec.dx = cos(theta); rec.dy = sin(theta);
+          rec.theta = theta; rec.dx = sdpl_cos(theta); rec.dy = sdpl_sin(theta);
           phase = PH_RECT_C; i = 0; a0 = 0; a1 = 0; a2 = 0; a3 = 0; nxt = SEG(cb);
         }
       } else if (phase == PH_RECT_C) {          // projections -> rectangle

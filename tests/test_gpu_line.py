@@ -66,6 +66,31 @@ def test_speculative_equals_sequential(frontend):
         assert all(o == outs[0] for o in outs[1:])
 
 
+def test_benchmarked_grow_variants_match_oracle(frontend, oracle):
+    """The schedule bench.py times: a batch big enough that the automatic choice is the many-CTAs-per-SM variant
+    (k_lsd_grow_block<4, 4> once frames x octaves exceeds the SM count), every frame compared with the oracle; then the
+    NW x MINB variants pinned through set_serial on a sub-batch, byte-identical to the verified output."""
+    seeds = range(1000, 1096)
+    imgs = synth.frames(seeds, 375, 1242)
+    gpu = frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 0)
+    res = gpu.extract_batch(imgs, capacity=4096)
+    ref = oracle.LineOracle(0, 2, 0.8, 2, 2.0, 0)
+    fracs = []
+    for f in range(len(imgs)):
+        kr, dr = ref(imgs[f])
+        fracs.append(_compare_lines(res[f][0], res[f][1], kr, dr))
+        assert len(kr) > 100
+    assert min(fracs) >= 0.99 and np.mean(fracs) >= 0.995
+    sub = imgs[:8]
+    want = [(k.tobytes(), d.tobytes()) for k, d in res[:8]]
+    for nw in (1, 2, 4, 8):
+        for mb in (1, 2, 4, 6, 8):
+            g = frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 0)
+            g.set_serial(0 | ((nw | (mb << 4)) << 8))
+            got = [(k.tobytes(), d.tobytes()) for k, d in g.extract_batch(sub, capacity=4096)]
+            assert got == want, (nw, mb)
+
+
 def test_lbd_on_oracle_keylines_is_bit_exact(frontend, oracle):
     img = synth.frame(21, 375, 1242)
     kr, dr = oracle.LineOracle()(img)
