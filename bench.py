@@ -208,6 +208,75 @@ def run_reference(args, stages):
         "gpu_launches": 0}))
 
 
+def verify_frames(res, himgs, k):
+    """Output check of the timed product path: K frames spread over the last collected batch, every array the
+    C ABI returned for them against the oracle on the same frames.  Integers, coordinates, responses, ORB descriptors and
+    match indices / distances must be equal; orientations and line end points within 1e-3 (north_star); LBD descriptors equal
+    wherever the key line's floats are equal."""
+    from oracle import oracle as orc
+    F = himgs.shape[0]
+    k = max(0, min(int(k), F - 1))
+    if k == 0:
+        return None
+    picks = sorted(set(1 + (j * (F - 1)) // k for j in range(k)))
+    orb = orc.OrbOracle(ORB_CFG["nfeatures"], ORB_CFG["scale"], ORB_CFG["nlevels"], ORB_CFG["ini"], ORB_CFG["mn"])
+    line = orc.LineOracle(LINE_CFG["nfeatures"], LINE_CFG["refine"], LINE_CFG["lsd_scale"], LINE_CFG["nlevels"], LINE_CFG["scale"],
+                          LINE_CFG["extractor"])
+    st = res["stats"]
+    fails, lbd_rows, lbd_equal, line_float_equal, nlines = [], 0, 0, 0, 0
+
+    def bad(f, what):
+        fails.append("frame %d: %s" % (f, what))
+
+    for f in picks:
+        ok_, od = orb(himgs[f]); pk_, pd = orb(himgs[f - 1])
+        n = int(st["n_kp"][f])
+        gk, gd = res["kps"][f, :n], res["desc"][f, :n]
+        if n != len(ok_):
+            bad(f, "keypoint count %d vs %d" % (n, len(ok_))); continue
+        for name in ("x", "y", "size", "response", "octave", "class_id"):
+            if not (gk[name] == ok_[name]).all():
+                bad(f, "keypoint field " + name)
+        if n and np.abs(gk["angle"] - ok_["angle"]).max() > 1e-3:
+            bad(f, "keypoint angle")
+        if not (gd == od).all():
+            bad(f, "ORB descriptors")
+        want, _ = orc.match_ratio(od, pd, RATIO, MAX_DIST)
+        gm = res["pt_matches"][f, :n]
+        if not ((gm["train"] == want["train"]).all() and (gm["distance"][want["train"] >= 0] == want["distance"][want["train"] >= 0]).all()):
+            bad(f, "point matches")
+        if int(st["n_pt_matches"][f]) != int((want["train"] >= 0).sum()):
+            bad(f, "point match count")
+        ol, old = line(himgs[f]); pl, pld = line(himgs[f - 1])
+        m = int(st["n_lines"][f])
+        gl, gld = res["kls"][f, :m], res["ldesc"][f, :m]
+        if m != len(ol):
+            bad(f, "line count %d vs %d" % (m, len(ol))); continue
+        for name in ("class_id", "octave", "num_pixels"):
+            if not (gl[name] == ol[name]).all():
+                bad(f, "keyline field " + name)
+        same = np.ones(m, bool)
+        for name in ("sx", "sy", "ex", "ey", "sx_oct", "sy_oct", "ex_oct", "ey_oct", "pt_x", "pt_y", "length", "response", "size", "angle"):
+            tol = 1e-3 if name not in ("response", "size", "angle") else (2e-5 if name == "angle" else None)
+            if tol is not None and m and np.abs(gl[name] - ol[name]).max() > tol:
+                bad(f, "keyline field " + name)
+            same &= gl[name] == ol[name]
+        if not (gld[same] == old[same]).all():
+            bad(f, "LBD descriptors")
+        nlines += m; line_float_equal += int(same.sum()); lbd_rows += m; lbd_equal += int((gld == old).all(1).sum())
+        # line matches: the oracle matcher on the descriptors the GPU returned for both frames (equal to the oracle's own
+        # wherever the floats are), so that a last-bit difference in one descriptor is not reported twice
+        mp_ = int(st["n_lines"][f - 1])
+        wantl, _ = orc.match_ratio(gld, res["ldesc"][f - 1, :mp_], RATIO, MAX_DIST) if m and mp_ else (np.zeros(0, orc.DM_DTYPE), 0)
+        glm = res["ln_matches"][f, :m]
+        if m and mp_ and not (glm["train"] == wantl["train"]).all():
+            bad(f, "line matches")
+    return {"frames": len(picks), "ok": not fails, "picked": picks, "failures": fails[:8],
+            "keylines_checked": nlines, "keylines_float_identical": line_float_equal, "lbd_rows_identical": lbd_equal,
+            "what": "ORB keypoints / descriptors, keylines / LBD, ratio-filtered point and line matches of the collected batch vs "
+                    "oracle/liboracle.so on the same frames"}
+
+
 def _config(stages, frames_per_gpu):
     return {"workload": "KITTI-size 1242x375 point+line front-end: ORB 2000 (8 levels, x1.2, FAST 20/7) + LSD/LBD lines "
                         "(refine ADV, 0.8, 2 octaves) + frame-to-frame (t vs t-1) Hamming knn-2 ratio matching of ORB and LBD descriptors "
@@ -394,6 +463,7 @@ def run_gpu(args, stages):
 
     # ---- end to end through the host-buffer C ABI (`e2e`): pinned host frames in, results back on the host ----
     e2e = None
+    verified = None
     if not args.no_e2e and use_line and use_match:
         # release the device-resident arm's buffers first
         for hdl in (orb, mat, line, lmat):
@@ -428,6 +498,8 @@ def run_gpu(args, stages):
                       "per-frame counts back on the host; batch k+1 is submitted before batch k is collected",
                "frame_stats_mean": {"keypoints": float(est["n_kp"].mean()), "keylines": float(est["n_lines"].mean()),
                                     "point_matches": float(est["n_pt_matches"].mean()), "line_matches": float(est["n_ln_matches"].mean())}}
+        if rank == 0 and args.verify > 0:
+            verified = verify_frames(res, himgs, args.verify)
         del front
 
     if rank == 0:
@@ -436,7 +508,7 @@ def run_gpu(args, stages):
                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                "data": "synthetic (seeded noise-texture + rectangles frames, sdpl_slam_b200/synth.py; %d distinct frames per GPU)" % F,
                "config": _config(stages, F), "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roofline,
-               "cpu_baseline": cpu, "stages": stage_rows,
+               "cpu_baseline": cpu, "verified": verified, "stages": stage_rows,
                "frame_stats_mean": {"keypoints": float(st[:, 0].mean()), "keylines": float(st[:, 1].mean()),
                                     "point_matches": float(st[:, 2].mean()), "line_matches": float(st[:, 3].mean())}}
         print(json.dumps(out))
@@ -454,6 +526,7 @@ def main():
     ap.add_argument("--stages", default="orb,line,match")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verify", type=int, default=8, help="frames of the last end-to-end batch compared with the oracle (0 = off)")
     args = ap.parse_args()
     stages = [s for s in args.stages.split(",") if s]
     if args.impl == "reference":

@@ -156,6 +156,10 @@ int sdpl_line_check(sdpl_line* h);
 /* the same flag copied to *host_flag (pinned host memory) on `stream` without synchronising or clearing; sticky */
 int sdpl_orb_peek_error_async(sdpl_orb* h, void* stream, int* host_flag);
 int sdpl_line_peek_error_async(sdpl_line* h, void* stream, int* host_flag);
+/* the same flag copied to *dst (pinned host or device memory) AND cleared, both on the handle's own stream: enqueue it right
+ * after a batch and the flag belongs to that batch alone (what sdpl_frontend_submit does) */
+int sdpl_orb_take_error_async(sdpl_orb* h, int* dst);
+int sdpl_line_take_error_async(sdpl_line* h, int* dst);
 
 /* ------------------------------------------------------------------------------------------------
  * The whole per-frame front-end in one call: Frame::Frame's ExtractORB + ExtractLines (src/Frame.cc:314,328 -> :927-949)
@@ -170,8 +174,12 @@ typedef struct { int32_t n_kp, n_lines, n_pt_matches, n_ln_matches; } sdpl_frame
 int sdpl_frontend_create(sdpl_frontend** h, int nfeatures, float scale, int nlevels, int ini_th, int min_th, int lsd_nfeatures,
                          int lsd_refine, float lsd_scale, int lsd_levels, float lsd_pyr_scale, float ratio, int max_dist, int device);
 void sdpl_frontend_destroy(sdpl_frontend* h);
-/* rows per frame of the output arrays of sdpl_frontend_process */
+/* rows per frame of the output arrays of sdpl_frontend_process.  kp_capacity = sdpl_orb_max_keypoints; kl_capacity =
+ * lsd_nfeatures when that is > 0, else 2048 by default (the reference has no cap then; a frame with more segments makes
+ * collect return SDPL_ERR_CAPACITY with the raw count in stats, its first kl_capacity lines are still matched and returned) */
 int sdpl_frontend_capacities(const sdpl_frontend* h, int* kp_capacity, int* kl_capacity);
+/* change kl_capacity (rows per frame of the key-line outputs); only while no batch is in flight */
+int sdpl_frontend_set_line_capacity(sdpl_frontend* h, int kl_capacity);
 /* forget the previous frame (start of a new sequence) */
 int sdpl_frontend_reset(sdpl_frontend* h);
 /* imgs: HOST, n frames frame_stride bytes apart.  Outputs (HOST): frame f owns rows [f*cap, f*cap + count):

@@ -17,8 +17,11 @@ struct FeSlot {
   // device buffers hold nframes+1 descriptor blocks: block 0 = last frame of the previous batch
   DevBuf imgs, kps, desc, nkp, kls, ldesc, nkl, pbest, psecond, pout, pacc, lbest, lsecond, lout, lacc;
   cudaEvent_t ev_in = nullptr, ev_orb = nullptr, ev_line = nullptr, ev_pm = nullptr, ev_lm = nullptr;
+  cudaEvent_t ev_pread = nullptr, ev_lread = nullptr;   // the NEXT batch has copied this slot's last descriptor block
+  bool read_pending = false;
   int* hn = nullptr; size_t hn_bytes = 0;     // pinned: [4][n] counts + 2 error flags
   int n = 0, w = 0, h = 0;
+  size_t herr_off = 0;                         // where in hn this batch's two overflow flags were written
   bool busy = false;
 };
 
@@ -37,6 +40,8 @@ struct sdpl_frontend {
   int have_prev = 0;
   int launches = 0;
 };
+
+static int fe_create_streams(sdpl_frontend* f);
 
 static int fe_reserve(sdpl_frontend* f, FeSlot& S, int n, int w, int h) {
   int rc;
@@ -82,6 +87,16 @@ int sdpl_frontend_create(sdpl_frontend** out, int nfeatures, float scale, int nl
   }
   f->kp_cap = sdpl_orb_max_keypoints(f->orb);
   f->kl_cap = lsd_nfeatures > 0 ? lsd_nfeatures : 2048;
+  *out = f;                        // from here on an error path hands the half-built object to the caller's destroy ...
+  int rc2 = fe_create_streams(f);
+  if (rc2) { sdpl_frontend_destroy(f); *out = nullptr; return rc2; }   // ... or frees it here
+  return SDPL_OK;
+}
+
+}  // extern "C"
+
+static int fe_create_streams(sdpl_frontend* f) {
+  const int device = f->device;
   SDPL_CUDA(cudaSetDevice(device));
   {
     // all streams share one priority by default: a high-priority line stream (SDPL_FE_LINE_PRIO=high) measured 1-5 % slower on
@@ -93,12 +108,14 @@ int sdpl_frontend_create(sdpl_frontend** out, int nfeatures, float scale, int nl
     SDPL_CUDA(cudaStreamCreateWithPriority(&f->s_line, cudaStreamNonBlocking, (lp && !strcmp(lp, "high")) ? hi : lo));
   }
   for (FeSlot& S : f->slot)
-    for (cudaEvent_t* e : {&S.ev_in, &S.ev_orb, &S.ev_line, &S.ev_pm, &S.ev_lm}) SDPL_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&S.ev_in, &S.ev_orb, &S.ev_line, &S.ev_pm, &S.ev_lm, &S.ev_pread, &S.ev_lread})
+      SDPL_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   sdpl_orb_set_stream(f->orb, f->s_orb); sdpl_line_set_stream(f->line, f->s_line);
   sdpl_matcher_set_stream(f->pm, f->s_pm); sdpl_matcher_set_stream(f->lm, f->s_lm);
-  *out = f;
   return SDPL_OK;
 }
+
+extern "C" {
 
 void sdpl_frontend_destroy(sdpl_frontend* f) {
   if (!f) return;
@@ -110,7 +127,7 @@ void sdpl_frontend_destroy(sdpl_frontend* f) {
                       &S.lout, &S.lacc})
       b->release();
     if (S.hn) cudaFreeHost(S.hn);
-    for (cudaEvent_t e : {S.ev_in, S.ev_orb, S.ev_line, S.ev_pm, S.ev_lm}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {S.ev_in, S.ev_orb, S.ev_line, S.ev_pm, S.ev_lm, S.ev_pread, S.ev_lread}) if (e) cudaEventDestroy(e);
   }
   for (cudaStream_t s : {f->s_io, f->s_orb, f->s_line, f->s_pm, f->s_lm, f->s_out}) if (s) cudaStreamDestroy(s);
   delete f;
@@ -120,6 +137,17 @@ int sdpl_frontend_capacities(const sdpl_frontend* f, int* kp_capacity, int* kl_c
   if (!f) return SDPL_ERR_ARG;
   if (kp_capacity) *kp_capacity = f->kp_cap;
   if (kl_capacity) *kl_capacity = f->kl_cap;
+  return SDPL_OK;
+}
+int sdpl_frontend_set_line_capacity(sdpl_frontend* f, int kl_capacity) {
+  if (!f || kl_capacity < 1 || f->count > 0) { set_last_error("sdpl_frontend_set_line_capacity: bad argument or batches in flight"); return SDPL_ERR_ARG; }
+  cudaSetDevice(f->device);
+  cudaDeviceSynchronize();
+  if (kl_capacity != f->kl_cap) {
+    // the per-slot blocks are laid out by capacity: drop the carried-over "previous frame" with the old layout
+    f->kl_cap = kl_capacity; f->have_prev = 0;
+    for (FeSlot& S : f->slot) S.n = 0;
+  }
   return SDPL_OK;
 }
 int sdpl_frontend_last_launches(const sdpl_frontend* f) { return f ? f->launches : 0; }
@@ -163,6 +191,10 @@ int sdpl_frontend_submit(sdpl_frontend* f, const uint8_t* imgs, int n, int w, in
     SDPL_CUDA(cudaMemcpyAsync(S.nkp.p, P.nkp.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_pm));
     SDPL_CUDA(cudaMemcpyAsync(S.ldesc.p, P.ldesc.as<uint8_t>() + (size_t)pl * LC * 32, (size_t)32 * LC, cudaMemcpyDeviceToDevice, f->s_lm));
     SDPL_CUDA(cudaMemcpyAsync(S.nkl.p, P.nkl.as<int>() + pl, sizeof(int), cudaMemcpyDeviceToDevice, f->s_lm));
+    // the batch after this one extracts into P again: it has to wait for these reads
+    SDPL_CUDA(cudaEventRecord(P.ev_pread, f->s_pm));
+    SDPL_CUDA(cudaEventRecord(P.ev_lread, f->s_lm));
+    P.read_pending = true;
     if (&P == &S) {
       // same buffers (cannot happen while the slots alternate): the extraction below overwrites the block just copied from
       SDPL_CUDA(cudaEventRecord(S.ev_pm, f->s_pm));
@@ -174,14 +206,22 @@ int sdpl_frontend_submit(sdpl_frontend* f, const uint8_t* imgs, int n, int w, in
     SDPL_CUDA(cudaMemsetAsync(S.nkp.p, 0, sizeof(int), f->s_pm));
     SDPL_CUDA(cudaMemsetAsync(S.nkl.p, 0, sizeof(int), f->s_lm));
   }
+  if (S.read_pending) {
+    // the previous submit copied this slot's last descriptor block on the matcher streams: do not overwrite it before that
+    SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, S.ev_pread, 0));
+    SDPL_CUDA(cudaStreamWaitEvent(f->s_line, S.ev_lread, 0));
+    S.read_pending = false;
+  }
   // ---- lines (launched first) and ORB concurrently ----
   SDPL_CUDA(cudaStreamWaitEvent(f->s_line, S.ev_in, 0));
   if ((rc = sdpl_line_extract_batch_dev(f->line, S.imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dl, dld, LC, dln, 0))) return rc;
   launches += sdpl_line_last_launches(f->line);
+  if ((rc = sdpl_line_take_error_async(f->line, S.hn + 4 * (size_t)std::max(n, S.n) + 1))) return rc;   // this batch's own overflow flag
   SDPL_CUDA(cudaEventRecord(S.ev_line, f->s_line));
   SDPL_CUDA(cudaStreamWaitEvent(f->s_orb, S.ev_in, 0));
   if ((rc = sdpl_orb_extract_batch_dev(f->orb, S.imgs.as<uint8_t>(), n, w, h, w, (size_t)w * h, dk, dd, KC, dn, 0))) return rc;
   launches += sdpl_orb_last_launches(f->orb);
+  if ((rc = sdpl_orb_take_error_async(f->orb, S.hn + 4 * (size_t)std::max(n, S.n)))) return rc;
   SDPL_CUDA(cudaEventRecord(S.ev_orb, f->s_orb));
   // ---- frame t against frame t-1 (block t+1 against block t), points then lines ----
   SDPL_CUDA(cudaStreamWaitEvent(f->s_pm, S.ev_orb, 0));
@@ -201,6 +241,7 @@ int sdpl_frontend_submit(sdpl_frontend* f, const uint8_t* imgs, int n, int w, in
   launches += sdpl_matcher_last_launches(f->lm);
   SDPL_CUDA(cudaEventRecord(S.ev_lm, f->s_lm));
   f->launches = launches;
+  S.herr_off = 4 * (size_t)std::max(n, S.n);
   S.n = n; S.w = w; S.h = h; S.busy = true;
   f->last = f->next; f->have_prev = 1;
   f->next ^= 1; f->count++;
@@ -223,14 +264,12 @@ int sdpl_frontend_collect(sdpl_frontend* f, sdpl_keypoint* kps, uint8_t* desc, s
   const uint8_t* dld = S.ldesc.as<uint8_t>() + (size_t)32 * LC;
   const int* dln = S.nkl.as<int>() + 1;
   int* hn = S.hn;                       // [4][n]: n_kp, n_lines, point matches, line matches ; then 2 error flags
-  int* herr = hn + 4 * (size_t)n;
+  int* herr = hn + S.herr_off;          // taken (copied and cleared) in stream order right after this batch's extraction
   cudaStream_t so = f->s_out;
   int status = SDPL_OK;
   // counts size the row copies: fetch them as soon as their stage is done, then only the valid rows of every frame
   SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_orb, 0));
   SDPL_CUDA(cudaMemcpyAsync(hn, dn, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
-  int rc;
-  if ((rc = sdpl_orb_peek_error_async(f->orb, so, herr))) return rc;
   SDPL_CUDA(cudaStreamSynchronize(so));
   for (int i = 0; i < n; i++) {
     int c = hn[i];
@@ -249,7 +288,6 @@ int sdpl_frontend_collect(sdpl_frontend* f, sdpl_keypoint* kps, uint8_t* desc, s
   }
   SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_line, 0));
   SDPL_CUDA(cudaMemcpyAsync(hn + n, dln, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
-  if ((rc = sdpl_line_peek_error_async(f->line, so, herr + 1))) return rc;
   SDPL_CUDA(cudaStreamSynchronize(so));
   for (int i = 0; i < n; i++) {
     int c = hn[n + i];

@@ -736,6 +736,8 @@ void exact_coeffs(double inv_scale, int srcsize, int dstsize, std::vector<ExactC
 static int line_setup(sdpl_line* o, int w, int h, int B) {
   if (o->gw == w && o->gh == h && o->gB >= B) { o->D.B = B; return SDPL_OK; }
   if (o->gw == w && o->gh == h) B = std::max(B, o->gB);
+  // a new geometry or a bigger batch rewrites tables, arenas and the overflow flag: nothing of this handle may be in flight
+  if (o->gw) cudaStreamSynchronize(o->stream);
   const int nl = o->nlevels;
   LineDev& D = o->D;
   memset(&D, 0, sizeof(D));
@@ -1080,6 +1082,15 @@ int sdpl_line_peek_error_async(sdpl_line* o, void* stream, int* host_flag) {
   if (!o || !host_flag) return SDPL_ERR_ARG;
   if (!o->err.p) { *host_flag = 0; return SDPL_OK; }
   SDPL_CUDA(cudaMemcpyAsync(host_flag, o->err.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return SDPL_OK;
+}
+// the overflow flag of everything enqueued so far on the handle's stream, copied to *dst (pinned host or device memory) and
+// cleared, both in stream order: the flag then belongs to the batch that raised it
+int sdpl_line_take_error_async(sdpl_line* o, int* dst) {
+  if (!o || !dst) return SDPL_ERR_ARG;
+  if (!o->err.p) { *dst = 0; return SDPL_OK; }
+  SDPL_CUDA(cudaMemcpyAsync(dst, o->err.p, sizeof(int), cudaMemcpyDefault, o->stream));
+  SDPL_CUDA(cudaMemsetAsync(o->err.p, 0, sizeof(int), o->stream));
   return SDPL_OK;
 }
 int sdpl_line_check(sdpl_line* o) {

@@ -60,10 +60,12 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
 __global__ void __launch_bounds__(kWarps * 32) k_match_partial(const uint8_t* __restrict__ q, const int* __restrict__ nq_arr,
                                                                size_t q_stride, const uint8_t* __restrict__ t,
                                                                const int* __restrict__ nt_arr, size_t t_stride, int max_q,
-                                                               int nsplit, Top2* __restrict__ partial) {
+                                                               int max_t, int nsplit, Top2* __restrict__ partial) {
   const int p = blockIdx.z, s = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nq = nq_arr[p], nt = nt_arr[p];
+  // device-side counts are clamped to the row capacity of their blocks: an extractor that found more features than its output
+  // capacity reports the raw count (the caller sees SDPL_ERR_CAPACITY) but only `capacity` rows exist
+  const int nq = min(nq_arr[p], max_q), nt = min(nt_arr[p], max_t);
   const int q0 = (blockIdx.x * kWarps + warp) * kQW;
   if (q0 >= nq) return;
   const uint8_t* qp = q + (size_t)p * q_stride;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) k_match_merge(const Top2* __restrict__ pa
                                                      int nsplit, sdpl_dmatch* __restrict__ best, sdpl_dmatch* __restrict__ second) {
   const int p = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq_arr[p]) return;
+  if (i >= min(nq_arr[p], max_q)) return;
   Top2 t{kNoDist, 0xFFFFFFFFu, kNoDist, 0xFFFFFFFFu};
   const Top2* src = partial + ((size_t)p * max_q + i) * nsplit;
   for (int s = 0; s < nsplit; s++) { Top2 u = src[s]; top2_insert(t, u.d1, u.i1); top2_insert(t, u.d2, u.i2); }
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256) k_match_ratio_batch(const sdpl_dmatch* __
   const int p = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
-  if (i < nq_arr[p]) {
+  if (i < min(nq_arr[p], max_q)) {
     sdpl_dmatch b = best[(size_t)p * max_q + i], s = second[(size_t)p * max_q + i];
     ok = b.train >= 0 && b.distance <= max_dist && b.distance < __fmul_rn(ratio, s.distance);
     if (!ok) b.train = -1;
@@ -225,7 +227,7 @@ static int match_run_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, s
   int rc = m->partial.reserve(sizeof(Top2) * (size_t)npairs * max_q * nsplit);
   if (rc) return rc;
   m->timer.begin(m->stream);
-  k_match_partial<<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q, nsplit,
+  k_match_partial<<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q, max_t, nsplit,
                                                                                  m->partial.as<Top2>());
   SDPL_LAUNCH_CHECK();
   m->timer.mark(m->stream, "match_partial");

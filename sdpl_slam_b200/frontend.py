@@ -98,6 +98,7 @@ def load_library(path=None):
     L.sdpl_frontend_create.argtypes = [C.POINTER(vp), i, f, i, i, i, i, i, f, i, f, f, i, i]
     L.sdpl_frontend_destroy.argtypes = [vp]; L.sdpl_frontend_destroy.restype = None
     L.sdpl_frontend_capacities.argtypes = [vp, ip, ip]
+    L.sdpl_frontend_set_line_capacity.argtypes = [vp, i]
     L.sdpl_frontend_reset.argtypes = [vp]
     L.sdpl_frontend_process.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp, vp, vp, vp, vp]
     L.sdpl_frontend_last_launches.argtypes = [vp]
@@ -482,7 +483,15 @@ class FrontEnd:
         a, b = C.c_int(), C.c_int()
         _check(self._L.sdpl_frontend_capacities(self._h, C.byref(a), C.byref(b)))
         self.kp_capacity, self.kl_capacity = a.value, b.value
-        self._bufs = None
+        self._bufs = [None, None]
+        self._flip = 0
+        self._inflight = []
+
+    def set_line_capacity(self, kl_capacity):
+        """rows per frame of the key-line outputs (default 2048 when lsd_nfeatures == 0); only while nothing is in flight"""
+        _check(self._L.sdpl_frontend_set_line_capacity(self._h, int(kl_capacity)))
+        self.kl_capacity = int(kl_capacity)
+        self._bufs = [None, None]
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -495,14 +504,16 @@ class FrontEnd:
 
     def _outputs(self, B):
         """two output sets, used alternately (a collected result stays valid until the collect after the next one)"""
-        if self._bufs is None or self._bufs[0][0].shape[0] < B:
-            KC, LC = self.kp_capacity, self.kl_capacity
-            self._bufs = [(np.empty((B, KC), KP_DTYPE), np.empty((B, KC, 32), np.uint8), np.empty((B, LC), KL_DTYPE),
-                           np.empty((B, LC, 32), np.uint8), np.empty((B, KC), DM_DTYPE), np.empty((B, LC), DM_DTYPE),
-                           np.empty(B, FS_DTYPE)) for _ in range(2)]
-            self._flip = 0
         self._flip ^= 1
-        return self._bufs[self._flip]
+        cur = self._bufs[self._flip]
+        if cur is None or cur[0].shape[0] < B:
+            # only the set about to be written is (re)allocated: the other one still holds the previous result
+            KC, LC = self.kp_capacity, self.kl_capacity
+            cur = (np.empty((B, KC), KP_DTYPE), np.empty((B, KC, 32), np.uint8), np.empty((B, LC), KL_DTYPE),
+                   np.empty((B, LC, 32), np.uint8), np.empty((B, KC), DM_DTYPE), np.empty((B, LC), DM_DTYPE),
+                   np.empty(B, FS_DTYPE))
+            self._bufs[self._flip] = cur
+        return cur
 
     def submit(self, images):
         """Enqueue a (B, H, W) uint8 batch (upload, ORB || lines, matching) without waiting.  The array must stay alive and
@@ -514,11 +525,13 @@ class FrontEnd:
             imgs = np.ascontiguousarray(imgs)
         B, H, W = imgs.shape
         _check(self._L.sdpl_frontend_submit(self._h, _p(imgs), B, W, H, W, W * H))
-        self._inflight = getattr(self, "_inflight", []) + [imgs]
+        self._inflight.append(imgs)       # only after the C FIFO accepted the batch
 
     def collect(self):
         """Results of the oldest submitted batch: dict(kps, desc, kls, ldesc, pt_matches, ln_matches: padded (B, cap, ...)
         arrays; stats: per-frame counts)."""
+        if not self._inflight:
+            raise SdplError(SDPL_ERR_ARG, "FrontEnd.collect: nothing submitted")
         imgs = self._inflight.pop(0)
         B = imgs.shape[0]
         kps, desc, kls, ldesc, pm, lm, st = self._outputs(B)

@@ -113,3 +113,41 @@ def test_pipelined_submit_collect_equals_process(frontend):
     b._inflight = [imgs[0:2]]
     with pytest.raises(frontend.SdplError):
         b.collect()
+
+
+def test_line_capacity_overflow_is_reported_and_recoverable(frontend):
+    """More key lines than kl_capacity: collect reports SDPL_ERR_CAPACITY (never a silent truncation), the matchers stay inside
+    the capacity-sized blocks, the flag does not stick to later batches, and a bigger capacity gives the normal result."""
+    imgs = _seq(4, 375, 1242)
+    ref = frontend.FrontEnd(500, 1.2, 8, 20, 7).process(imgs)
+    want = ref["stats"].copy()
+    assert want["n_lines"].min() > 64
+    fe = frontend.FrontEnd(500, 1.2, 8, 20, 7)
+    fe.set_line_capacity(64)
+    for _ in range(2):
+        with pytest.raises(frontend.SdplError) as e:
+            fe.process(imgs)
+        assert e.value.code == frontend.SDPL_ERR_CAPACITY
+    fe.set_line_capacity(2048)
+    got = fe.process(imgs)
+    np.testing.assert_array_equal(got["stats"]["n_lines"], want["n_lines"])
+    np.testing.assert_array_equal(got["stats"]["n_kp"], want["n_kp"])
+    np.testing.assert_array_equal(got["stats"]["n_pt_matches"][1:], want["n_pt_matches"][1:])
+    np.testing.assert_array_equal(got["stats"]["n_ln_matches"][1:], want["n_ln_matches"][1:])
+    with pytest.raises(frontend.SdplError):
+        frontend.FrontEnd(500, 1.2, 8, 20, 7).collect()
+
+
+def test_pipelined_batches_of_varying_size(frontend):
+    """submit / collect with two batches in flight and batch sizes that change: results equal the one-call path, and a
+    collected result stays valid until the collect after the next one."""
+    imgs = _seq(10)
+    one = frontend.FrontEnd(500, 1.2, 8, 20, 7).process(imgs)["stats"].copy()
+    fe = frontend.FrontEnd(500, 1.2, 8, 20, 7)
+    fe.submit(imgs[:2]); fe.submit(imgs[2:6])
+    a = fe.collect(); a_stats = a["stats"].copy()
+    fe.submit(imgs[6:])
+    b = fe.collect()
+    assert (a["stats"] == a_stats).all()          # still intact after the next collect
+    c = fe.collect()
+    np.testing.assert_array_equal(np.concatenate([a_stats, b["stats"], c["stats"]]), one)
