@@ -17,6 +17,7 @@
 //   g      [B][sum_o w_o*h_o] u8, dx/dy [B][sum_o w_o*h_o] i16   LBD Gaussian octaves and Sobel derivatives     (L8)
 // No tensor cores: integer / byte stencils (HBM-bound when batched), a latency-bound greedy stage, fp32/fp64 scalar math.
 #include "lsd_grow.cuh"
+#include "lsd_grow2.cuh"
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -52,6 +53,7 @@ struct LineDev {
   lsd::PxA* px; double* ang; int* g2; uint32_t* state; uint32_t* order;
   uint32_t* hist; int* maxg2; int* ndef; int* task_order;
   int* reg; lsd::Pending* pend; int pend_cap; int* npend;
+  lsd::SlotCtx* ctx; int grow_ta;      // per-task seed-slot contexts of the two-phase schedule; phase-A expansion cap
   uint8_t* g; short* sdx; short* sdy;
   int* err;
   long long* prof;
@@ -342,6 +344,16 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_lsd_grow_block(LineDev D) {
   lsd::Task T;
   make_task(D, f, o, T);
   lsd::grow_task_block(T, S);
+}
+
+// round-2 schedule (lsd_grow2.cuh): phase A per lane, phase B per warp from a CTA-wide queue
+template <int NW, int MINB>
+__global__ void __launch_bounds__(32 * NW, MINB) k_lsd_grow2(LineDev D) {
+  __shared__ lsd::Block2Shared<NW> S;
+  const int task = D.task_order[blockIdx.x], f = task / D.nl, o = task % D.nl;
+  lsd::Task T;
+  make_task(D, f, o, T);
+  lsd::grow_task_block2<NW>(T, D.ctx + (size_t)task * lsd::kCtxSlots, D.grow_ta, S);
 }
 
 constexpr int kLgamN = 32768;
@@ -700,8 +712,9 @@ struct sdpl_line {
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
   DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
-  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx;
+  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
+  int grow_legacy = 0, grow_ta = 8;
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
   int last_B = 0, launches = 0, serial_mode = 0;
@@ -857,6 +870,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->robrect.reserve(sizeof(lsd::Rect) * (size_t)o->rob_w * nl * B))) return rc;
   if ((rc = o->rob.reserve(sizeof(lsd::RobEntry) * (size_t)o->rob_w * nl * B))) return rc;
   if ((rc = o->nbig.reserve(sizeof(int) * 2 * nl * B))) return rc;
+  if ((rc = o->ctx.reserve(sizeof(lsd::SlotCtx) * (size_t)lsd::kCtxSlots * nl * B))) return rc;
   if ((rc = o->bigidx.reserve(sizeof(int) * (size_t)D.pend_cap * nl * B))) return rc;
   if (!o->lgam.p) {
     if ((rc = o->lgam.reserve(sizeof(double) * kLgamN))) return rc;
@@ -891,6 +905,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   D.maxg2 = o->maxg2.as<int>(); D.ndef = o->ndef.as<int>(); D.task_order = o->torder.as<int>(); D.reg = o->reg.as<int>(); D.pend = o->pend.as<lsd::Pending>();
   D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sdx = o->sdx.as<short>(); D.sdy = o->sdy.as<short>();
   D.err = o->err.as<int>(); D.prof = o->prof.as<long long>(); D.lgam = o->lgam.as<double>(); D.lgam_n = kLgamN;
+  D.ctx = o->ctx.as<lsd::SlotCtx>(); D.grow_ta = o->grow_ta;
   D.rob_rect = o->robrect.as<lsd::Rect>(); D.rob = o->rob.as<lsd::RobEntry>(); D.rob_w = o->rob_w;
   D.nbig = o->nbig.as<int>(); D.bigidx = o->bigidx.as<int>();
   D.B = B;
@@ -937,8 +952,25 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   k_lsd_task_rank<<<div_up(nl * B, 128), 128, 0, st>>>(D, nl * B);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_sort");
-  if (o->serial_mode == 0) {
-    // warps per task / CTAs per SM: 8 warps and one CTA per SM (256-seed waves, shortest latency) while every task gets an
+  if (o->serial_mode == 0 && !o->grow_legacy) {
+    // two-phase waves (lsd_grow2.cuh).  Warps per task / CTAs per SM as below
+    const bool small = nl * B <= o->sm_count;
+    const int nw = o->grow_warps > 0 ? o->grow_warps : (small ? 8 : 4);
+    const int mb = o->grow_minb > 0 ? o->grow_minb : (small ? 1 : 4);
+    D.grow_ta = o->grow_ta;
+    if (nw >= 8 && mb >= 2) k_lsd_grow2<8, 2><<<nl * B, 256, 0, st>>>(D);
+    else if (nw >= 8) k_lsd_grow2<8, 1><<<nl * B, 256, 0, st>>>(D);
+    else if (nw >= 4 && mb <= 2) k_lsd_grow2<4, 2><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb <= 4) k_lsd_grow2<4, 4><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb <= 6) k_lsd_grow2<4, 6><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4) k_lsd_grow2<4, 8><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 2 && mb <= 4) k_lsd_grow2<2, 4><<<nl * B, 64, 0, st>>>(D);
+    else if (nw >= 2 && mb <= 8) k_lsd_grow2<2, 8><<<nl * B, 64, 0, st>>>(D);
+    else if (nw >= 2) k_lsd_grow2<2, 12><<<nl * B, 64, 0, st>>>(D);
+    else k_lsd_grow2<1, 16><<<nl * B, 32, 0, st>>>(D);
+  }
+  else if (o->serial_mode == 0) {
+    // legacy round-1 schedule (per-lane speculation): warps per task / CTAs per SM: 8 warps and one CTA per SM (256-seed waves, shortest latency) while every task gets an
     // SM to itself; 4 warps and 4 CTAs per SM (127 registers) for big batches (measured best at 512 frames: 134 ms vs 158 ms
     // for 8x2 and 250 ms for 8x1); sdpl_line_set_serial can pin both
     const bool small = nl * B <= o->sm_count;
@@ -1055,7 +1087,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
   for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
-                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx})
+                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx, &o->ctx})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
   o->timer.release();
@@ -1112,9 +1144,12 @@ int sdpl_line_stage_times(sdpl_line* o, float* ms, const char** names, int* laun
 int sdpl_line_set_serial(sdpl_line* o, int on) {
   if (!o || on < 0) return SDPL_ERR_ARG;
   // bits 0-1: schedule; bits 8..: re-order buffer size override (power of two, <= allocated), for tuning
-  const int w = on >> 8;
-  if (w && (on & 3) == 2 && (w < 1 || w > 2048 || (w & (w - 1)))) return SDPL_ERR_ARG;
+  const int w0 = (on >> 8) & 0xffff;
+  if (w0 && (on & 3) == 2 && (w0 < 1 || w0 > 2048 || (w0 & (w0 - 1)))) return SDPL_ERR_ARG;
   o->serial_mode = on & 3;
+  o->grow_legacy = (on >> 2) & 1;                    // bit 2: the round-1 per-lane schedule instead of the two-phase one
+  if ((on >> 24) & 0x7f) o->grow_ta = ((on >> 24) & 0x7f) - 1;   // bits 24-30: phase-A expansion cap + 1
+  const int w = (on >> 8) & 0xffff;
   if (w && o->serial_mode == 2) o->rob_w_run = std::max(w, 32);
   if (w && o->serial_mode == 0) { o->grow_warps = std::min(w & 15, lsd::kMaxGrowWarps); if (w >> 4) o->grow_minb = w >> 4; }
   return SDPL_OK;

@@ -10,7 +10,7 @@ i = 0
 cur_line = None
 while i < len(rows):
     r = rows[i]
-    if r and r[0] == "File Name":
+    if r and r[0] in ("File Name", "File Path"):
         cur_file = r[1]; i += 1; continue
     if r and r[0] == "Line No":
         hdr = r; i += 1; continue
@@ -43,8 +43,9 @@ if len(sys.argv) > 4:
     print("--- buckets")
     for spec in sys.argv[4].split(","):
         name, rng = spec.split(":"); lo, hi = map(int, rng.split("-"))
+        fsub = name.split("@")[1] if "@" in name else ""
         a = [0, 0, 0]
         for (f, l), v in agg.items():
-            if lo <= l <= hi:
+            if lo <= l <= hi and fsub in str(f):
                 a[0] += v[0]; a[1] += v[1]; a[2] += v[2]
         print("%-28s inst %5.1f%%  thr/inst %5.1f  samples %5.1f%%" % (name, 100 * a[0] / tot[0], a[1] / max(1, a[0]), 100 * a[2] / max(1, tot[2])))
