@@ -208,6 +208,13 @@ int sdpl_line_stage_times(sdpl_line* h, float* ms, const char** names, int* laun
 int sdpl_matcher_set_profiling(sdpl_matcher* h, int on);
 int sdpl_matcher_stage_times(sdpl_matcher* h, float* ms, const char** names, int* launches, int cap);
 
+/* Order-independent 64-bit digest of per-frame result rows resident on the device: adds, for every frame f, the sum of the
+ * hashes of rows [0, min(d_n[f], max_rows)) of its block (row_bytes per row, a multiple of 4; blocks frame_stride bytes apart)
+ * to d_digest[f] (DEVICE uint64 array the caller zeroes), asynchronously on `stream` (cudaStream_t as void*).  Used to check
+ * that a batch sharded over several GPUs gives byte-identical per-frame results. */
+int sdpl_rows_digest_dev(const void* d_rows, int row_bytes, size_t frame_stride, const int* d_n, int nframes, int max_rows,
+                         unsigned long long salt, unsigned long long* d_digest, void* stream);
+
 /* Bind a handle's work to a caller stream (cudaStream_t as void*; NULL = the handle's own stream). */
 int sdpl_orb_set_stream(sdpl_orb* h, void* cuda_stream);
 int sdpl_line_set_stream(sdpl_line* h, void* cuda_stream);

@@ -714,7 +714,7 @@ struct sdpl_line {
   DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
-  int grow_legacy = 0, grow_ta = 8;
+  int grow_legacy = 0, grow_ta = 16;   // phase-A cap: 16 measured best at 512 frames (4: 51.2, 8: 49.9, 16: 47.6 ms)
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
   int last_B = 0, launches = 0, serial_mode = 0;

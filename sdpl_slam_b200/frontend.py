@@ -105,6 +105,7 @@ def load_library(path=None):
     L.sdpl_frontend_submit.argtypes = [vp, vp, i, i, i, i, sz]
     L.sdpl_frontend_collect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ip]
     L.sdpl_frontend_pending.argtypes = [vp]
+    L.sdpl_rows_digest_dev.argtypes = [vp, i, sz, vp, i, i, C.c_ulonglong, vp, vp]
     if path is None:
         _lib = L
     return L
@@ -546,6 +547,12 @@ class FrontEnd:
 
     def last_launches(self):
         return self._L.sdpl_frontend_last_launches(self._h)
+
+
+def rows_digest_dev(d_rows, row_bytes, frame_stride, d_n, nframes, max_rows, salt, d_digest, cuda_stream=0):
+    """sdpl_rows_digest_dev: adds the 64-bit digest of every frame's valid rows to d_digest[f] (device pointers as ints)."""
+    _check(load_library().sdpl_rows_digest_dev(C.c_void_p(d_rows), int(row_bytes), int(frame_stride), C.c_void_p(d_n), int(nframes),
+                                               int(max_rows), int(salt), C.c_void_p(d_digest), C.c_void_p(cuda_stream)))
 
 
 def device_count():

@@ -45,6 +45,50 @@ def gather_frame_stats(stats, group=None):
     return torch.cat([out[r * m:r * m + counts[r]] for r in range(world)], 0)
 
 
+class StatsGather:
+    """The per-step form of gather_frame_stats for a batch whose size is known to every rank (the bench's and a production
+    loop's case): the shard sizes follow from shard_range, so there is no count exchange and no host synchronisation -- one
+    asynchronous all_gather_into_tensor per step into a buffer allocated once; table() waits for the last one and returns the
+    (n_total, cols) table in frame order.  Ragged shards are padded to the longest one."""
+
+    def __init__(self, n_total, cols, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.counts = [e - s for s, e in (shard_range(n_total, r, self.world) for r in range(self.world))]
+        self.m = max(self.counts) if self.counts else 0
+        self.ragged = any(c != self.m for c in self.counts)
+        self.out = torch.zeros((self.world * self.m, cols), dtype=dtype, device=device)
+        self.pad = torch.zeros((self.m, cols), dtype=dtype, device=device) if self.ragged else None
+        self.work = None
+
+    def start(self, stats):
+        """Enqueue the gather of this rank's (n_local, cols) table; returns at once."""
+        import torch.distributed as dist
+        if stats.shape[0] != self.counts[self.rank]:
+            raise ValueError("rank %d holds %d rows, its shard has %d" % (self.rank, stats.shape[0], self.counts[self.rank]))
+        if not self.on:
+            self.out[:stats.shape[0]].copy_(stats)
+            return
+        src = stats
+        if self.ragged:
+            self.pad[:stats.shape[0]].copy_(stats)
+            src = self.pad
+        self.work = dist.all_gather_into_tensor(self.out, src.contiguous(), group=self.group, async_op=True)
+
+    def table(self):
+        import torch
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        if not self.ragged:
+            return self.out
+        return torch.cat([self.out[r * self.m:r * self.m + self.counts[r]] for r in range(self.world)], 0)
+
+
 def frame_checksum(img: np.ndarray) -> np.ndarray:
     """Cheap deterministic 4-int summary of a frame; stands in for the GPU statistics in the CPU (gloo) tests."""
     a = img.astype(np.int64)

@@ -37,12 +37,44 @@ def frame(seed: int, h: int = 375, w: int = 1242, n_rect: int = 40) -> np.ndarra
     return np.clip(img, 0, 255).astype(np.uint8)
 
 
-def partner(seed: int, h: int = 375, w: int = 1242, dx: int = 3, dy: int = 1, gain: int = 6) -> np.ndarray:
-    """Integer-shifted, brightness-offset copy of frame(seed) (edge pixels replicated)."""
-    f = frame(seed, h, w).astype(np.int64)
+def partner_from(f: np.ndarray, dx: int = 3, dy: int = 1, gain: int = 6) -> np.ndarray:
+    """Integer-shifted, brightness-offset copy of the frame `f` (edge pixels replicated)."""
+    h, w = f.shape
     ys = np.clip(np.arange(h) - dy, 0, h - 1)
     xs = np.clip(np.arange(w) - dx, 0, w - 1)
-    return np.clip(f[ys][:, xs] + gain, 0, 255).astype(np.uint8)
+    return np.clip(f.astype(np.int64)[ys][:, xs] + gain, 0, 255).astype(np.uint8)
+
+
+def partner(seed: int, h: int = 375, w: int = 1242, dx: int = 3, dy: int = 1, gain: int = 6) -> np.ndarray:
+    """partner_from(frame(seed))."""
+    return partner_from(frame(seed, h, w), dx, dy, gain)
+
+
+def _pair(args):
+    seed, h, w = args
+    f = frame(seed, h, w)
+    return f, partner_from(f)
+
+
+def sequence(g0: int, g1: int, h: int = 375, w: int = 1242, workers: int = 1) -> np.ndarray:
+    """Frames [g0, g1) of THE synthetic sequence frame(0), partner(0), frame(1), partner(1), ...: global frame g is
+    frame(g // 2) for even g and partner(g // 2) for odd g.  This is the batch BASELINE.json configs[3] shards across GPUs;
+    every rank synthesises its own block (and the halo frame before it) from the global frame numbers alone."""
+    out = np.empty((max(0, g1 - g0), h, w), np.uint8)
+    if g1 <= g0:
+        return out
+    seeds = list(range(g0 // 2, (g1 + 1) // 2))
+    if workers > 1 and len(seeds) > 4:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            pairs = pool.map(_pair, [(s, h, w) for s in seeds], chunksize=4)
+    else:
+        pairs = [_pair((s, h, w)) for s in seeds]
+    for s, (a, b) in zip(seeds, pairs):
+        for g, img in ((2 * s, a), (2 * s + 1, b)):
+            if g0 <= g < g1:
+                out[g - g0] = img
+    return out
 
 
 def frames(seeds, h: int = 375, w: int = 1242) -> np.ndarray:

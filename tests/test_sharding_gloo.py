@@ -39,6 +39,11 @@ def _worker(rank, world, port, n_frames, q):
         local = np.stack([shard.frame_checksum(synth.frame(100 + f, 48, 64, n_rect=3)) for f in range(s, e)]) if e > s \
             else np.zeros((0, 4), np.int32)
         table = shard.gather_frame_stats(torch.from_numpy(local))
+        # the per-step form (shard sizes from shard_range: no count exchange, asynchronous) must give the same table
+        g = shard.StatsGather(n_frames, 4, torch.int32, "cpu")
+        for _ in range(2):
+            g.start(torch.from_numpy(local))
+        assert torch.equal(g.table(), table)
         if rank == 0:
             q.put(table.numpy())
         dist.barrier()
