@@ -58,6 +58,7 @@ struct LineDev {
   int* err;
   long long* prof;
   const double* lgam; int lgam_n;
+  const double* nfa_tab;               // [nl][kNfaTabLevels][kNfaTabTri] (lsd::nfa_lookup), filled by k_nfa_table at set-up
   lsd::Rect* rob_rect; lsd::RobEntry* rob; int rob_w, rob_w_run;
   int* nbig; int* bigidx;
   double rho, prec, p, density_th, log_eps, scale;
@@ -309,6 +310,7 @@ __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::T
   T.min_reg = O.min_reg; T.refine = D.refine; T.err = D.err;
   T.prof = D.prof ? D.prof + (size_t)task * 8 : nullptr;
   T.lgam = D.lgam; T.lgam_n = D.lgam_n;
+  T.nfa_tab = D.nfa_tab ? D.nfa_tab + (size_t)o * lsd::kNfaTabLevels * lsd::kNfaTabTri : nullptr;
   T.rob_rect = D.rob_rect + (size_t)task * D.rob_w; T.rob = D.rob + (size_t)task * D.rob_w; T.rob_w = D.rob_w_run;
 }
 
@@ -365,6 +367,21 @@ static double host_log_gamma(double x) {
   return a + std::log(b);
 }
 
+// the NFA table of lsd::nfa_lookup: entry (octave, halvings j, n, k) = nfa(n, k, p / 2^j), one thread per entry
+__global__ void __launch_bounds__(128) k_nfa_table(LineDev D, double* __restrict__ tab) {
+  const int o = blockIdx.z, j = blockIdx.y, e = blockIdx.x * 128 + threadIdx.x;
+  if (e >= lsd::kNfaTabTri) return;
+  int n = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) / 2.0);
+  while (n * (n + 1) / 2 > e) --n;
+  while ((n + 1) * (n + 2) / 2 <= e) ++n;
+  const int k = e - n * (n + 1) / 2;
+  lsd::Task T;
+  T.log_nt = D.O[o].log_nt; T.lgam = D.lgam; T.lgam_n = D.lgam_n;
+  double p = D.p;
+  for (int i = 0; i < j; i++) p /= 2;
+  tab[((size_t)o * lsd::kNfaTabLevels + j) * lsd::kNfaTabTri + e] = lsd::nfa(T, n, k, p);
+}
+
 // small rectangles: one thread each; rectangles whose scan visits more than kBigRect pixels are queued for the warp kernel
 constexpr double kBigRect = 384.0;
 __global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
@@ -389,7 +406,8 @@ __global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
 // (lsd::validate_rest_warp).  A warp wants a dozen rectangles to keep its six groups busy: the number of warps that work on a
 // task follows the length of its list
 constexpr int kRestBlocks = 16;
-__global__ void __launch_bounds__(128, 16) k_lsd_nfa_rest(LineDev D) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_lsd_nfa_rest(LineDev D) {
   const int task = blockIdx.y;
   const int f = task / D.nl, o = task % D.nl;
   const int nf = D.nbig[(size_t)D.nl * D.B + task];
@@ -712,8 +730,9 @@ struct sdpl_line {
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
   DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
-  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx;
+  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx, nfatab;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
+  int nfa_minb = 10;      // second NFA pass compiled for 10 CTAs per SM (48 registers): 6.11 ms at 16, 5.33 at 12, 5.24 at 10, 5.37 at 8 (512 frames)
   int grow_legacy = 0, grow_ta = 16;   // phase-A cap: 16 measured best at 512 frames (4: 51.2, 8: 49.9, 16: 47.6 ms)
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
   int pend_cap = 4096;
@@ -909,6 +928,15 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   D.rob_rect = o->robrect.as<lsd::Rect>(); D.rob = o->rob.as<lsd::RobEntry>(); D.rob_w = o->rob_w;
   D.nbig = o->nbig.as<int>(); D.bigidx = o->bigidx.as<int>();
   D.B = B;
+  {
+    // NFA values of every small rectangle this geometry can produce (lsd::nfa_lookup); asynchronous on the handle's stream
+    if ((rc = o->nfatab.reserve(sizeof(double) * (size_t)nl * lsd::kNfaTabLevels * lsd::kNfaTabTri))) return rc;
+    D.nfa_tab = nullptr;
+    k_nfa_table<<<dim3(div_up(lsd::kNfaTabTri, 128), lsd::kNfaTabLevels, nl), 128, 0, o->stream>>>(D, o->nfatab.as<double>());
+    SDPL_LAUNCH_CHECK();
+    SDPL_CUDA(cudaStreamSynchronize(o->stream));      // set-up is the rare path; the caller may switch streams before the next call
+    D.nfa_tab = o->nfatab.as<double>();
+  }
   o->gw = w; o->gh = h; o->gB = B;
   return SDPL_OK;
 }
@@ -996,7 +1024,10 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   SDPL_LAUNCH_CHECK();
   k_lsd_nfa_big<<<dim3(64, nl * B), 128, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
-  k_lsd_nfa_rest<<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
+  if (o->nfa_minb >= 16) k_lsd_nfa_rest<16><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
+  else if (o->nfa_minb >= 12) k_lsd_nfa_rest<12><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
+  else if (o->nfa_minb >= 10) k_lsd_nfa_rest<10><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
+  else k_lsd_nfa_rest<8><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_nfa");
   k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());
@@ -1087,7 +1118,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
   for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
-                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx, &o->ctx})
+                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx, &o->ctx, &o->nfatab})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
   o->timer.release();
@@ -1147,6 +1178,7 @@ int sdpl_line_set_serial(sdpl_line* o, int on) {
   const int w0 = (on >> 8) & 0xffff;
   if (w0 && (on & 3) == 2 && (w0 < 1 || w0 > 2048 || (w0 & (w0 - 1)))) return SDPL_ERR_ARG;
   o->serial_mode = on & 3;
+  if ((on >> 3) & 31) o->nfa_minb = (on >> 3) & 31;    // bits 3-7: CTAs per SM the second NFA pass is compiled for (tuning)
   o->grow_legacy = (on >> 2) & 1;                    // bit 2: the round-1 per-lane schedule instead of the two-phase one
   if ((on >> 24) & 0x7f) o->grow_ta = ((on >> 24) & 0x7f) - 1;   // bits 24-30: phase-A expansion cap + 1
   const int w = (on >> 8) & 0xffff;

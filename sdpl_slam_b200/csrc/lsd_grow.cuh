@@ -62,6 +62,7 @@ struct Task {                      // one (frame, level)
   int* err;
   struct RobEntry* rob; Rect* rob_rect; int rob_w;   // re-order buffer (rob_w entries, power of two): metadata + rectangle staging
   const double* lgam; int lgam_n;  // log_gamma(i) for integer i < lgam_n (same formulas, tabulated once per handle)
+  const double* nfa_tab;           // nfa(n, k, p / 2^j) of this octave for n <= kNfaTabN, j < kNfaTabLevels (or null): see nfa_lookup
   long long* prof;                 // optional [8]: cycles in select / speculate / evaluate+commit / re-run, waves, re-runs, dead, seeds
 };
 
@@ -1478,6 +1479,23 @@ __device__ __noinline__ double nfa(const Task& T, int n, int k, double p) {
   return -log10(bin_tail) - log_nt;
 }
 
+// nfa(n, k, p) depends on two small integers, on p -- which rect_improve only ever halves, starting from T.p, at most ten times --
+// and on the octave's log_nt.  The values for n <= kNfaTabN are therefore tabulated once per handle and geometry BY THIS VERY
+// FUNCTION (k_nfa_table in line.cu), so a look-up returns bit for bit what the call would: the validation kernels then consist of
+// the pixel scans alone -- no log / exp / pow / division chains, no divergent binomial-tail loops, a fraction of the code footprint
+// (the second NFA pass was instruction-fetch bound with them).
+constexpr int kNfaTabN = 512;
+constexpr int kNfaTabLevels = 11;
+constexpr int kNfaTabTri = (kNfaTabN + 1) * (kNfaTabN + 2) / 2;
+__device__ __forceinline__ double nfa_lookup(const Task& T, int n, int k, double p) {
+  if (T.nfa_tab && n <= kNfaTabN) {
+    const int j = ((__double2hiint(T.p) >> 20) & 0x7ff) - ((__double2hiint(p) >> 20) & 0x7ff);   // number of halvings
+    if ((unsigned)j < (unsigned)kNfaTabLevels && p * (double)(1 << j) == T.p)
+      return T.nfa_tab[(size_t)j * kNfaTabTri + ((n * (n + 1)) >> 1) + k];
+  }
+  return nfa(T, n, k, p);
+}
+
 // counts the pixels of the rotated rectangle and those aligned with it.  Integer counting is order-independent, so any
 // traversal gives the oracle's totals.  COOP = false: one thread per rectangle; COOP = true: one warp per rectangle (lanes
 // over rows for tall rectangles, over columns otherwise; the NFA itself is evaluated by lane 0 and broadcast).
@@ -1515,11 +1533,11 @@ __device__ __noinline__ double rect_nfa(const Task& T, const Rect& rec) {
       if (aligned_angle(row[x], rec.theta, rec.prec)) ++alg;
     }
   }
-  if (!COOP) return nfa(T, total, alg, rec.p);
+  if (!COOP) return nfa_lookup(T, total, alg, rec.p);
 #pragma unroll
   for (int o = 16; o; o >>= 1) { total += __shfl_xor_sync(0xffffffffu, total, o); alg += __shfl_xor_sync(0xffffffffu, alg, o); }
   double v = 0;
-  if (lane == 0) v = nfa(T, total, alg, rec.p);
+  if (lane == 0) v = nfa_lookup(T, total, alg, rec.p);
   return __shfl_sync(0xffffffffu, v, 0);
 }
 
