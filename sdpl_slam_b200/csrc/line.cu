@@ -33,6 +33,9 @@ struct OctDev {
   int w, h;                 // octave image size
   int sw, sh, npx;          // LSD working size (0.8x) and pixel count
   int lw, lh;               // LBD octave size (w>>o, h>>o)
+  int sc_stride; unsigned long long sc_off;   // LSD working image (0.8x): 16-byte row pitch, offset inside one frame's block
+  int gstride;              // row pitch of the LBD Gaussian octave (multiple of 16 bytes: aligned word loads / stores)
+  unsigned long long g_off; // its offset inside one frame's block of D.g
   unsigned long long lvl_off, px_off, lbd_off;   // element offsets inside one frame's block
   int nchunks; unsigned long long hist_off;       // per task (frame-independent) offsets inside one frame's hist block
   unsigned long long reg_off;                     // inside one frame's reg block (ints)
@@ -48,7 +51,7 @@ struct LineDev {
   int nl, B;
   int in_w, in_h, in_stride; unsigned long long in_frame;
   const uint8_t* in;
-  unsigned long long lvl_frame, px_frame, lbd_frame, hist_frame, reg_frame;
+  unsigned long long lvl_frame, px_frame, lbd_frame, g_frame, sc_frame, hist_frame, reg_frame;
   uint8_t *lvl, *scaled;
   lsd::PxA* px; double* ang; int* g2; uint32_t* state; uint32_t* order;
   uint32_t* hist; int* maxg2; int* ndef; int* task_order;
@@ -68,6 +71,67 @@ struct LineDev {
   OctDev O[kMaxOct];
   float gaussL[21], gaussG[63];
 };
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory staging of an u8 image window as aligned 32-bit words, for the word / dp4a stencils below (L2, L8).
+// Staged word m of a row holds the image columns xf + 4m - 4 .. xf + 4m - 1, whatever the alignment of the image rows in
+// global memory (a frame of width 1242 has rows that are not word aligned): every staged word is cut from two aligned global
+// words with a funnel shift.  Rows beyond the top / bottom edge are reflected (reflect-101) by index; columns beyond the left /
+// right edge -- up to column xlast -- are patched in shared memory from their mirror columns.  [lo, hi) bounds the aligned words
+// that overlap the caller's buffer: nothing outside is read.  One warp per row; warps = blockDim.x / 32.
+// ------------------------------------------------------------------------------------------------
+template <int NWORDS>
+__device__ __forceinline__ void stage_tile(uint32_t (*s_in)[NWORDS], int nrows, int nwords, const uint8_t* img, int stride, int W, int H, int xf,
+                                           int yf, int xlast, uintptr_t lo, uintptr_t hi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int r = warp; r < nrows; r += nwarp) {
+    const int ry = reflect101(min(max(yf + r, -H + 1), 2 * H - 2), H);
+    const uintptr_t a = (uintptr_t)(img + (size_t)ry * stride) + xf - 4;
+    const int sh = (int)(a & 3) * 8;
+    const uintptr_t a0 = a - (a & 3);
+    for (int m = lane; m < nwords; m += 32) {
+      const uintptr_t wa = a0 + 4 * (uintptr_t)m;
+      const bool need = xf - 4 + 4 * m <= xlast;
+      const uint32_t w0 = (need && wa >= lo && wa < hi) ? __ldg((const uint32_t*)wa) : 0u;
+      const uint32_t w1 = (need && sh && wa + 4 >= lo && wa + 4 < hi) ? __ldg((const uint32_t*)(wa + 4)) : 0u;
+      s_in[r][m] = __funnelshift_r(w0, w1, sh);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      uint8_t* row = (uint8_t*)s_in[r] + 4;                   // row[c] = image column xf + c
+      for (int c = -4; c < 0; c++) if (xf + c < 0) row[c] = row[-(xf + c) - xf];
+      for (int xi = W; xi <= xlast && xi - xf < 4 * nwords - 4; xi++) row[xi - xf] = row[2 * (W - 1) - xi - xf];
+    }
+  }
+}
+// horizontal 5-tap pass (k0, k1, k2, k1, k0) over staged words: word m -> the four 16-bit row sums of its columns
+template <int NWORDS>
+__device__ __forceinline__ void hz5_tile(const uint32_t (*s_in)[NWORDS], uint2 (*s_hz)[NWORDS], int nrows, int nwords, uint32_t k0, uint32_t k1,
+                                         uint32_t k2) {
+  const uint32_t K_lo = k0 | (k1 << 8) | (k2 << 16) | (k1 << 24), K_hi = k0;
+  for (int i = threadIdx.x; i < nrows * nwords; i += blockDim.x) {
+    const int r = i / nwords, m = i - r * nwords;
+    const uint32_t P = m > 0 ? s_in[r][m - 1] : 0u, C = s_in[r][m], N = m < nwords - 1 ? s_in[r][m + 1] : 0u;
+    const uint32_t h0 = __dp4a(__funnelshift_r(P, C, 16), K_lo, __dp4a(__funnelshift_r(C, N, 16), K_hi, 0u));
+    const uint32_t h1 = __dp4a(__funnelshift_r(P, C, 24), K_lo, __dp4a(__funnelshift_r(C, N, 24), K_hi, 0u));
+    const uint32_t h2 = __dp4a(C, K_lo, __dp4a(N, K_hi, 0u));
+    const uint32_t h3 = __dp4a(__funnelshift_r(C, N, 8), K_lo, __dp4a(N >> 8, K_hi, 0u));
+    s_hz[r][m] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+  }
+}
+// vertical 5-tap pass on the row sums of rows gr .. gr + 4 of word m: four blurred bytes ((v + 2^15) >> 16; the weights add up to
+// 2^16, so a result cannot exceed 255)
+template <int NWORDS>
+__device__ __forceinline__ uint32_t vt5_word(const uint2 (*s_hz)[NWORDS], int gr, int m, uint32_t k0, uint32_t k1, uint32_t k2) {
+  const uint2 a = s_hz[gr][m], b = s_hz[gr + 1][m], c = s_hz[gr + 2][m], d = s_hz[gr + 3][m], e = s_hz[gr + 4][m];
+  uint32_t v[4];
+  v[0] = k0 * ((a.x & 0xffffu) + (e.x & 0xffffu)) + k1 * ((b.x & 0xffffu) + (d.x & 0xffffu)) + k2 * (c.x & 0xffffu) + (1u << 15);
+  v[1] = k0 * ((a.x >> 16) + (e.x >> 16)) + k1 * ((b.x >> 16) + (d.x >> 16)) + k2 * (c.x >> 16) + (1u << 15);
+  v[2] = k0 * ((a.y & 0xffffu) + (e.y & 0xffffu)) + k1 * ((b.y & 0xffffu) + (d.y & 0xffffu)) + k2 * (c.y & 0xffffu) + (1u << 15);
+  v[3] = k0 * ((a.y >> 16) + (e.y >> 16)) + k1 * ((b.y >> 16) + (d.y >> 16)) + k2 * (c.y >> 16) + (1u << 15);
+  const uint32_t lo2 = __byte_perm(v[0], v[1], 0x0062), hi2 = __byte_perm(v[2], v[3], 0x0062);
+  return __byte_perm(lo2, hi2, 0x5410);
+}
 
 // ------------------------------------------------------------------------------------------------
 // L1: octave o from octave o-1, cv::resize INTER_LINEAR (LSDDetectorC::ComputePyramid, LSDDetector_custom.cpp:76-109).
@@ -110,55 +174,72 @@ __global__ void __launch_bounds__(128) k_line_resize(LineDev D, int o) {
 //     resize(fx=fy=0.8, INTER_LINEAR_EXACT) (Q8.8 coefficients).  One CTA = 64x16 output pixels; the source tile is
 //     staged in shared memory, blurred there (horizontal Q8.8 -> u16, vertical Q16.16 -> u8), then down-sampled.
 // ------------------------------------------------------------------------------------------------
-constexpr int kST_W = 64, kST_H = 16;
-constexpr int kSS_W = 88, kSS_H = 28;     // max source tile (incl. +-3 halo): 64/0.8+2+6, 16/0.8+2+6
+constexpr int kST_W = 128, kST_H = 32;
+constexpr int kSS_W = 168, kSS_H = 48;    // max source tile (incl. +-3 halo): 128/0.8+2+6, 32/0.8+2+6 (bounds checked at set-up)
+constexpr int kSS_WW = 44;                // staged words per row: columns -4 .. 171 relative to the first blurred column
+//     The source window is staged as aligned words (stage_tile), blurred with the dp4a row pass / 16-bit column pass of the
+//     LBD kernel (the outer taps of the 7-tap kernel are zero: five taps 4, 56, 136, 56, 4), and a thread then interpolates four
+//     adjacent output pixels and stores them as one word (the scaled plane has a 16-byte row pitch of its own).
 __global__ void __launch_bounds__(256) k_lsd_scale(LineDev D, int o) {
-  __shared__ uint8_t in[kSS_H][kSS_W];
-  __shared__ unsigned short hz[kSS_H][kSS_W - 6];
-  __shared__ uint8_t bl[kSS_H - 6][kSS_W - 6];
+  __shared__ uint32_t s_in[kSS_H][kSS_WW];
+  __shared__ uint2 s_hz[kSS_H][kSS_WW];
+  uint32_t (*s_bl)[kSS_WW] = s_in;          // the blurred window takes the place of the staged one (dead after the row pass)
   const OctDev& O = D.O[o];
   const int ox0 = blockIdx.x * kST_W, oy0 = blockIdx.y * kST_H;
   const int ox1 = min(ox0 + kST_W, O.sw) - 1, oy1 = min(oy0 + kST_H, O.sh) - 1;
-  const uint8_t* src; int sstride;
-  if (o == 0) { src = D.in + (size_t)blockIdx.z * D.in_frame; sstride = D.in_stride; }
-  else { src = D.lvl + (size_t)blockIdx.z * D.lvl_frame + O.lvl_off; sstride = O.w; }
+  const uint8_t* src; int sstride; uintptr_t lo, hi;
+  if (o == 0) {
+    src = D.in + (size_t)blockIdx.z * D.in_frame; sstride = D.in_stride;
+    lo = (uintptr_t)D.in & ~(uintptr_t)3;
+    hi = ((uintptr_t)D.in + (size_t)(D.B - 1) * D.in_frame + (size_t)(O.h - 1) * D.in_stride + O.w + 3) & ~(uintptr_t)3;
+  } else {
+    src = D.lvl + (size_t)blockIdx.z * D.lvl_frame + O.lvl_off; sstride = O.w;
+    lo = (uintptr_t)D.lvl; hi = (uintptr_t)D.lvl + (size_t)D.B * D.lvl_frame;        // own arena, 256-byte granules
+  }
   // blurred source range needed by this tile
   const int bx0 = O.ex_ofs[ox0], bx1 = min(O.ex_ofs[ox1] + 1, O.w - 1);
   const int by0 = O.ey_ofs[oy0], by1 = min(O.ey_ofs[oy1] + 1, O.h - 1);
-  const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;      // <= 82 x 22
-  const int iw = bw + 6, ih = bh + 6;
-  // one warp per row, lanes over columns: no integer division by the (run-time) tile width
-  const int wr = threadIdx.x >> 5, ln = threadIdx.x & 31;
-  for (int yy = wr; yy < ih; yy += 8) {
-    const uint8_t* srow = src + (size_t)reflect101(by0 - 3 + yy, O.h) * sstride;
-    for (int xx = ln; xx < iw; xx += 32) in[yy][xx] = srow[reflect101(bx0 - 3 + xx, O.w)];
+  const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;      // <= 162 x 42
+  constexpr int nwords = kSS_WW;                         // columns -4 .. 171 >= bw + 1 (words beyond the need are staged as zeros)
+  const int nrows = bh + 4;                              // rows by0 - 2 .. by1 + 2
+  stage_tile<kSS_WW>(s_in, nrows, nwords, src, sstride, O.w, O.h, bx0, by0 - 2, bx1 + 2, lo, hi);
+  __syncthreads();
+  hz5_tile<kSS_WW>(s_in, s_hz, nrows, nwords, 4u, 56u, 136u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < bh * nwords; i += 256) {
+    const int gr = i / nwords, m = i - gr * nwords;
+    s_bl[gr][m] = vt5_word<kSS_WW>(s_hz, gr, m, 4u, 56u, 136u);
   }
   __syncthreads();
-  for (int yy = wr; yy < ih; yy += 8)
-    for (int xx = ln; xx < bw; xx += 32) {
-      const uint8_t* p = &in[yy][xx];
-      hz[yy][xx] = (unsigned short)(4 * (p[1] + p[5]) + 56 * (p[2] + p[4]) + 136 * p[3]);
+  // INTER_LINEAR_EXACT down-sampling of the blurred window; bl(y, x) = byte 4 + x of row y.  A thread owns four adjacent
+  // output columns (their source offsets and weights are read once) and every eighth row of the tile
+  const int xq = (threadIdx.x & 31) * 4;
+  if (ox0 + xq >= O.sw) return;
+  int sx[4], sx1[4]; uint32_t cx1[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const int ox = min(ox0 + xq + e, O.sw - 1);
+    sx[e] = O.ex_ofs[ox] - bx0; cx1[e] = O.ex_c1[ox]; sx1[e] = min(sx[e] + 1, bw - 1);
+  }
+  uint8_t* dst = D.scaled + (size_t)blockIdx.z * D.sc_frame + O.sc_off;
+#pragma unroll
+  for (int k = 0; k < kST_H / 8; k++) {
+    const int oy = oy0 + (threadIdx.x >> 5) + 8 * k;
+    if (oy >= O.sh) break;
+    const int sy = O.ey_ofs[oy] - by0;
+    const uint32_t cy1 = O.ey_c1[oy];
+    const int sy1 = min(sy + 1, bh - 1);
+    const uint8_t* b0 = (const uint8_t*)s_bl[sy] + 4;
+    const uint8_t* b1 = (const uint8_t*)s_bl[sy1] + 4;
+    uint32_t out = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const uint32_t r0 = (256u - cx1[e]) * b0[sx[e]] + cx1[e] * b0[sx1[e]];
+      const uint32_t r1 = (256u - cx1[e]) * b1[sx[e]] + cx1[e] * b1[sx1[e]];
+      const uint32_t v = (256u - cy1) * (r0 & 0xFFFFu) + cy1 * (r1 & 0xFFFFu);
+      out |= min(255u, (v + (1u << 15)) >> 16) << (8 * e);
     }
-  __syncthreads();
-  for (int yy = wr; yy < bh; yy += 8)
-    for (int xx = ln; xx < bw; xx += 32) {
-      const uint32_t v = 4u * ((uint32_t)hz[yy + 1][xx] + hz[yy + 5][xx]) + 56u * ((uint32_t)hz[yy + 2][xx] + hz[yy + 4][xx]) +
-                         136u * (uint32_t)hz[yy + 3][xx];
-      bl[yy][xx] = (uint8_t)min(255u, (v + (1u << 15)) >> 16);
-    }
-  __syncthreads();
-  uint8_t* dst = D.scaled + (size_t)blockIdx.z * D.px_frame + O.px_off;
-  for (int i = threadIdx.x; i < kST_W * kST_H; i += 256) {
-    const int yy = i / kST_W, xx = i % kST_W;
-    const int ox = ox0 + xx, oy = oy0 + yy;
-    if (ox >= O.sw || oy >= O.sh) continue;
-    const int sx = O.ex_ofs[ox] - bx0, sy = O.ey_ofs[oy] - by0;
-    const uint32_t cx1 = O.ex_c1[ox], cy1 = O.ey_c1[oy];
-    const int sx1 = min(sx + 1, bw - 1), sy1 = min(sy + 1, bh - 1);
-    const uint32_t r0 = (256u - cx1) * bl[sy][sx] + cx1 * bl[sy][sx1];
-    const uint32_t r1 = (256u - cx1) * bl[sy1][sx] + cx1 * bl[sy1][sx1];
-    const uint32_t v = (256u - cy1) * (r0 & 0xFFFFu) + cy1 * (r1 & 0xFFFFu);
-    dst[(size_t)oy * O.sw + ox] = (uint8_t)min(255u, (v + (1u << 15)) >> 16);
+    *(uint32_t*)(dst + (size_t)oy * O.sc_stride + ox0 + xq) = out;
   }
 }
 
@@ -171,12 +252,12 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
   const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
   int g2 = 0;
   if (x < O.sw && y < O.sh) {
-    const uint8_t* img = D.scaled + (size_t)f * D.px_frame + O.px_off;
+    const uint8_t* img = D.scaled + (size_t)f * D.sc_frame + O.sc_off;
     const size_t q = (size_t)f * D.px_frame + O.px_off + (size_t)y * O.sw + x;
     lsd::PxA a; a.ang = lsd::kNotDef; a.c = 0.f; a.s = 0.f;
     if (x < O.sw - 1 && y < O.sh - 1) {
-      const uint8_t* r0 = img + (size_t)y * O.sw + x;
-      const uint8_t* r1 = r0 + O.sw;
+      const uint8_t* r0 = img + (size_t)y * O.sc_stride + x;
+      const uint8_t* r1 = r0 + O.sc_stride;
       const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
       const int gx = DA + BC, gy = DA - BC;
       g2 = gx * gx + gy * gy;
@@ -528,32 +609,76 @@ __global__ void __launch_bounds__(256) k_keylines(LineDev D, sdpl_keyline* __res
 // ------------------------------------------------------------------------------------------------
 // L8: LBD inputs (BinaryDescriptor::computeGaussianPyramid / computeSobel, binary_descriptor_custom.cpp:350-398):
 //     octave 0 = GaussianBlur 5x5 sigma 1 (Q8.8 [14,62,104,62,14]); octave k = pyrDown(prev, (w/2,h/2)); Sobel 3x3 -> s16.
+//     Octave 0 is ONE kernel: a CTA stages a (128+8) x (32+6) window of the frame in shared memory as aligned 32-bit words
+//     (the frame's rows are not word aligned -- 1242 is no multiple of 4 --, so every staged word is cut from two aligned global
+//     words with a funnel shift; rows and the three columns beyond an image edge are reflected while staging), runs the
+//     horizontal 5-tap pass as two dp4a per pixel on byte windows of (previous | own | next) word, the vertical pass on the
+//     16-bit row sums, keeps the blurred tile (+1 pixel all round) in shared memory, writes its interior once (source of octave 1)
+//     and takes the Sobel derivatives from it.  The blurred image mirrors about the image edges exactly as the frame does
+//     (symmetric kernel, reflect-101 on both), so Sobel's own reflect-101 border is what the halo already holds.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_lbd_blur5(LineDev D) {
-  __shared__ uint8_t in[16 + 4][64 + 4];
-  __shared__ unsigned short hz[16 + 4][64];
-  const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 16, f = blockIdx.z;
+constexpr int kLT_W = 128, kLT_H = 32;          // output tile
+constexpr int kLT_WW = kLT_W / 4 + 2;           // staged words per row: columns -4 .. kLT_W + 3
+constexpr int kLT_IR = kLT_H + 6;               // staged rows: -3 .. kLT_H + 2
+constexpr int kLT_GR = kLT_H + 2;               // blurred rows: -1 .. kLT_H
+__global__ void __launch_bounds__(256) k_lbd_blur_sobel(LineDev D) {
+  __shared__ uint32_t s_in[kLT_IR][kLT_WW];
+  __shared__ uint2 s_hz[kLT_IR][kLT_WW];
+  __shared__ uint32_t s_g[kLT_GR][kLT_WW];
+  const int x0 = blockIdx.x * kLT_W, y0 = blockIdx.y * kLT_H, f = blockIdx.z;
   const int W = D.in_w, H = D.in_h;
-  const uint8_t* src = D.in + (size_t)f * D.in_frame;
-  for (int i = threadIdx.x; i < 20 * 68; i += 256) {
-    const int yy = i / 68, xx = i - yy * 68;
-    in[yy][xx] = src[(size_t)reflect101(min(y0 - 2 + yy, H + 1), H) * D.in_stride + reflect101(min(x0 - 2 + xx, W + 1), W)];
+  const OctDev& O = D.O[0];
+  {
+    const uintptr_t lo = (uintptr_t)D.in & ~(uintptr_t)3;
+    const uintptr_t hi = ((uintptr_t)D.in + (size_t)(D.B - 1) * D.in_frame + (size_t)(H - 1) * D.in_stride + W + 3) & ~(uintptr_t)3;
+    stage_tile<kLT_WW>(s_in, kLT_IR, kLT_WW, D.in + (size_t)f * D.in_frame, D.in_stride, W, H, x0, y0 - 3, min(x0 + kLT_W + 2, W + 2), lo, hi);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 20 * 64; i += 256) {
-    const int yy = i >> 6, xx = i & 63;
-    const uint8_t* p = &in[yy][xx];
-    hz[yy][xx] = (unsigned short)(14 * (p[0] + p[4]) + 62 * (p[1] + p[3]) + 104 * p[2]);
+  hz5_tile<kLT_WW>(s_in, s_hz, kLT_IR, kLT_WW, 14u, 62u, 104u);       // word m = columns x0 + 4m - 4 ..
+  __syncthreads();
+  // vertical pass: blurred row gr = image row y0 - 1 + gr from staged rows gr .. gr + 4
+  {
+    uint8_t* gdst = D.g + (size_t)f * D.g_frame + O.g_off;
+    for (int i = threadIdx.x; i < kLT_GR * kLT_WW; i += 256) {
+      const int gr = i / kLT_WW, m = i - gr * kLT_WW;
+      const uint32_t g4 = vt5_word<kLT_WW>(s_hz, gr, m, 14u, 62u, 104u);
+      s_g[gr][m] = g4;
+      const int y = y0 - 1 + gr, x = x0 + 4 * (m - 1);
+      if (gr >= 1 && gr <= kLT_H && m >= 1 && m <= kLT_W / 4 && y < H && x < W) *(uint32_t*)(gdst + (size_t)y * O.gstride + x) = g4;
+    }
   }
   __syncthreads();
-  uint8_t* dst = D.g + (size_t)f * D.lbd_frame + D.O[0].lbd_off;
-  for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-    const int yy = i >> 6, xx = i & 63;
-    const int gx = x0 + xx, gy = y0 + yy;
-    if (gx >= W || gy >= H) continue;
-    const uint32_t v = 14u * ((uint32_t)hz[yy][xx] + hz[yy + 4][xx]) + 62u * ((uint32_t)hz[yy + 1][xx] + hz[yy + 3][xx]) +
-                       104u * (uint32_t)hz[yy + 2][xx];
-    dst[(size_t)gy * W + gx] = (uint8_t)min(255u, (v + (1u << 15)) >> 16);
+  // Sobel 3x3 on the blurred tile: dx(c) = A(c+1) - A(c-1), A = r0 + 2 r1 + r2;  dy(c) = B(c-1) + 2 B(c) + B(c+1), B = r2 - r0
+  {
+    short* dxo = D.sdx + (size_t)f * D.lbd_frame + O.lbd_off;
+    short* dyo = D.sdy + (size_t)f * D.lbd_frame + O.lbd_off;
+    for (int i = threadIdx.x; i < kLT_H * (kLT_W / 4); i += 256) {
+      const int r = i / (kLT_W / 4), m = 1 + (i - r * (kLT_W / 4));
+      const int y = y0 + r, x = x0 + 4 * (m - 1);
+      if (y >= H || x >= W) continue;
+      int A[6], Bv[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        // column x - 1 + k: byte 3 of word m-1, bytes 0..3 of word m, byte 0 of word m+1
+        const int wi = k == 0 ? m - 1 : (k == 5 ? m + 1 : m), bi = k == 0 ? 3 : (k == 5 ? 0 : k - 1);
+        const int t0 = (int)((s_g[r][wi] >> (8 * bi)) & 0xffu), t1 = (int)((s_g[r + 1][wi] >> (8 * bi)) & 0xffu),
+                  t2 = (int)((s_g[r + 2][wi] >> (8 * bi)) & 0xffu);
+        A[k] = t0 + 2 * t1 + t2; Bv[k] = t2 - t0;
+      }
+      short gx[4], gy[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) { gx[e] = (short)(A[e + 2] - A[e]); gy[e] = (short)(Bv[e] + 2 * Bv[e + 1] + Bv[e + 2]); }
+      const size_t q = (size_t)y * W + x;
+      if (x + 3 < W && ((q & 1) == 0)) {
+        *(uint32_t*)(dxo + q) = (uint32_t)(uint16_t)gx[0] | ((uint32_t)(uint16_t)gx[1] << 16);
+        *(uint32_t*)(dxo + q + 2) = (uint32_t)(uint16_t)gx[2] | ((uint32_t)(uint16_t)gx[3] << 16);
+        *(uint32_t*)(dyo + q) = (uint32_t)(uint16_t)gy[0] | ((uint32_t)(uint16_t)gy[1] << 16);
+        *(uint32_t*)(dyo + q + 2) = (uint32_t)(uint16_t)gy[2] | ((uint32_t)(uint16_t)gy[3] << 16);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (x + e < W) { dxo[q + e] = gx[e]; dyo[q + e] = gy[e]; }
+      }
+    }
   }
 }
 
@@ -562,19 +687,19 @@ __global__ void __launch_bounds__(256) k_lbd_pyrdown(LineDev D, int o) {
   const OctDev& Os = D.O[o - 1];
   const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6), f = blockIdx.z;
   if (x >= Od.lw || y >= Od.lh) return;
-  const uint8_t* src = D.g + (size_t)f * D.lbd_frame + Os.lbd_off;
-  const int sw = Os.lw, sh = Os.lh;
+  const uint8_t* src = D.g + (size_t)f * D.g_frame + Os.g_off;
+  const int sw = Os.lw, sh = Os.lh, sp = Os.gstride;
   int cx[5];
 #pragma unroll
   for (int k = 0; k < 5; k++) cx[k] = reflect101(2 * x + k - 2, sw);
   int rows[5];
 #pragma unroll
   for (int k = 0; k < 5; k++) {
-    const uint8_t* s = src + (size_t)reflect101(2 * y + k - 2, sh) * sw;
+    const uint8_t* s = src + (size_t)reflect101(2 * y + k - 2, sh) * sp;
     rows[k] = s[cx[0]] + s[cx[4]] + 4 * (s[cx[1]] + s[cx[3]]) + 6 * s[cx[2]];
   }
   const int v = rows[0] + rows[4] + 4 * (rows[1] + rows[3]) + 6 * rows[2];
-  D.g[(size_t)f * D.lbd_frame + Od.lbd_off + (size_t)y * Od.lw + x] = (uint8_t)((v + 128) >> 8);
+  D.g[(size_t)f * D.g_frame + Od.g_off + (size_t)y * Od.gstride + x] = (uint8_t)((v + 128) >> 8);
 }
 
 __global__ void __launch_bounds__(256) k_lbd_sobel(LineDev D, int o) {
@@ -582,10 +707,10 @@ __global__ void __launch_bounds__(256) k_lbd_sobel(LineDev D, int o) {
   const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6), f = blockIdx.z;
   if (x >= O.lw || y >= O.lh) return;
   const int w = O.lw, h = O.lh;
-  const uint8_t* src = D.g + (size_t)f * D.lbd_frame + O.lbd_off;
-  const uint8_t* r0 = src + (size_t)reflect101(y - 1, h) * w;
-  const uint8_t* r1 = src + (size_t)y * w;
-  const uint8_t* r2 = src + (size_t)reflect101(y + 1, h) * w;
+  const uint8_t* src = D.g + (size_t)f * D.g_frame + O.g_off;
+  const uint8_t* r0 = src + (size_t)reflect101(y - 1, h) * O.gstride;
+  const uint8_t* r1 = src + (size_t)y * O.gstride;
+  const uint8_t* r2 = src + (size_t)reflect101(y + 1, h) * O.gstride;
   const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
   const int gx = ((int)r0[xp] - r0[xm]) + 2 * ((int)r1[xp] - r1[xm]) + ((int)r2[xp] - r2[xm]);
   const int gy = ((int)r2[xm] + 2 * r2[x] + r2[xp]) - ((int)r0[xm] + 2 * r0[x] + r0[xp]);
@@ -789,7 +914,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   }
   std::vector<unsigned short> t_u16; std::vector<short> t_s16; std::vector<int> t_i32;
   std::vector<size_t> xofs_at(nl), yofs_at(nl), xa_at(nl), ya_at(nl), exo_at(nl), eyo_at(nl), exc_at(nl), eyc_at(nl);
-  size_t lvl_off = 0, px_off = 0, lbd_off = 0, hist_off = 0, reg_off = 0;
+  size_t lvl_off = 0, px_off = 0, lbd_off = 0, g_off = 0, sc_off = 0, hist_off = 0, reg_off = 0;
   int lw = w, lh = h;
   for (int l = 0; l < nl; l++) {
     OctDev& O = D.O[l];
@@ -804,7 +929,9 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
     if (lw < 1 || lh < 1 || lw > 32767 || lh > 32767) { set_last_error("LBD octave size out of range"); return SDPL_ERR_ARG; }
     O.lvl_off = lvl_off; if (l > 0) lvl_off += align_up((size_t)O.w * O.h, 16);
     O.px_off = px_off; px_off += align_up((size_t)O.npx, 16);
+    O.sc_stride = (int)align_up((size_t)O.sw, 16); O.sc_off = sc_off; sc_off += (size_t)O.sc_stride * O.sh;
     O.lbd_off = lbd_off; lbd_off += align_up((size_t)lw * lh, 16);
+    O.gstride = (int)align_up((size_t)lw, 16); O.g_off = g_off; g_off += (size_t)O.gstride * lh;
     O.nchunks = div_up(O.npx, kSortChunk);
     O.hist_off = hist_off; hist_off += (size_t)O.nchunks * kBins;
     O.lane_cap = 4096;                                   // per-lane list ring, power of two >= npx/32
@@ -859,7 +986,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
       if (std::min(cy[y1].ofs + 1, O.h - 1) - cy[y0].ofs + 1 + 6 > kSS_H) { set_last_error("unsupported LSD scale (tile span)"); return SDPL_ERR_UNSUPPORTED; }
     }
   }
-  D.lvl_frame = align_up(std::max<size_t>(lvl_off, 16), 256); D.px_frame = align_up(px_off, 256); D.lbd_frame = align_up(lbd_off, 256);
+  D.lvl_frame = align_up(std::max<size_t>(lvl_off, 16), 256); D.px_frame = align_up(px_off, 256); D.lbd_frame = align_up(lbd_off, 256); D.g_frame = align_up(g_off, 256); D.sc_frame = align_up(sc_off, 256);
   D.hist_frame = hist_off; D.reg_frame = reg_off;
   // rectangles per (frame, octave): scales with the working image (1242x375 -> 6400; an overflow is reported, never silent)
   o->pend_cap = std::max(4096, (int)align_up((size_t)D.O[0].npx / 48, 256));
@@ -867,7 +994,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   D.in_w = w; D.in_h = h;
   int rc;
   if ((rc = o->lvl.reserve(D.lvl_frame * B))) return rc;
-  if ((rc = o->scaled.reserve(D.px_frame * B))) return rc;
+  if ((rc = o->scaled.reserve(D.sc_frame * B))) return rc;
   if ((rc = o->px.reserve(sizeof(lsd::PxA) * D.px_frame * B))) return rc;
   if ((rc = o->ang.reserve(sizeof(double) * D.px_frame * B))) return rc;
   if ((rc = o->g2.reserve(sizeof(int) * D.px_frame * B))) return rc;
@@ -880,7 +1007,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->reg.reserve(sizeof(int) * D.reg_frame * B))) return rc;
   if ((rc = o->pend.reserve(sizeof(lsd::Pending) * (size_t)D.pend_cap * nl * B))) return rc;
   if ((rc = o->npend.reserve(sizeof(int) * nl * B))) return rc;
-  if ((rc = o->g.reserve(D.lbd_frame * B))) return rc;
+  if ((rc = o->g.reserve(D.g_frame * B))) return rc;
   if ((rc = o->sdx.reserve(sizeof(short) * D.lbd_frame * B))) return rc;
   if ((rc = o->sdy.reserve(sizeof(short) * D.lbd_frame * B))) return rc;
   if ((rc = o->tmpkl.reserve(sizeof(sdpl_keyline) * (size_t)D.pend_cap * nl * (o->nfeatures ? B : 1)))) return rc;
@@ -1046,13 +1173,13 @@ static int line_lbd_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, int h
   D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride;
   cudaStream_t st = o->stream;
   const int nl = o->nlevels;
-  k_lbd_blur5<<<dim3(div_up(w, 64), div_up(h, 16), B), 256, 0, st>>>(D);
+  k_lbd_blur_sobel<<<dim3(div_up(w, kLT_W), div_up(h, kLT_H), B), 256, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   for (int l = 1; l < nl; l++) {
     k_lbd_pyrdown<<<dim3(div_up(D.O[l].lw, 64), div_up(D.O[l].lh, 4), B), 256, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
-  for (int l = 0; l < nl; l++) {
+  for (int l = 1; l < nl; l++) {
     k_lbd_sobel<<<dim3(div_up(D.O[l].lw, 64), div_up(D.O[l].lh, 4), B), 256, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
