@@ -121,27 +121,55 @@ class Lineextractor {
 }  // namespace SDPL_SLAM
 
 namespace sdpl {
-// Brute-force 256-bit Hamming search with the match / knnMatch surface of BinaryDescriptorMatcher.
+// Brute-force 256-bit Hamming search with the surface of cv::line_descriptor::BinaryDescriptorMatcher
+// (descriptor_custom.hpp:1015-1126): match / knnMatch against an explicit train matrix or against the set kept by add() / train()
+// (resident on the device; trainIdx = row of the concatenated set, imgIdx = image, binary_descriptor_matcher.cpp:381-401).
 class HammingMatcher {
  public:
   explicit HammingMatcher(int device = 0) { check(sdpl_matcher_create(&h_, device)); }
   ~HammingMatcher() { sdpl_matcher_destroy(h_); }
+  HammingMatcher(const HammingMatcher&) = delete;
+  HammingMatcher& operator=(const HammingMatcher&) = delete;
+  void add(const std::vector<cv::Mat>& descriptors) {
+    for (size_t i = 0; i < descriptors.size(); i++) { check_desc(descriptors[i]); check(sdpl_matcher_add(h_, descriptors[i].data, descriptors[i].rows)); }
+  }
+  void train() { check(sdpl_matcher_train(h_)); }
+  void clear() { check(sdpl_matcher_clear(h_)); }
   void match(const cv::Mat& query, const cv::Mat& train, std::vector<cv::DMatch>& matches) {
-    std::vector<cv::DMatch> second;
-    knn2(query, train, matches, second);
+    std::vector<std::vector<cv::DMatch> > knn;
+    knnMatch(query, train, knn, 1);
+    matches.clear();
+    for (size_t i = 0; i < knn.size(); i++) if (!knn[i].empty()) matches.push_back(knn[i][0]);
+  }
+  void match(const cv::Mat& query, std::vector<cv::DMatch>& matches) {
+    std::vector<std::vector<cv::DMatch> > knn;
+    knnMatch(query, knn, 1);
+    matches.clear();
+    for (size_t i = 0; i < knn.size(); i++) if (!knn[i].empty()) matches.push_back(knn[i][0]);
   }
   void knnMatch(const cv::Mat& query, const cv::Mat& train, std::vector<std::vector<cv::DMatch> >& matches, int k = 2) {
-    CV_Assert(k == 2);
-    std::vector<cv::DMatch> b, s;
-    knn2(query, train, b, s);
-    matches.resize(b.size());
-    for (size_t i = 0; i < b.size(); i++) { matches[i].clear(); matches[i].push_back(b[i]); if (s[i].trainIdx >= 0) matches[i].push_back(s[i]); }
+    check_desc(query);
+    if (!train.empty()) check_desc(train);
+    CV_Assert(k >= 1);
+    std::vector<cv::DMatch> flat((size_t)query.rows * k);
+    check(sdpl_match_knn(h_, query.data, query.rows, train.data, train.rows, k, reinterpret_cast<sdpl_dmatch*>(flat.data())));
+    unflatten(flat, query.rows, k, matches);
+  }
+  void knnMatch(const cv::Mat& query, std::vector<std::vector<cv::DMatch> >& matches, int k = 2) {
+    check_desc(query);
+    CV_Assert(k >= 1);
+    std::vector<cv::DMatch> flat((size_t)query.rows * k);
+    check(sdpl_matcher_knn(h_, query.data, query.rows, k, reinterpret_cast<sdpl_dmatch*>(flat.data())));
+    unflatten(flat, query.rows, k, matches);
   }
  private:
-  void knn2(const cv::Mat& q, const cv::Mat& t, std::vector<cv::DMatch>& b, std::vector<cv::DMatch>& s) {
-    CV_Assert(q.type() == CV_8U && q.cols == 32 && q.isContinuous() && (t.empty() || (t.type() == CV_8U && t.cols == 32 && t.isContinuous())));
-    b.resize(q.rows); s.resize(q.rows);
-    check(sdpl_match_knn2(h_, q.data, q.rows, t.data, t.rows, reinterpret_cast<sdpl_dmatch*>(b.data()), reinterpret_cast<sdpl_dmatch*>(s.data())));
+  static void check_desc(const cv::Mat& d) { CV_Assert(d.type() == CV_8U && d.cols == 32 && d.isContinuous()); }
+  static void unflatten(const std::vector<cv::DMatch>& flat, int nq, int k, std::vector<std::vector<cv::DMatch> >& matches) {
+    matches.resize(nq);
+    for (int i = 0; i < nq; i++) {
+      matches[i].clear();
+      for (int j = 0; j < k; j++) if (flat[(size_t)i * k + j].trainIdx >= 0) matches[i].push_back(flat[(size_t)i * k + j]);
+    }
   }
   sdpl_matcher* h_ = nullptr;
 };

@@ -138,6 +138,26 @@ int sdpl_match_ratio(sdpl_matcher* h, const uint8_t* q, int nq, const uint8_t* t
 /* radius search: counts[i] = #train within radius; out[i*k ..] = k nearest within radius (ascending distance, index) */
 int sdpl_match_radius(sdpl_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt, int radius, int k,
                       int* counts, sdpl_dmatch* out);
+/* general k against an explicit train set: out[i*k + j] = j-th nearest train row of query i, ascending (distance, train index);
+ * missing neighbours (nt < k) have train = -1, distance = 257.  BinaryDescriptorMatcher::knnMatch(query, train, matches, k),
+ * binary_descriptor_matcher.cpp:258-335 */
+int sdpl_match_knn(sdpl_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt, int k, sdpl_dmatch* out);
+/* The train set kept by the matcher -- BinaryDescriptorMatcher::add / train / clear (descriptor_custom.hpp:1015-1126,
+ * binary_descriptor_matcher.cpp:127-194): every add() appends one image's descriptors (HOST pointer; _dev: DEVICE pointer) to a
+ * set resident on the device; train() is where the reference builds its hash tables (nothing to do for brute force);
+ * queries against the stored set return trainIdx = row in the concatenation of all added images and imgIdx = the image it came
+ * from, exactly as the reference composes its DMatch (binary_descriptor_matcher.cpp:161-175, 381-401). */
+int sdpl_matcher_add(sdpl_matcher* h, const uint8_t* desc, int n);
+int sdpl_matcher_add_dev(sdpl_matcher* h, const uint8_t* d_desc, int n);
+int sdpl_matcher_train(sdpl_matcher* h);
+int sdpl_matcher_clear(sdpl_matcher* h);
+int sdpl_matcher_train_size(const sdpl_matcher* h, int* n_desc, int* n_imgs);
+/* match / knnMatch(query, matches, k) against the stored set (binary_descriptor_matcher.cpp:127-194, 339-425): out[i*k + j] */
+int sdpl_matcher_knn(sdpl_matcher* h, const uint8_t* q, int nq, int k, sdpl_dmatch* out);
+/* radiusMatch(query, matches, maxDistance) against the stored set (binary_descriptor_matcher.cpp:507-590): as sdpl_match_radius */
+int sdpl_matcher_radius(sdpl_matcher* h, const uint8_t* q, int nq, int radius, int k, int* counts, sdpl_dmatch* out);
+/* DEVICE pointer and row count of the stored set, for the batched device entry points (t_stride = 0: one set for all problems) */
+int sdpl_matcher_train_dev(const sdpl_matcher* h, const uint8_t** d_train, int* n_desc);
 /* Batched DEVICE variant: npairs problems; problem p matches d_q + p*q_stride (nq[p] rows) against
  * d_t + p*t_stride (nt[p] rows); d_nq/d_nt are DEVICE int arrays; outputs [p*max_q + i]. */
 int sdpl_match_knn2_batch_dev(sdpl_matcher* h, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t,

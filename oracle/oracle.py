@@ -273,6 +273,20 @@ def match_ratio(q, t, ratio=0.8, max_dist=100):
     return out, n
 
 
+def match_stored_knn(q, train_sets, k):
+    """BinaryDescriptorMatcher::add(train_sets) / train() / knnMatch(query, matches, k) on the stored set
+    (binary_descriptor_matcher.cpp:127-194, 339-425): the k nearest rows of the CONCATENATION of all added images; trainIdx is
+    the row of the concatenation (`results[j] - 1`, :393), imgIdx the image that row came from (`indexesMap.upper_bound(idx) - 1`,
+    :381-383).  Returns an (nq, k) DMatch array; missing neighbours have train = -1."""
+    sets = [np.ascontiguousarray(t, np.uint8).reshape(-1, 32) for t in train_sets]
+    allt = np.concatenate(sets) if sets else np.zeros((0, 32), np.uint8)
+    starts = np.cumsum([0] + [len(t) for t in sets])[:-1]
+    _, out = match_radius(q, allt, 256, k)
+    ok = out["train"] >= 0
+    out["img"][ok] = np.searchsorted(starts, out["train"][ok], side="right") - 1
+    return out
+
+
 def match_radius(q, t, radius, k):
     q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
     counts = np.zeros(q.shape[0], np.int32); out = np.zeros((q.shape[0], k), DM_DTYPE)

@@ -48,6 +48,7 @@ def lib():
     L.ref_hamming256.argtypes = [vp, vp]
     L.ref_matcher_knn.argtypes = [vp, ci, vp, ci, ci, vp, vp, vp]
     L.ref_matcher_match.argtypes = [vp, ci, vp, ci, vp, vp]
+    L.ref_matcher_stored_knn.argtypes = [vp, ci, vp, ci, vp, ci, ci, vp, vp, vp]
     _lib = L
     return L
 
@@ -154,6 +155,15 @@ def matcher_knn(q, t, k):
     lib().ref_matcher_knn(q.ctypes.data, len(q), t.ctypes.data, len(t), k, train.ctypes.data, dist.ctypes.data,
                           counts.ctypes.data)
     return train, dist, counts
+
+
+def matcher_stored_knn(q, t1, t2, k):
+    """add([t1, t2]); train(); knnMatch(query, matches, k) on the stored set: (trainIdx[nq,k], imgIdx[nq,k], distance[nq,k])."""
+    q, t1, t2 = (np.ascontiguousarray(a, np.uint8) for a in (q, t1, t2))
+    train, img, dist = np.zeros((len(q), k), np.int32), np.zeros((len(q), k), np.int32), np.zeros((len(q), k), np.float32)
+    lib().ref_matcher_stored_knn(q.ctypes.data, len(q), t1.ctypes.data, len(t1), t2.ctypes.data, len(t2), k, train.ctypes.data,
+                                 img.ctypes.data, dist.ctypes.data)
+    return train, img, dist
 
 
 def matcher_match(q, t):

@@ -37,6 +37,19 @@ int main(int argc, char** argv) {
     sdpl::HammingMatcher matcher;
     std::vector<std::vector<cv::DMatch> > knn;
     matcher.knnMatch(mDescriptors, mDescriptors2, knn, 2);
+    {
+      // the stored (device-resident) train set and a general k must agree with the explicit-train call
+      std::vector<cv::Mat> set; set.push_back(mDescriptors2);
+      matcher.add(set); matcher.train();
+      std::vector<std::vector<cv::DMatch> > knn3;
+      matcher.knnMatch(mDescriptors, knn3, 3);
+      if (knn3.size() != knn.size()) return 4;
+      for (size_t i = 0; i < knn.size(); i++)
+        for (size_t j = 0; j < knn[i].size(); j++)
+          if (knn3[i].size() < knn[i].size() || knn3[i][j].trainIdx != knn[i][j].trainIdx || knn3[i][j].distance != knn[i][j].distance ||
+              knn3[i][j].imgIdx != 0) return 4;
+      matcher.clear();
+    }
     int32_t head[3] = {(int32_t)mvKeys.size(), (int32_t)mvKeys_Line.size(), (int32_t)knn.size()};
     FILE* f = fopen(argv[5], "wb");
     fwrite(head, 4, 3, f);

@@ -139,4 +139,23 @@ void ref_matcher_match(const uint8_t* q, int nq, const uint8_t* t, int nt, int32
   for (int i = 0; i < nq; i++) { train[i] = -1; dist[i] = -1.f; }
   for (size_t i = 0; i < out.size(); i++) { train[out[i].queryIdx] = out[i].trainIdx; dist[out[i].queryIdx] = out[i].distance; }
 }
+/* add({T1, T2}) / train() / knnMatch(query, matches, k) on the stored set (binary_descriptor_matcher.cpp:127-194, 339-425): what
+   the reference puts into trainIdx / imgIdx for a data set of two images */
+void ref_matcher_stored_knn(const uint8_t* q, int nq, const uint8_t* t1, int n1, const uint8_t* t2, int n2, int k, int32_t* train,
+                            int32_t* img, float* dist) {
+  cv::Mat Q(nq, 32, CV_8UC1, (void*)q), T1(n1, 32, CV_8UC1, (void*)t1), T2(n2, 32, CV_8UC1, (void*)t2);
+  cv::Ptr<cv::line_descriptor::BinaryDescriptorMatcher> m = cv::line_descriptor::BinaryDescriptorMatcher::createBinaryDescriptorMatcher();
+  std::vector<cv::Mat> set; set.push_back(T1); set.push_back(T2);
+  m->add(set);
+  m->train();
+  std::vector<std::vector<cv::DMatch> > out;
+  m->knnMatch(Q, out, k);
+  for (int i = 0; i < nq; i++)
+    for (int j = 0; j < k; j++) {
+      const bool have = i < (int)out.size() && j < (int)out[i].size();
+      train[(size_t)i * k + j] = have ? out[i][j].trainIdx : -1;
+      img[(size_t)i * k + j] = have ? out[i][j].imgIdx : -1;
+      dist[(size_t)i * k + j] = have ? out[i][j].distance : -1.f;
+    }
+}
 }  // extern "C"

@@ -267,43 +267,39 @@ int sdpl_frontend_collect(sdpl_frontend* f, sdpl_keypoint* kps, uint8_t* desc, s
   int* herr = hn + S.herr_off;          // taken (copied and cleared) in stream order right after this batch's extraction
   cudaStream_t so = f->s_out;
   int status = SDPL_OK;
-  // counts size the row copies: fetch them as soon as their stage is done, then only the valid rows of every frame
+  // counts size the copies: fetch them as soon as their stage is done, then ONE strided copy per output array -- for every frame
+  // its first max-count rows (cudaMemcpy2DAsync: pitch = the frame's capacity-sized block, width = the longest frame's rows), so a
+  // batch costs nine copies whatever its size
+  auto rows2d = [&](void* dst, const void* src, size_t row_bytes, int cap, int maxc) -> cudaError_t {
+    if (maxc <= 0) return cudaSuccess;
+    return cudaMemcpy2DAsync(dst, row_bytes * cap, src, row_bytes * cap, row_bytes * maxc, n, cudaMemcpyDeviceToHost, so);
+  };
   SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_orb, 0));
   SDPL_CUDA(cudaMemcpyAsync(hn, dn, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
   SDPL_CUDA(cudaStreamSynchronize(so));
+  int kmax = 0;
   for (int i = 0; i < n; i++) {
-    int c = hn[i];
-    if (c > KC) { c = KC; status = SDPL_ERR_CAPACITY; }
-    if (c > 0) {
-      SDPL_CUDA(cudaMemcpyAsync(kps + (size_t)i * KC, dk + (size_t)i * KC, sizeof(sdpl_keypoint) * c, cudaMemcpyDeviceToHost, so));
-      SDPL_CUDA(cudaMemcpyAsync(desc + (size_t)i * KC * 32, dd + (size_t)i * KC * 32, (size_t)32 * c, cudaMemcpyDeviceToHost, so));
-    }
+    if (hn[i] > KC) status = SDPL_ERR_CAPACITY;
+    kmax = std::max(kmax, std::min(hn[i], KC));
   }
+  SDPL_CUDA(rows2d(kps, dk, sizeof(sdpl_keypoint), KC, kmax));
+  SDPL_CUDA(rows2d(desc, dd, 32, KC, kmax));
   SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_pm, 0));
   SDPL_CUDA(cudaMemcpyAsync(hn + 2 * n, S.pacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
-  for (int i = 0; i < n; i++) {
-    const int c = std::min(hn[i], KC);
-    if (c > 0) SDPL_CUDA(cudaMemcpyAsync(pt_matches + (size_t)i * KC, S.pout.as<sdpl_dmatch>() + (size_t)i * KC, sizeof(sdpl_dmatch) * c,
-                                         cudaMemcpyDeviceToHost, so));
-  }
+  SDPL_CUDA(rows2d(pt_matches, S.pout.p, sizeof(sdpl_dmatch), KC, kmax));
   SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_line, 0));
   SDPL_CUDA(cudaMemcpyAsync(hn + n, dln, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
   SDPL_CUDA(cudaStreamSynchronize(so));
+  int lmax = 0;
   for (int i = 0; i < n; i++) {
-    int c = hn[n + i];
-    if (c > LC) { c = LC; status = SDPL_ERR_CAPACITY; }
-    if (c > 0) {
-      SDPL_CUDA(cudaMemcpyAsync(kls + (size_t)i * LC, dl + (size_t)i * LC, sizeof(sdpl_keyline) * c, cudaMemcpyDeviceToHost, so));
-      SDPL_CUDA(cudaMemcpyAsync(ldesc + (size_t)i * LC * 32, dld + (size_t)i * LC * 32, (size_t)32 * c, cudaMemcpyDeviceToHost, so));
-    }
+    if (hn[n + i] > LC) status = SDPL_ERR_CAPACITY;
+    lmax = std::max(lmax, std::min(hn[n + i], LC));
   }
+  SDPL_CUDA(rows2d(kls, dl, sizeof(sdpl_keyline), LC, lmax));
+  SDPL_CUDA(rows2d(ldesc, dld, 32, LC, lmax));
   SDPL_CUDA(cudaStreamWaitEvent(so, S.ev_lm, 0));
   SDPL_CUDA(cudaMemcpyAsync(hn + 3 * n, S.lacc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
-  for (int i = 0; i < n; i++) {
-    const int c = std::min(hn[n + i], LC);
-    if (c > 0) SDPL_CUDA(cudaMemcpyAsync(ln_matches + (size_t)i * LC, S.lout.as<sdpl_dmatch>() + (size_t)i * LC, sizeof(sdpl_dmatch) * c,
-                                         cudaMemcpyDeviceToHost, so));
-  }
+  SDPL_CUDA(rows2d(ln_matches, S.lout.p, sizeof(sdpl_dmatch), LC, lmax));
   SDPL_CUDA(cudaStreamSynchronize(so));
   S.busy = false;
   f->head ^= 1; f->count--;

@@ -213,6 +213,11 @@ struct sdpl_matcher {
   int device;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   DevBuf q, t, best, second, out, partial, scal, counts;
+  // train set kept on the device (BinaryDescriptorMatcher::add / train / clear): the concatenation of every added image's
+  // descriptors; img_start[i] = first row of image i (the reference's indexesMap, binary_descriptor_matcher.cpp:127-160)
+  DevBuf train;
+  int train_n = 0;
+  std::vector<int> img_start;
   int launches = 0;
   int sm_count = 148;
   StageTimer timer;
@@ -260,7 +265,7 @@ void sdpl_matcher_destroy(sdpl_matcher* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
-  for (DevBuf* b : {&m->q, &m->t, &m->best, &m->second, &m->out, &m->partial, &m->scal, &m->counts}) b->release();
+  for (DevBuf* b : {&m->q, &m->t, &m->best, &m->second, &m->out, &m->partial, &m->scal, &m->counts, &m->train}) b->release();
   m->timer.release();
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   delete m;
@@ -377,6 +382,141 @@ int sdpl_match_radius(sdpl_matcher* m, const uint8_t* q, int nq, const uint8_t* 
   SDPL_CUDA(cudaMemcpyAsync(counts, m->counts.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
   if (k > 0) SDPL_CUDA(cudaMemcpyAsync(out, m->out.p, sizeof(sdpl_dmatch) * (size_t)nq * k, cudaMemcpyDeviceToHost, m->stream));
   SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  return SDPL_OK;
+}
+
+// ---- general k, explicit train set: k <= 2 on the top-2 kernels, larger k by k rounds of arg-min selection (k_match_radius with
+//      the radius wide open).  out[i*k + j] = j-th nearest of query i, ascending (distance, train index); missing: train = -1 ----
+static int match_knn_dev_train(sdpl_matcher* m, const uint8_t* q, int nq, const uint8_t* d_t, int nt, int k, sdpl_dmatch* out) {
+  int rc;
+  if ((rc = m->q.reserve((size_t)nq * 32))) return rc;
+  if ((rc = m->out.reserve(sizeof(sdpl_dmatch) * (size_t)nq * std::max(k, 2)))) return rc;
+  SDPL_CUDA(cudaMemcpyAsync(m->q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+  if (k <= 2) {
+    if ((rc = m->best.reserve(sizeof(sdpl_dmatch) * nq))) return rc;
+    if ((rc = m->second.reserve(sizeof(sdpl_dmatch) * nq))) return rc;
+    if ((rc = m->scal.reserve(sizeof(int) * 4))) return rc;
+    int scal[4] = {nq, nt, 0, 0};
+    SDPL_CUDA(cudaMemcpyAsync(m->scal.p, scal, sizeof(scal), cudaMemcpyHostToDevice, m->stream));
+    // dummy non-null train pointer for an empty set (never dereferenced: nt == 0)
+    if ((rc = match_run_dev(m, m->q.as<uint8_t>(), m->scal.as<int>(), 0, d_t ? d_t : m->q.as<uint8_t>(), m->scal.as<int>() + 1, 0, 1, nq,
+                            std::max(nt, 1), m->best.as<sdpl_dmatch>(), m->second.as<sdpl_dmatch>()))) return rc;
+    std::vector<sdpl_dmatch> b(nq), c(k == 2 ? nq : 0);
+    SDPL_CUDA(cudaMemcpyAsync(b.data(), m->best.p, sizeof(sdpl_dmatch) * nq, cudaMemcpyDeviceToHost, m->stream));
+    if (k == 2) SDPL_CUDA(cudaMemcpyAsync(c.data(), m->second.p, sizeof(sdpl_dmatch) * nq, cudaMemcpyDeviceToHost, m->stream));
+    SDPL_CUDA(cudaStreamSynchronize(m->stream));
+    for (int i = 0; i < nq; i++) { out[(size_t)i * k] = b[i]; if (k == 2) out[(size_t)i * k + 1] = c[i]; }
+    return SDPL_OK;
+  }
+  if ((rc = m->counts.reserve(sizeof(int) * nq))) return rc;
+  k_match_radius<<<div_up(nq, 8), 256, 0, m->stream>>>(m->q.as<uint8_t>(), nq, d_t, nt, 256, k, m->counts.as<int>(), m->out.as<sdpl_dmatch>());
+  SDPL_LAUNCH_CHECK();
+  SDPL_CUDA(cudaMemcpyAsync(out, m->out.p, sizeof(sdpl_dmatch) * (size_t)nq * k, cudaMemcpyDeviceToHost, m->stream));
+  SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  return SDPL_OK;
+}
+
+int sdpl_match_knn(sdpl_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int k, sdpl_dmatch* out) {
+  if (!m || nq < 0 || nt < 0 || k < 1) { set_last_error("sdpl_match_knn: bad argument"); return SDPL_ERR_ARG; }
+  if (nq == 0) return SDPL_OK;
+  if (!q || (nt > 0 && !t) || !out) { set_last_error("sdpl_match_knn: null pointer"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = m->t.reserve((size_t)std::max(nt, 1) * 32))) return rc;
+  if (nt > 0) SDPL_CUDA(cudaMemcpyAsync(m->t.p, t, (size_t)nt * 32, cudaMemcpyHostToDevice, m->stream));
+  g_launches = 0;
+  rc = match_knn_dev_train(m, q, nq, m->t.as<uint8_t>(), nt, k, out);
+  m->launches = g_launches;
+  return rc;
+}
+
+// ---- the stored train set ----
+static int matcher_append(sdpl_matcher* m, const uint8_t* desc, int n, cudaMemcpyKind kind) {
+  SDPL_CUDA(cudaSetDevice(m->device));
+  const size_t need = (size_t)(m->train_n + n) * 32;
+  if (need > m->train.bytes) {
+    // grow geometrically; the rows already stored move device to device
+    DevBuf bigger;
+    int rc = bigger.reserve(std::max(need, std::max<size_t>(2 * m->train.bytes, (size_t)4096 * 32)));
+    if (rc) return rc;
+    if (m->train_n) SDPL_CUDA(cudaMemcpyAsync(bigger.p, m->train.p, (size_t)m->train_n * 32, cudaMemcpyDeviceToDevice, m->stream));
+    SDPL_CUDA(cudaStreamSynchronize(m->stream));
+    m->train.release();
+    m->train = bigger;
+  }
+  if (n > 0) SDPL_CUDA(cudaMemcpyAsync((uint8_t*)m->train.p + (size_t)m->train_n * 32, desc, (size_t)n * 32, kind, m->stream));
+  SDPL_CUDA(cudaStreamSynchronize(m->stream));       // the caller may free `desc` on return
+  m->img_start.push_back(m->train_n);
+  m->train_n += n;
+  return SDPL_OK;
+}
+int sdpl_matcher_add(sdpl_matcher* m, const uint8_t* desc, int n) {
+  if (!m || n < 0 || (n > 0 && !desc)) { set_last_error("sdpl_matcher_add: bad argument"); return SDPL_ERR_ARG; }
+  return matcher_append(m, desc, n, cudaMemcpyHostToDevice);
+}
+int sdpl_matcher_add_dev(sdpl_matcher* m, const uint8_t* d_desc, int n) {
+  if (!m || n < 0 || (n > 0 && !d_desc)) { set_last_error("sdpl_matcher_add_dev: bad argument"); return SDPL_ERR_ARG; }
+  return matcher_append(m, d_desc, n, cudaMemcpyDeviceToDevice);
+}
+int sdpl_matcher_train(sdpl_matcher* m) { return m ? SDPL_OK : SDPL_ERR_ARG; }   // brute force: nothing to index
+int sdpl_matcher_clear(sdpl_matcher* m) {
+  if (!m) return SDPL_ERR_ARG;
+  m->train_n = 0; m->img_start.clear();
+  return SDPL_OK;
+}
+int sdpl_matcher_train_size(const sdpl_matcher* m, int* n_desc, int* n_imgs) {
+  if (!m) return SDPL_ERR_ARG;
+  if (n_desc) *n_desc = m->train_n;
+  if (n_imgs) *n_imgs = (int)m->img_start.size();
+  return SDPL_OK;
+}
+// imgIdx of a row of the concatenated set: the image whose first row is the last one <= train (the reference's
+// indexesMap.upper_bound(idx) - 1, binary_descriptor_matcher.cpp:161-163); trainIdx stays the row of the concatenation, as there
+static void matcher_set_img(const sdpl_matcher* m, sdpl_dmatch* out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    if (out[i].train < 0) continue;
+    const auto it = std::upper_bound(m->img_start.begin(), m->img_start.end(), out[i].train);
+    out[i].img = (int)(it - m->img_start.begin()) - 1;
+  }
+}
+int sdpl_matcher_knn(sdpl_matcher* m, const uint8_t* q, int nq, int k, sdpl_dmatch* out) {
+  if (!m || nq < 0 || k < 1) { set_last_error("sdpl_matcher_knn: bad argument"); return SDPL_ERR_ARG; }
+  if (nq == 0) return SDPL_OK;
+  if (!q || !out) { set_last_error("sdpl_matcher_knn: null pointer"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  g_launches = 0;
+  int rc = match_knn_dev_train(m, q, nq, m->train.as<uint8_t>(), m->train_n, k, out);
+  m->launches = g_launches;
+  if (rc) return rc;
+  matcher_set_img(m, out, (size_t)nq * k);
+  return SDPL_OK;
+}
+int sdpl_matcher_radius(sdpl_matcher* m, const uint8_t* q, int nq, int radius, int k, int* counts, sdpl_dmatch* out) {
+  if (!m || nq < 0 || k < 0 || radius < 0) { set_last_error("sdpl_matcher_radius: bad argument"); return SDPL_ERR_ARG; }
+  if (nq == 0) return SDPL_OK;
+  if (!q || !counts || (k > 0 && !out)) { set_last_error("sdpl_matcher_radius: null pointer"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(m->device));
+  int rc;
+  if ((rc = m->q.reserve((size_t)nq * 32))) return rc;
+  if ((rc = m->counts.reserve(sizeof(int) * nq))) return rc;
+  if ((rc = m->out.reserve(sizeof(sdpl_dmatch) * (size_t)nq * std::max(k, 1)))) return rc;
+  SDPL_CUDA(cudaMemcpyAsync(m->q.p, q, (size_t)nq * 32, cudaMemcpyHostToDevice, m->stream));
+  g_launches = 0;
+  k_match_radius<<<div_up(nq, 8), 256, 0, m->stream>>>(m->q.as<uint8_t>(), nq, m->train.as<uint8_t>(), m->train_n, radius, k, m->counts.as<int>(),
+                                                       m->out.as<sdpl_dmatch>());
+  SDPL_LAUNCH_CHECK();
+  m->launches = g_launches;
+  SDPL_CUDA(cudaMemcpyAsync(counts, m->counts.p, sizeof(int) * nq, cudaMemcpyDeviceToHost, m->stream));
+  if (k > 0) SDPL_CUDA(cudaMemcpyAsync(out, m->out.p, sizeof(sdpl_dmatch) * (size_t)nq * k, cudaMemcpyDeviceToHost, m->stream));
+  SDPL_CUDA(cudaStreamSynchronize(m->stream));
+  if (k > 0) matcher_set_img(m, out, (size_t)nq * k);
+  return SDPL_OK;
+}
+// the stored set for the batched device entry points (sdpl_match_knn2_batch_dev with t_stride = 0): DEVICE pointer + row count
+int sdpl_matcher_train_dev(const sdpl_matcher* m, const uint8_t** d_train, int* n_desc) {
+  if (!m || !d_train) return SDPL_ERR_ARG;
+  *d_train = m->train.as<uint8_t>();
+  if (n_desc) *n_desc = m->train_n;
   return SDPL_OK;
 }
 

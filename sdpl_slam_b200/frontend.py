@@ -93,6 +93,13 @@ def load_library(path=None):
     L.sdpl_match_knn2_batch_dev.argtypes = [vp, vp, vp, sz, vp, vp, sz, i, i, i, vp, vp, i]
     L.sdpl_match_ratio_batch_dev.argtypes = [vp, vp, vp, vp, i, i, f, i, vp, vp, i]
     L.sdpl_matcher_last_launches.argtypes = [vp]
+    L.sdpl_match_knn.argtypes = [vp, vp, i, vp, i, i, vp]
+    L.sdpl_matcher_add.argtypes = [vp, vp, i]; L.sdpl_matcher_add_dev.argtypes = [vp, vp, i]
+    L.sdpl_matcher_train.argtypes = [vp]; L.sdpl_matcher_clear.argtypes = [vp]
+    L.sdpl_matcher_train_size.argtypes = [vp, ip, ip]
+    L.sdpl_matcher_knn.argtypes = [vp, vp, i, i, vp]
+    L.sdpl_matcher_radius.argtypes = [vp, vp, i, i, i, vp, vp]
+    L.sdpl_matcher_train_dev.argtypes = [vp, C.POINTER(vp), ip]
     L.sdpl_matcher_set_stream.argtypes = [vp, vp]
     L.sdpl_orb_check.argtypes = [vp]; L.sdpl_line_check.argtypes = [vp]
     L.sdpl_frontend_create.argtypes = [C.POINTER(vp), i, f, i, i, i, i, i, f, i, f, f, i, i]
@@ -390,46 +397,44 @@ class BinaryDescriptorMatcher(_Profiled):
             raise TypeError("descriptors must be (N, 32) uint8")
         return d
 
-    # --- train set kept on the matcher: BinaryDescriptorMatcher::add / train / clear (descriptor_custom.hpp:1015-1126) ---
+    # --- train set kept on the matcher, on the device: BinaryDescriptorMatcher::add / train / clear
+    #     (descriptor_custom.hpp:1015-1126, binary_descriptor_matcher.cpp:127-194) ---
     def add(self, descriptors):
-        """Append train descriptors (one (N, 32) array or a list of them); img index = position in the list."""
+        """Append train descriptors (one (N, 32) array or a list of them, one per image).  Queries against the stored set
+        return trainIdx = row in the concatenation of everything added and imgIdx = position of the image, as the reference."""
         ds = descriptors if isinstance(descriptors, (list, tuple)) else [descriptors]
-        if not hasattr(self, "_train"):
-            self._train = []
-        self._train += [self._desc(d) for d in ds]
+        for d in ds:
+            d = self._desc(d)
+            _check(self._L.sdpl_matcher_add(self._h, _p(d), d.shape[0]))
 
     def train(self):
         """The reference builds its multi-index hash tables here; brute force needs no index."""
+        _check(self._L.sdpl_matcher_train(self._h))
 
     def clear(self):
-        self._train = []
+        _check(self._L.sdpl_matcher_clear(self._h))
 
-    def _stored(self):
-        tr = getattr(self, "_train", [])
-        if not tr:
-            raise ValueError("no train descriptors: call add() first or pass trainDescriptors")
-        img = np.concatenate([np.full(len(d), i, np.int32) for i, d in enumerate(tr)])
-        base = np.concatenate([np.arange(len(d), dtype=np.int32) for d in tr])
-        return np.concatenate(tr), img, base
-
-    def _localise(self, m, img, base):
-        ok = m["train"] >= 0
-        m["img"][ok] = img[m["train"][ok]]
-        m["train"][ok] = base[m["train"][ok]]
-        return m
+    def train_size(self):
+        a, b = C.c_int(), C.c_int()
+        _check(self._L.sdpl_matcher_train_size(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2):
         """k nearest train descriptors per query, ascending (distance, index).  k == 2 -> (best, second) arrays;
         other k -> an (nq, k) array (missing neighbours have train = -1).  Without trainDescriptors the stored set is used."""
+        q = self._desc(queryDescriptors)
+        k = int(k)
         if trainDescriptors is None:
-            t, img, base = self._stored()
-            r = self.knnMatch(queryDescriptors, t, k)
-            if k == 2:
-                return self._localise(r[0], img, base), self._localise(r[1], img, base)
-            return self._localise(r.reshape(-1), img, base).reshape(r.shape)
+            if self.train_size()[1] == 0:
+                raise ValueError("no train descriptors: call add() first or pass trainDescriptors")
+            out = np.zeros((q.shape[0], k), DM_DTYPE)
+            _check(self._L.sdpl_matcher_knn(self._h, _p(q), q.shape[0], k, _p(out)))
+            return (out[:, 0].copy(), out[:, 1].copy()) if k == 2 else out
+        t = self._desc(trainDescriptors)
         if k != 2:
-            return self.radiusMatch(queryDescriptors, trainDescriptors, 256, k=int(k))[1]
-        q, t = self._desc(queryDescriptors), self._desc(trainDescriptors)
+            out = np.zeros((q.shape[0], k), DM_DTYPE)
+            _check(self._L.sdpl_match_knn(self._h, _p(q), q.shape[0], _p(t), t.shape[0], k, _p(out)))
+            return out
         best = np.zeros(q.shape[0], DM_DTYPE); second = np.zeros(q.shape[0], DM_DTYPE)
         _check(self._L.sdpl_match_knn2(self._h, _p(q), q.shape[0], _p(t), t.shape[0], _p(best), _p(second)))
         return best, second
@@ -445,8 +450,12 @@ class BinaryDescriptorMatcher(_Profiled):
         return out, n.value
 
     def radiusMatch(self, queryDescriptors, trainDescriptors, maxDistance, k=8):
-        q, t = self._desc(queryDescriptors), self._desc(trainDescriptors)
+        q = self._desc(queryDescriptors)
         counts = np.zeros(q.shape[0], np.int32); out = np.zeros((q.shape[0], k), DM_DTYPE)
+        if trainDescriptors is None:
+            _check(self._L.sdpl_matcher_radius(self._h, _p(q), q.shape[0], int(maxDistance), int(k), _p(counts), _p(out)))
+            return counts, out
+        t = self._desc(trainDescriptors)
         _check(self._L.sdpl_match_radius(self._h, _p(q), q.shape[0], _p(t), t.shape[0], int(maxDistance), int(k), _p(counts),
                                          _p(out)))
         return counts, out

@@ -105,11 +105,30 @@ def test_knn_general_k_and_stored_train_set(frontend, oracle):
     order = np.lexsort((np.broadcast_to(np.arange(full.shape[1]), full.shape), full), axis=1)[:, :4]
     np.testing.assert_array_equal(r["train"], order)
     np.testing.assert_array_equal(r["distance"], np.take_along_axis(full, order, 1))
-    # add / train / match on the stored set: img index and per-image train index
+    # add / train / match / knnMatch / radiusMatch on the stored (device-resident) set, through sdpl_matcher_add / _knn / _radius:
+    # trainIdx = row of the concatenation, imgIdx = image, as the reference composes them (oracle.match_stored_knn)
     g.add([t1, t2]); g.train()
+    assert g.train_size() == (500, 2)
     m = g.match(q)
+    want1 = oracle.match_stored_knn(q, [t1, t2], 1)[:, 0]
+    for name in ("query", "train", "img", "distance"):
+        np.testing.assert_array_equal(m[name], want1[name])
     assert (m["img"][:40] == 0).all() and (m["img"][40:] == 1).all()
-    assert (m["train"][:40] == np.arange(40)).all() and (m["train"][40:] == np.arange(40)).all()
+    assert (m["train"][:40] == np.arange(40)).all() and (m["train"][40:] == 300 + np.arange(40)).all()
+    for k in (2, 5):
+        r = g.knnMatch(q, k=k)
+        r = np.stack(r, 1) if k == 2 else r
+        want = oracle.match_stored_knn(q, [t1, t2], k)
+        for name in ("train", "img", "distance"):
+            np.testing.assert_array_equal(r[name], want[name])
+    counts, near = g.radiusMatch(q, None, 100, k=3)
+    wc, wn = oracle.match_radius(q, allt, 100, 3)
+    np.testing.assert_array_equal(counts, wc); np.testing.assert_array_equal(near["train"], wn["train"])
+    # the set grows across add() calls without losing what is stored
+    g.add(t1[:7])
+    assert g.train_size() == (507, 3)
+    assert (g.match(t1[:7])["img"] == 0).all()            # ties (distance 0 twice) go to the lowest row
     g.clear()
+    assert g.train_size() == (0, 0)
     with pytest.raises(ValueError):
         g.match(q)

@@ -167,6 +167,24 @@ def test_matcher_knn_equals_reference(ref, oracle):
     assert (mt[got & untied] == best["train"][got & untied]).all()
 
 
+def test_stored_train_set_indices_follow_the_reference(ref, oracle):
+    """add([T1, T2]) / train() / knnMatch(query, matches, k): the reference returns trainIdx = row of the concatenated data set
+    and imgIdx = the image the row came from (binary_descriptor_matcher.cpp:381-401); the oracle's restatement must agree
+    (distances always; indices wherever the k-th and (k+1)-th distances are not tied)."""
+    rng = np.random.default_rng(21)
+    t1 = rng.integers(0, 256, (300, 32), dtype=np.uint8); t2 = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    q = np.concatenate([t1[:40], t2[:40]]).copy()
+    for i in range(len(q)):                    # a few flipped bits: the true neighbour stays within the reference's radius
+        for b in rng.choice(256, 10, replace=False):
+            q[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    train, img, dist = ref.matcher_stored_knn(q, t1, t2, 1)
+    want = oracle.match_stored_knn(q, [t1, t2], 1)
+    assert (train[:, 0] == want["train"][:, 0]).all() and (img[:, 0] == want["img"][:, 0]).all()
+    assert (dist[:, 0] == want["distance"][:, 0]).all()
+    assert (train[:40, 0] == np.arange(40)).all() and (train[40:, 0] == 300 + np.arange(40)).all()     # rows of the concatenation
+    assert (img[:40, 0] == 0).all() and (img[40:, 0] == 1).all()
+
+
 _HEAP_SCRIPT = r"""
 import sys, numpy as np
 sys.path.insert(0, %r)
