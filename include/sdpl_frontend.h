@@ -228,6 +228,53 @@ int sdpl_line_stage_times(sdpl_line* h, float* ms, const char** names, int* laun
 int sdpl_matcher_set_profiling(sdpl_matcher* h, int on);
 int sdpl_matcher_stage_times(sdpl_matcher* h, float* ms, const char** names, int* launches, int cap);
 
+/* ------------------------------------------------------------------------------------------------
+ * Frame post-processing on the device -- the loops Frame::Frame runs on the extractor outputs (src/Frame.cc), SURVEY.md 8f rows
+ * 1 and 2.  Inputs are the reference's per-frame planes as they sit in cv::Mat: maskSEM int32 [h][w], imDepth float [h][w],
+ * imFlow float [h][w][2]; the *_dev entry points take DEVICE pointers to nframes consecutive planes and per-frame feature blocks
+ * of `capacity` rows (the layout the extractors' *_batch_dev calls produce), and are asynchronous on the handle's stream unless
+ * sync != 0.  Every output list is in the order the reference's sequential loops push it.  Counts may exceed the capacity (only
+ * `capacity` rows are written).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sdpl_post sdpl_post;
+int sdpl_post_create(sdpl_post** h, int device);
+void sdpl_post_destroy(sdpl_post* h);
+int sdpl_post_set_stream(sdpl_post* h, void* cuda_stream);
+int sdpl_post_last_launches(const sdpl_post* h);
+int sdpl_post_set_profiling(sdpl_post* h, int on);
+int sdpl_post_stage_times(sdpl_post* h, float* ms, const char** names, int* launches, int cap);
+/* semi-dense features on objects, src/Frame.cc:769-809: every step-th pixel with a non-zero mask label, 0 < depth < th_depth_obj
+ * and a flow that stays inside the image.  keys = mvObjKeys (x = column, y = row), corres = mvObjCorres, flow_next = mvObjFlowNext
+ * (2 floats), depth_out = mvObjDepth, label = vSemObjLabel */
+int sdpl_post_sample_objects_dev(sdpl_post* h, const int32_t* d_mask, const float* d_depth, const float* d_flow, int nframes, int w, int h_,
+                                 int step, float th_depth_obj, sdpl_keypoint* d_keys, sdpl_keypoint* d_corres, float* d_flow_next,
+                                 float* d_depth_out, int32_t* d_label, int capacity, int* d_n, int sync);
+/* the same for ONE frame with HOST buffers (uploads the planes, downloads the lists) */
+int sdpl_post_sample_objects(sdpl_post* h, const int32_t* mask, const float* depth, const float* flow, int w, int h_, int step,
+                             float th_depth_obj, sdpl_keypoint* keys, sdpl_keypoint* corres, float* flow_next, float* depth_out,
+                             int32_t* label, int capacity, int* n_out);
+/* the two erase loops on mvKeys_Line, src/Frame.cc:349-389 (depth step at the mid point; end points on different mask labels).
+ * keep_idx[k] = row of the k-th surviving line in the input, i.e. the row of its LBD descriptor */
+int sdpl_post_filter_lines_dev(sdpl_post* h, const int32_t* d_mask, const float* d_depth, int nframes, int w, int h_, const sdpl_keyline* d_kls,
+                               const int* d_n_in, int capacity, sdpl_keyline* d_out, int32_t* d_keep_idx, int* d_n_out, int sync);
+/* static point correspondences from the detected features (UseSampleFea == 0), src/Frame.cc:482-512, with their depths (:728-745):
+ * stat = mvStatKeysTmp, corres = mvCorres, flow_next = mvFlowNext (2 floats), stat_depth = mvStatDepthTmp, src_idx = row in the input */
+int sdpl_post_point_corres_dev(sdpl_post* h, const int32_t* d_mask, const float* d_depth, const float* d_flow, int nframes, int w, int h_,
+                               const sdpl_keypoint* d_kps, const int* d_n_in, int capacity, float th_depth, sdpl_keypoint* d_stat,
+                               sdpl_keypoint* d_corres, float* d_flow_next, float* d_stat_depth, int32_t* d_src_idx, int* d_n_out, int sync);
+/* line correspondences, src/Frame.cc:513-604, with their depths (:746-763): obj = mvObjKeys_Line (both end points on one object),
+ * stat = mvStatKeysLineTmp, corres = mvCorresLine, flow_next = mvFlowNext_Line (4 floats: start x, y, end x, y), inf_line =
+ * mvInfiniteLinesCorr (3 doubles), stat_depth = mvStatDepthLineTmp (2 floats) */
+int sdpl_post_line_corres_dev(sdpl_post* h, const int32_t* d_mask, const float* d_depth, const float* d_flow, int nframes, int w, int h_,
+                              const sdpl_keyline* d_kls, const int* d_n_in, int capacity, float th_depth, sdpl_keyline* d_obj, int* d_n_obj,
+                              sdpl_keyline* d_stat, sdpl_keyline* d_corres, float* d_flow_next, double* d_inf_line, float* d_stat_depth,
+                              int32_t* d_src_idx, int* d_n_out, int sync);
+/* AssignFeaturesToGrid / PosInGrid, src/Frame.cc:910-925, 1023-1035 (undistorted key points = key points, mDistCoef[0] == 0):
+ * cell c = posX * grid_rows + posY; items[cell_start[c] .. cell_start[c+1]) = key point indices of the cell in ascending order.
+ * d_cell_start: [nframes][grid_cols * grid_rows + 1], d_items: [nframes][capacity] */
+int sdpl_post_grid_dev(sdpl_post* h, int nframes, int w, int h_, const sdpl_keypoint* d_kps, const int* d_n_in, int capacity, int grid_cols,
+                       int grid_rows, int32_t* d_cell_start, int32_t* d_items, int sync);
+
 /* Order-independent 64-bit digest of per-frame result rows resident on the device: adds, for every frame f, the sum of the
  * hashes of rows [0, min(d_n[f], max_rows)) of its block (row_bytes per row, a multiple of 4; blocks frame_stride bytes apart)
  * to d_digest[f] (DEVICE uint64 array the caller zeroes), asynchronously on `stream` (cudaStream_t as void*).  Used to check

@@ -92,6 +92,18 @@ int orc_match_ratio(const uint8_t* q, int nq, const uint8_t* t, int nt, float ra
 void orc_match_radius(const uint8_t* q, int nq, const uint8_t* t, int nt, int radius, int k,
                       int* counts, orc_dmatch* out);
 
+/* ---- Frame post-processing (src/Frame.cc), oracle/post_oracle.cpp ---- */
+int orc_post_sample_objects(const int32_t* mask, const float* depth, const float* flow, int w, int h, int step, float th_depth_obj,
+                            orc_keypoint* keys, orc_keypoint* corres, float* flow_next, float* depth_out, int32_t* label, int cap);
+int orc_post_filter_lines(const orc_keyline* kls, int n, const int32_t* mask, const float* depth, int w, int h, orc_keyline* out,
+                          int32_t* keep_idx);
+int orc_post_point_corres(const orc_keypoint* kps, int n, const int32_t* mask, const float* depth, const float* flow, int w, int h,
+                          float th_depth, orc_keypoint* stat, orc_keypoint* corres, float* flow_next, float* stat_depth, int32_t* src_idx);
+int orc_post_line_corres(const orc_keyline* kls, int n, const int32_t* mask, const float* depth, const float* flow, int w, int h,
+                         float th_depth, orc_keyline* obj, int32_t* n_obj, orc_keyline* stat, orc_keyline* corres, float* flow_next,
+                         double* inf_line, float* stat_depth, int32_t* src_idx);
+void orc_post_grid(const orc_keypoint* kps, int n, int w, int h, int grid_cols, int grid_rows, int32_t* cell_start, int32_t* items);
+
 #ifdef __cplusplus
 }
 #endif

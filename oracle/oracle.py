@@ -292,3 +292,61 @@ def match_radius(q, t, radius, k):
     counts = np.zeros(q.shape[0], np.int32); out = np.zeros((q.shape[0], k), DM_DTYPE)
     lib().orc_match_radius(_p(q), q.shape[0], _p(t), t.shape[0], int(radius), int(k), _p(counts), _p(out))
     return counts, out
+
+
+# ---- Frame post-processing (oracle/post_oracle.cpp; reference: src/Frame.cc) ----
+def _planes(mask, depth, flow):
+    return (np.ascontiguousarray(mask, np.int32), np.ascontiguousarray(depth, np.float32), np.ascontiguousarray(flow, np.float32))
+
+
+def post_sample_objects(mask, depth, flow, step=4, th_depth_obj=25.0):
+    mask, depth, flow = _planes(mask, depth, flow)
+    h, w = mask.shape
+    cap = ((h + step - 1) // step) * ((w + step - 1) // step)
+    keys, corres = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    fn, d, lab = np.zeros((cap, 2), np.float32), np.zeros(cap, np.float32), np.zeros(cap, np.int32)
+    L = lib(); L.orc_post_sample_objects.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_float] + [C.c_void_p] * 5 + [C.c_int]
+    n = L.orc_post_sample_objects(_p(mask), _p(depth), _p(flow), w, h, step, th_depth_obj, _p(keys), _p(corres), _p(fn), _p(d), _p(lab), cap)
+    return dict(keys=keys[:n], corres=corres[:n], flow_next=fn[:n], depth=d[:n], label=lab[:n])
+
+
+def post_filter_lines(kls, mask, depth):
+    mask, depth, _ = _planes(mask, depth, np.zeros((1, 1, 2), np.float32))
+    h, w = mask.shape
+    kls = np.ascontiguousarray(kls, KL_DTYPE); n = len(kls)
+    out, idx = np.zeros(max(n, 1), KL_DTYPE), np.zeros(max(n, 1), np.int32)
+    L = lib(); L.orc_post_filter_lines.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    k = L.orc_post_filter_lines(_p(kls), n, _p(mask), _p(depth), w, h, _p(out), _p(idx))
+    return out[:k], idx[:k]
+
+
+def post_point_corres(kps, mask, depth, flow, th_depth=40.0):
+    mask, depth, flow = _planes(mask, depth, flow)
+    h, w = mask.shape
+    kps = np.ascontiguousarray(kps, KP_DTYPE); n = len(kps); m = max(n, 1)
+    stat, corres = np.zeros(m, KP_DTYPE), np.zeros(m, KP_DTYPE)
+    fn, sd, idx = np.zeros((m, 2), np.float32), np.zeros(m, np.float32), np.zeros(m, np.int32)
+    L = lib(); L.orc_post_point_corres.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 5
+    k = L.orc_post_point_corres(_p(kps), n, _p(mask), _p(depth), _p(flow), w, h, th_depth, _p(stat), _p(corres), _p(fn), _p(sd), _p(idx))
+    return dict(stat=stat[:k], corres=corres[:k], flow_next=fn[:k], depth=sd[:k], src_idx=idx[:k])
+
+
+def post_line_corres(kls, mask, depth, flow, th_depth=40.0):
+    mask, depth, flow = _planes(mask, depth, flow)
+    h, w = mask.shape
+    kls = np.ascontiguousarray(kls, KL_DTYPE); n = len(kls); m = max(n, 1)
+    obj, stat, corres = np.zeros(m, KL_DTYPE), np.zeros(m, KL_DTYPE), np.zeros(m, KL_DTYPE)
+    fn, inf, sd, idx = np.zeros((m, 4), np.float32), np.zeros((m, 3), np.float64), np.zeros((m, 2), np.float32), np.zeros(m, np.int32)
+    nobj = C.c_int32(0)
+    L = lib(); L.orc_post_line_corres.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_float] + [C.c_void_p] * 8
+    k = L.orc_post_line_corres(_p(kls), n, _p(mask), _p(depth), _p(flow), w, h, th_depth, _p(obj), C.byref(nobj), _p(stat), _p(corres), _p(fn),
+                               _p(inf), _p(sd), _p(idx))
+    return dict(obj=obj[:nobj.value], stat=stat[:k], corres=corres[:k], flow_next=fn[:k], inf_line=inf[:k], depth=sd[:k], src_idx=idx[:k])
+
+
+def post_grid(kps, w, h, grid_cols=64, grid_rows=48):
+    kps = np.ascontiguousarray(kps, KP_DTYPE); n = len(kps)
+    cs, items = np.zeros(grid_cols * grid_rows + 1, np.int32), np.zeros(max(n, 1), np.int32)
+    L = lib(); L.orc_post_grid.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p] * 2
+    L.orc_post_grid(_p(kps), n, w, h, grid_cols, grid_rows, _p(cs), _p(items))
+    return cs, items[:cs[-1]]

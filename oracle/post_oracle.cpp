@@ -1,0 +1,190 @@
+// oracle/post_oracle.cpp -- CPU ORACLE (test infrastructure, NOT the product) of the per-frame post-processing that
+// Frame::Frame runs on the extractor outputs (reference: src/Frame.cc).  Each function restates
+// one loop of the constructor, statement by statement, with std::vector push_back semantics replaced by output arrays in the
+// same order.  Inputs are the reference's own per-frame planes: maskSEM (CV_32S), imDepth (CV_32F), imFlow (CV_32FC2).
+//
+// Parity status: Frame.cc cannot be compiled here (it pulls in g2o, Eigen, OpenCV highgui / xfeatures2d / flann through Frame.h),
+// so these restatements are "parity unpinned" against a compiled reference; they are checked against an independent numpy
+// restatement (tests/test_oracle_post.py) and read side by side with the cited lines.
+//
+// C++ conversions the code below relies on (all as written in Frame.cc, which has `using namespace std`, :24):
+//   int x = kp.pt.x            float -> int truncates toward zero                                   (:353-356, :488-489, :519-522)
+//   Mat::at<T>(float, float)   the float indices convert to int the same way                        (:737, :756-757)
+//   abs(float)                 std::abs(float) (float result)                                         (:376)
+//   pow(int, 2), sqrt(double)  computed in double, then narrowed to float on assignment              (:371)
+//   j + flow_x                 int + float -> float                                                   (:792)
+#include "oracle.h"
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+struct Planes {
+  const int32_t* mask; const float* depth; const float* flow; int w, h;
+  int m(int y, int x) const { return mask[(size_t)y * w + x]; }
+  float d(int y, int x) const { return depth[(size_t)y * w + x]; }
+  float fx(int y, int x) const { return flow[((size_t)y * w + x) * 2]; }
+  float fy(int y, int x) const { return flow[((size_t)y * w + x) * 2 + 1]; }
+};
+orc_keypoint make_kp(float x, float y, float size, float angle, float response, int octave, int class_id) {
+  orc_keypoint k; k.x = x; k.y = y; k.size = size; k.angle = angle; k.response = response; k.octave = octave; k.class_id = class_id;
+  return k;
+}
+// KeyLine corr_line of Frame.cc:566-582 (and :672-687, :842-856): the fields the reference assigns; the octave-relative end points,
+// which it leaves uninitialised, are zero here
+orc_keyline make_corr_line(float sx, float sy, float ex, float ey, int octave) {
+  orc_keyline c; memset(&c, 0, sizeof(c));
+  c.sx = sx; c.sy = sy; c.ex = ex; c.ey = ey; c.octave = octave;
+  c.angle = std::atan2(c.ey - c.sy, c.ex - c.sx);                     // std::atan2(float, float)
+  c.pt_x = (c.sx + c.ex) / 2; c.pt_y = (c.sy + c.ey) / 2;
+  c.size = (c.ex - c.sx) * (c.ey - c.sy);
+  c.length = (float)std::sqrt(std::pow(c.ex - c.sx, 2) + std::pow(c.ey - c.sy, 2));
+  c.response = 0; c.class_id = -1; c.num_pixels = 0;
+  return c;
+}
+}  // namespace
+
+extern "C" {
+
+/* Semi-dense features on objects, Frame.cc:769-809.  Outputs in scan order; returns the count (may exceed cap: only cap are
+   written). */
+int orc_post_sample_objects(const int32_t* mask, const float* depth, const float* flow, int w, int h, int step, float th_depth_obj,
+                            orc_keypoint* keys, orc_keypoint* corres, float* flow_next, float* depth_out, int32_t* label, int cap) {
+  const Planes P{mask, depth, flow, w, h};
+  int n = 0;
+  for (int i = 0; i < h; i = i + step)
+    for (int j = 0; j < w; j = j + step) {
+      if (P.m(i, j) != 0 && P.d(i, j) < th_depth_obj && P.d(i, j) > 0) {
+        const float flow_x = P.fx(i, j), flow_y = P.fy(i, j);
+        if (j + flow_x < w && j + flow_x > 0 && i + flow_y < h && i + flow_y > 0) {
+          if (n < cap) {
+            flow_next[2 * n] = flow_x; flow_next[2 * n + 1] = flow_y;
+            corres[n] = make_kp(j + flow_x, i + flow_y, 0, 0, 0, -1, -1);     // cv::KeyPoint(x, y, size, angle, response, octave)
+            keys[n] = make_kp((float)j, (float)i, 0, 0, 0, -1, -1);
+            depth_out[n] = P.d(i, j);
+            label[n] = P.m(i, j);
+          }
+          n++;
+        }
+      }
+    }
+  return n;
+}
+
+/* The two erase loops on mvKeys_Line, Frame.cc:349-389: a line goes when the depth at its mid point departs from the mean of
+   the end-point depths by more than 10 * length / 1000, or when its end points carry different mask labels.  keep_idx[k] = index
+   (in the input) of the k-th surviving line -- the row of its LBD descriptor (the reference forgets to erase those). */
+int orc_post_filter_lines(const orc_keyline* kls, int n, const int32_t* mask, const float* depth, int w, int h, orc_keyline* out,
+                          int32_t* keep_idx) {
+  const Planes P{mask, depth, nullptr, w, h};
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    const orc_keyline& l = kls[i];
+    const int x1 = (int)l.sx, y1 = (int)l.sy, x2 = (int)l.ex, y2 = (int)l.ey;
+    const int xm = (x1 + x2) / 2, ym = (y1 + y2) / 2;
+    const float depthStart = P.d(y1, x1), depthMid = P.d(ym, xm), depthEnd = P.d(y2, x2);
+    const float depthMidExpected = (depthStart + depthEnd) / 2;
+    const float baseThreshold = 10.0;
+    const float lineLength = std::sqrt(std::pow(x2 - x1, 2) + std::pow(y2 - y1, 2));
+    const float threshold = baseThreshold * (lineLength / 1000);
+    if (std::abs(depthMid - depthMidExpected) > threshold) continue;
+    if (P.m(y1, x1) != P.m(y2, x2)) continue;
+    out[k] = l; keep_idx[k] = i; k++;
+  }
+  return k;
+}
+
+/* Static point correspondences from the detected features (UseSampleFea == 0), Frame.cc:482-512, and their depths, :728-745.
+   Returns the count; src_idx[k] = index of the key point in the input. */
+int orc_post_point_corres(const orc_keypoint* kps, int n, const int32_t* mask, const float* depth, const float* flow, int w, int h,
+                          float th_depth, orc_keypoint* stat, orc_keypoint* corres, float* flow_next, float* stat_depth, int32_t* src_idx) {
+  const Planes P{mask, depth, flow, w, h};
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    const int x = (int)kps[i].x, y = (int)kps[i].y;
+    if (P.m(y, x) != 0) continue;
+    if (P.d(y, x) > th_depth || P.d(y, x) <= 0) continue;
+    const float flow_xe = P.fx(y, x), flow_ye = P.fy(y, x);
+    if (flow_xe != 0 && flow_ye != 0) {
+      if (kps[i].x + flow_xe < w && kps[i].y + flow_ye < h && kps[i].x < w && kps[i].y < h) {
+        stat[k] = kps[i];
+        corres[k] = make_kp(kps[i].x + flow_xe, kps[i].y + flow_ye, 0, 0, 0, kps[i].octave, -1);
+        flow_next[2 * k] = flow_xe; flow_next[2 * k + 1] = flow_ye;
+        // :728-745: mvStatDepthTmp[i] = d if d > 0 else -1, with d = imDepth.at<float>(kp.pt.y, kp.pt.x)
+        const float d = P.d((int)kps[i].y, (int)kps[i].x);
+        stat_depth[k] = d > 0 ? d : -1.f;
+        src_idx[k] = i;
+        k++;
+      }
+    }
+  }
+  return k;
+}
+
+/* Line correspondences, Frame.cc:513-604 and :746-763.  Lines with both end points on the same object go to obj (n_obj), lines on
+   the static background with valid depth and flow to stat / corres / flow_next (4 floats: start x,y, end x,y) / inf_line (3
+   doubles: normalised cross product of the homogeneous end points) / stat_depth (2 floats).  Returns the static count. */
+int orc_post_line_corres(const orc_keyline* kls, int n, const int32_t* mask, const float* depth, const float* flow, int w, int h,
+                         float th_depth, orc_keyline* obj, int32_t* n_obj, orc_keyline* stat, orc_keyline* corres, float* flow_next,
+                         double* inf_line, float* stat_depth, int32_t* src_idx) {
+  const Planes P{mask, depth, flow, w, h};
+  int k = 0, no = 0;
+  for (int i = 0; i < n; ++i) {
+    const int start_x = (int)kls[i].sx, start_y = (int)kls[i].sy, end_x = (int)kls[i].ex, end_y = (int)kls[i].ey;
+    if (P.m(start_y, start_x) != 0 && P.m(end_y, end_x) != 0) {
+      if (P.m(start_y, start_x) == P.m(end_y, end_x)) obj[no++] = kls[i];
+      continue;
+    }
+    if (P.m(start_y, start_x) != 0 || P.m(end_y, end_x) != 0) continue;
+    if (std::fabs(start_x - end_x) < 1e-6 && std::fabs(start_y - end_y) < 1e-6) continue;
+    if (P.d(start_y, start_x) > th_depth || P.d(start_y, start_x) <= 0 || P.d(end_y, end_x) > th_depth || P.d(end_y, end_x) <= 0) continue;
+    const float fsx = P.fx(start_y, start_x), fsy = P.fy(start_y, start_x), fex = P.fx(end_y, end_x), fey = P.fy(end_y, end_x);
+    if (fsx != 0 && fsy != 0 && fex != 0 && fey != 0) {
+      if (start_x + fsx < w && start_y + fsy < h && end_x + fex < w && end_y + fey < h && start_x + fsx > 0 && start_y + fsy > 0 &&
+          end_x + fex > 0 && end_y + fey > 0) {
+        stat[k] = kls[i];
+        const orc_keyline c = make_corr_line(start_x + fsx, start_y + fsy, end_x + fex, end_y + fey, kls[i].octave);
+        corres[k] = c;
+        flow_next[4 * k] = fsx; flow_next[4 * k + 1] = fsy; flow_next[4 * k + 2] = fex; flow_next[4 * k + 3] = fey;
+        // Eigen::Vector3d start(sx, sy, 1), end(ex, ey, 1); inf_line = start.cross(end).normalized()   (:590-594)
+        const double a0 = c.sx, a1 = c.sy, a2 = 1, b0 = c.ex, b1 = c.ey, b2 = 1;
+        const double c0 = a1 * b2 - a2 * b1, c1 = a2 * b0 - a0 * b2, c2 = a0 * b1 - a1 * b0;
+        const double nn = std::sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+        inf_line[3 * k] = nn > 0 ? c0 / nn : c0; inf_line[3 * k + 1] = nn > 0 ? c1 / nn : c1; inf_line[3 * k + 2] = nn > 0 ? c2 / nn : c2;
+        // :746-763 -- mind the missing braces of the reference: `second` is assigned unconditionally
+        const float d_start = P.d((int)kls[i].sy, (int)kls[i].sx), d_end = P.d((int)kls[i].ey, (int)kls[i].ex);
+        stat_depth[2 * k] = -1.f; stat_depth[2 * k + 1] = -1.f;
+        if (d_start > 0 && d_end > 0) stat_depth[2 * k] = d_start;
+        stat_depth[2 * k + 1] = d_end;
+        src_idx[k] = i;
+        k++;
+      }
+    }
+  }
+  *n_obj = no;
+  return k;
+}
+
+/* AssignFeaturesToGrid / PosInGrid, Frame.cc:910-925, 1023-1035, for undistorted key points (mDistCoef[0] == 0: mvKeysUn = mvKeys,
+   :1039-1043; image bounds 0 .. cols / rows, ComputeImageBounds).  cell c = posX * rows + posY; cell_start[c] .. cell_start[c+1]
+   index `items`, which lists the key points of a cell in ascending index order (push_back order). */
+void orc_post_grid(const orc_keypoint* kps, int n, int w, int h, int grid_cols, int grid_rows, int32_t* cell_start, int32_t* items) {
+  const float mnMinX = 0.f, mnMaxX = (float)w, mnMinY = 0.f, mnMaxY = (float)h;
+  const float wInv = static_cast<float>(grid_cols) / static_cast<float>(mnMaxX - mnMinX);
+  const float hInv = static_cast<float>(grid_rows) / static_cast<float>(mnMaxY - mnMinY);
+  std::vector<std::vector<int>> grid((size_t)grid_cols * grid_rows);
+  for (int i = 0; i < n; i++) {
+    const int posX = (int)std::round((kps[i].x - mnMinX) * wInv), posY = (int)std::round((kps[i].y - mnMinY) * hInv);
+    if (posX < 0 || posX >= grid_cols || posY < 0 || posY >= grid_rows) continue;
+    grid[(size_t)posX * grid_rows + posY].push_back(i);
+  }
+  int k = 0;
+  for (size_t c = 0; c < grid.size(); c++) {
+    cell_start[c] = k;
+    for (int v : grid[c]) items[k++] = v;
+  }
+  cell_start[grid.size()] = k;
+}
+
+}  // extern "C"

@@ -112,6 +112,16 @@ def load_library(path=None):
     L.sdpl_frontend_submit.argtypes = [vp, vp, i, i, i, i, sz]
     L.sdpl_frontend_collect.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ip]
     L.sdpl_frontend_pending.argtypes = [vp]
+    L.sdpl_post_create.argtypes = [C.POINTER(vp), i]
+    L.sdpl_post_destroy.argtypes = [vp]; L.sdpl_post_destroy.restype = None
+    L.sdpl_post_set_stream.argtypes = [vp, vp]; L.sdpl_post_last_launches.argtypes = [vp]
+    L.sdpl_post_set_profiling.argtypes = [vp, i]; L.sdpl_post_stage_times.argtypes = [vp, vp, vp, vp, i]
+    L.sdpl_post_sample_objects_dev.argtypes = [vp, vp, vp, vp, i, i, i, i, f, vp, vp, vp, vp, vp, i, vp, i]
+    L.sdpl_post_sample_objects.argtypes = [vp, vp, vp, vp, i, i, i, f, vp, vp, vp, vp, vp, i, ip]
+    L.sdpl_post_filter_lines_dev.argtypes = [vp, vp, vp, i, i, i, vp, vp, i, vp, vp, vp, i]
+    L.sdpl_post_point_corres_dev.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, i, f, vp, vp, vp, vp, vp, vp, i]
+    L.sdpl_post_line_corres_dev.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, i, f, vp, vp, vp, vp, vp, vp, vp, vp, vp, i]
+    L.sdpl_post_grid_dev.argtypes = [vp, i, i, i, vp, vp, i, i, i, vp, vp, i]
     L.sdpl_rows_digest_dev.argtypes = [vp, i, sz, vp, i, i, C.c_ulonglong, vp, vp]
     if path is None:
         _lib = L
@@ -556,6 +566,77 @@ class FrontEnd:
 
     def last_launches(self):
         return self._L.sdpl_frontend_last_launches(self._h)
+
+
+class FramePost(_Profiled):
+    _kind = "post"
+    """The loops Frame::Frame runs on the extractor outputs (src/Frame.cc:349-389, 482-604, 728-809, 910-925) on the device.
+    The *_dev methods take raw device addresses (ints, e.g. torch tensor.data_ptr()) of batched planes / feature blocks and are
+    asynchronous on the handle's stream unless sync=True; sample_objects takes one frame's numpy planes."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        _check(self._L.sdpl_post_create(C.byref(self._h), int(device)))
+        self.device = int(device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.sdpl_post_destroy(h)
+            self._h = None
+
+    def set_stream(self, cuda_stream):
+        _check(self._L.sdpl_post_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def last_launches(self):
+        return self._L.sdpl_post_last_launches(self._h)
+
+    def sample_objects(self, maskSEM, imDepth, imFlow, step=4, thDepthObj=25.0):
+        """Semi-dense features on objects of one frame (src/Frame.cc:769-809) -> dict(keys = mvObjKeys, corres = mvObjCorres,
+        flow_next = mvObjFlowNext, depth = mvObjDepth, label = vSemObjLabel)."""
+        m = np.ascontiguousarray(maskSEM, np.int32); d = np.ascontiguousarray(imDepth, np.float32); fl = np.ascontiguousarray(imFlow, np.float32)
+        h, w = m.shape
+        if d.shape != (h, w) or fl.shape != (h, w, 2):
+            raise TypeError("maskSEM (h, w) int32, imDepth (h, w) float32 and imFlow (h, w, 2) float32 must agree in size")
+        cap = ((h + step - 1) // step) * ((w + step - 1) // step)
+        keys, corres = np.empty(cap, KP_DTYPE), np.empty(cap, KP_DTYPE)
+        fn, dep, lab = np.empty((cap, 2), np.float32), np.empty(cap, np.float32), np.empty(cap, np.int32)
+        n = C.c_int(0)
+        _check(self._L.sdpl_post_sample_objects(self._h, _p(m), _p(d), _p(fl), w, h, int(step), float(thDepthObj), _p(keys), _p(corres), _p(fn),
+                                                _p(dep), _p(lab), cap, C.byref(n)))
+        k = n.value
+        return dict(keys=keys[:k].copy(), corres=corres[:k].copy(), flow_next=fn[:k].copy(), depth=dep[:k].copy(), label=lab[:k].copy())
+
+    def sample_objects_dev(self, d_mask, d_depth, d_flow, nframes, w, h, step, th_depth_obj, d_keys, d_corres, d_flow_next, d_depth_out, d_label,
+                           capacity, d_n, sync=False):
+        v = C.c_void_p
+        _check(self._L.sdpl_post_sample_objects_dev(self._h, v(d_mask), v(d_depth), v(d_flow), nframes, w, h, step, float(th_depth_obj), v(d_keys),
+                                                    v(d_corres), v(d_flow_next), v(d_depth_out), v(d_label), capacity, v(d_n), int(sync)))
+
+    def filter_lines_dev(self, d_mask, d_depth, nframes, w, h, d_kls, d_n_in, capacity, d_out, d_keep_idx, d_n_out, sync=False):
+        v = C.c_void_p
+        _check(self._L.sdpl_post_filter_lines_dev(self._h, v(d_mask), v(d_depth), nframes, w, h, v(d_kls), v(d_n_in), capacity, v(d_out),
+                                                  v(d_keep_idx), v(d_n_out), int(sync)))
+
+    def point_corres_dev(self, d_mask, d_depth, d_flow, nframes, w, h, d_kps, d_n_in, capacity, th_depth, d_stat, d_corres, d_flow_next,
+                         d_stat_depth, d_src_idx, d_n_out, sync=False):
+        v = C.c_void_p
+        _check(self._L.sdpl_post_point_corres_dev(self._h, v(d_mask), v(d_depth), v(d_flow), nframes, w, h, v(d_kps), v(d_n_in), capacity,
+                                                  float(th_depth), v(d_stat), v(d_corres), v(d_flow_next), v(d_stat_depth), v(d_src_idx),
+                                                  v(d_n_out), int(sync)))
+
+    def line_corres_dev(self, d_mask, d_depth, d_flow, nframes, w, h, d_kls, d_n_in, capacity, th_depth, d_obj, d_n_obj, d_stat, d_corres,
+                        d_flow_next, d_inf_line, d_stat_depth, d_src_idx, d_n_out, sync=False):
+        v = C.c_void_p
+        _check(self._L.sdpl_post_line_corres_dev(self._h, v(d_mask), v(d_depth), v(d_flow), nframes, w, h, v(d_kls), v(d_n_in), capacity,
+                                                 float(th_depth), v(d_obj), v(d_n_obj), v(d_stat), v(d_corres), v(d_flow_next), v(d_inf_line),
+                                                 v(d_stat_depth), v(d_src_idx), v(d_n_out), int(sync)))
+
+    def grid_dev(self, nframes, w, h, d_kps, d_n_in, capacity, d_cell_start, d_items, grid_cols=64, grid_rows=48, sync=False):
+        v = C.c_void_p
+        _check(self._L.sdpl_post_grid_dev(self._h, nframes, w, h, v(d_kps), v(d_n_in), capacity, grid_cols, grid_rows, v(d_cell_start),
+                                          v(d_items), int(sync)))
 
 
 def rows_digest_dev(d_rows, row_bytes, frame_stride, d_n, nframes, max_rows, salt, d_digest, cuda_stream=0):

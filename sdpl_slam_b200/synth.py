@@ -93,3 +93,29 @@ def map_descriptors(desc: np.ndarray, n_map: int, seed: int, flips: int = 12) ->
     rest = rng.integers(0, 256, size=(max(0, n_map - own.shape[0]), 32), dtype=np.uint8)
     allm = np.concatenate([own, rest])[:n_map]
     return allm[rng.permutation(allm.shape[0])].copy()
+
+
+def scene_planes(seed: int, h: int = 375, w: int = 1242, n_obj: int = 6):
+    """The per-frame planes Frame::Frame reads next to the image (src/Frame.cc): a semantic / motion mask (int32, 0 =
+    background, 1.. = object label: a few rectangles), a depth plane (float32 metres, with holes of 0 and a far region beyond
+    the thresholds) and an optical-flow plane (float32, 2 channels; exactly 0 in some patches, pointing out of the image near
+    two borders).  Deterministic in the seed."""
+    rng = np.random.default_rng(int(seed) + 777_000)
+    mask = np.zeros((h, w), np.int32)
+    for k in range(n_obj):
+        rw = int(rng.integers(w // 16, w // 5)); rh = int(rng.integers(h // 8, h // 2))
+        rx = int(rng.integers(0, w - rw)); ry = int(rng.integers(0, h - rh))
+        mask[ry:ry + rh, rx:rx + rw] = k + 1
+    yy, xx = np.mgrid[0:h, 0:w]
+    depth = (4.0 + 36.0 * (1.0 - yy / float(h)) + 2.0 * np.sin(xx / 37.0)).astype(np.float32)        # 4 .. 42 m, far at the top
+    depth[mask > 0] = (6.0 + 3.0 * mask[mask > 0]).astype(np.float32)                                # objects: flat depth per label
+    holes = rng.integers(0, 50, size=(h // 5 + 1, w // 5 + 1)) == 0
+    depth[np.kron(holes, np.ones((5, 5), bool))[:h, :w]] = 0.0
+    flow = np.empty((h, w, 2), np.float32)
+    flow[..., 0] = (1.5 + xx / 300.0 - 2.0 * (mask > 0)).astype(np.float32)
+    flow[..., 1] = (-0.75 + yy / 250.0 + 0.5 * (mask % 2)).astype(np.float32)
+    zero = rng.integers(0, 30, size=(h // 8 + 1, w // 8 + 1)) == 0
+    flow[np.kron(zero, np.ones((8, 8), bool))[:h, :w]] = 0.0
+    flow[:, w - 3:, 0] += 6.0          # leaves the image on the right
+    flow[:2, :, 1] -= 4.0              # and at the top
+    return mask, depth, flow
