@@ -372,8 +372,8 @@ class ResidentArm:
             self.d_map = torch.from_numpy(_map_descriptors(cfg["n_map"])).to(dev)
             self.d_nmap = torch.full((F,), cfg["n_map"], dtype=i32, device=dev)
         self.stats = z(F, 8, dt=i32)          # n_kp, n_lines, n_pt_matches, n_ln_matches, 2 x 64-bit digests (points, lines)
-        self.dig = z(F, 2, dt=torch.int64)
-        self.s_line, self.s_orb, self.s_match, self.s_lmatch = (torch.cuda.Stream(device=dev, priority=0) for _ in range(4))
+        self.dig = z(2, F, dt=torch.int64)     # [0]: points, [1]: lines
+        self.s_line, self.s_orb, self.s_match, self.s_lmatch, self.s_tail = (torch.cuda.Stream(device=dev, priority=0) for _ in range(5))
         self.launches = 0
         self.bind()
 
@@ -412,8 +412,13 @@ class ResidentArm:
         W, H = self.cfg["w"], self.cfg["h"]
         E = F + lead
         k0 = 1 - lead                       # first slot the extraction writes
+        # Everything is enqueued on the arm's own streams behind the caller's current position, and nothing makes the caller's stream
+        # wait: two arms used alternately overlap the tail of one step (matching, statistics) with the extraction of the next.
+        # The arm's buffers are reused every time: its streams first wait for its previous statistics pass (s_tail)
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event(); ev.record(main)
+        for s in (self.s_orb, self.s_line, self.s_match, self.s_lmatch):
+            s.wait_stream(self.s_tail)
         if self.use_line:
             self.s_line.wait_event(ev)
             self.line.extract_batch_dev(d_imgs.data_ptr(), E, W, H, self.d_kls.data_ptr() + k0 * LINE_CAP * 68,
@@ -429,13 +434,20 @@ class ResidentArm:
             if self.use_line and not self.map_mode:
                 self.s_lmatch.wait_stream(self.s_line)
                 self._match(self.lmat, self.d_ldesc, self.d_nkl, LINE_CAP, self.d_lbest, self.d_lsecond, self.d_lout, self.d_lnacc)
+        tail = self.s_tail
         for s in (self.s_orb, self.s_line, self.s_match, self.s_lmatch):
-            main.wait_stream(s)
-        # per-frame statistics {n_kp, n_lines, n_point_matches, n_line_matches} + digests of the frame's result rows
-        st, ms = self.stats, main.cuda_stream
+            tail.wait_stream(s)
+        with torch.cuda.stream(tail):
+            self._stats(tail)
+        return self.stats
+
+    def _stats(self, tail):
+        """per-frame statistics {n_kp, n_lines, n_point_matches, n_line_matches} + digests of the frame's result rows (on s_tail)"""
+        torch, fe, F, cap = self.torch, self.fe, self.F, self.cap
+        st, ms = self.stats, tail.cuda_stream
         st[:, 0].copy_(self.d_nkp[1:]); st[:, 2].copy_(self.d_nacc)
         self.dig.zero_()
-        dg = self.dig.data_ptr()
+        dg, dgl = self.dig[0].data_ptr(), self.dig[1].data_ptr()
         n1 = self.d_nkp.data_ptr() + 4
         fe.rows_digest_dev(self.d_kps.data_ptr() + cap * 28, 28, cap * 28, n1, F, cap, 1, dg, ms)
         fe.rows_digest_dev(self.d_desc.data_ptr() + cap * 32, 32, cap * 32, n1, F, cap, 2, dg, ms)
@@ -445,13 +457,16 @@ class ResidentArm:
         if self.use_line:
             st[:, 1].copy_(self.d_nkl[1:]); st[:, 3].copy_(self.d_lnacc)
             l1 = self.d_nkl.data_ptr() + 4
-            fe.rows_digest_dev(self.d_kls.data_ptr() + LINE_CAP * 68, 68, LINE_CAP * 68, l1, F, LINE_CAP, 4, dg + 8, ms)
-            fe.rows_digest_dev(self.d_ldesc.data_ptr() + LINE_CAP * 32, 32, LINE_CAP * 32, l1, F, LINE_CAP, 5, dg + 8, ms)
+            fe.rows_digest_dev(self.d_kls.data_ptr() + LINE_CAP * 68, 68, LINE_CAP * 68, l1, F, LINE_CAP, 4, dgl, ms)
+            fe.rows_digest_dev(self.d_ldesc.data_ptr() + LINE_CAP * 32, 32, LINE_CAP * 32, l1, F, LINE_CAP, 5, dgl, ms)
             self.launches += 2
             if self.use_match and not self.map_mode:
-                fe.rows_digest_dev(self.d_lout.data_ptr(), 16, LINE_CAP * 16, l1, F, LINE_CAP, 6, dg + 8, ms); self.launches += 1
-        st[:, 4:8].copy_(self.dig.view(torch.int32).view(F, 4))
-        return st
+                fe.rows_digest_dev(self.d_lout.data_ptr(), 16, LINE_CAP * 16, l1, F, LINE_CAP, 6, dgl, ms); self.launches += 1
+        st[:, 4:6].copy_(self.dig[0].view(torch.int32).view(F, 2)); st[:, 6:8].copy_(self.dig[1].view(torch.int32).view(F, 2))
+
+    def wait(self):
+        """the caller's current stream waits for the arm's last step"""
+        self.torch.cuda.current_stream().wait_stream(self.s_tail)
 
 
 def stage_table(arm, d_imgs, cfg, peak, facts, reps=3):
@@ -505,6 +520,72 @@ def stage_table(arm, d_imgs, cfg, peak, facts, reps=3):
     return rows
 
 
+def post_stage_rows(fe, torch, dev, local, cfg, arm, peak, F):
+    """Frame post-processing on the device (src/Frame.cc:349-389, 482-604, 728-809, 910-925) over the F frames
+    of the step, on the key points / key lines the extractors left in HBM: stage times by CUDA events on the handle's stream.
+    Not part of the headline step (the metric is ORB + LSD/LBD + match); reported beside it."""
+    from sdpl_slam_b200 import synth
+    H, W = cfg["h"], cfg["w"]
+    nsc = 8
+    planes = [synth.scene_planes(s, H, W) for s in range(nsc)]
+    rep = (F + nsc - 1) // nsc
+    dm = torch.from_numpy(np.stack([p[0] for p in planes])).to(dev).repeat(rep, 1, 1)[:F].contiguous()
+    dd = torch.from_numpy(np.stack([p[1] for p in planes])).to(dev).repeat(rep, 1, 1)[:F].contiguous()
+    df = torch.from_numpy(np.stack([p[2] for p in planes])).to(dev).repeat(rep, 1, 1, 1)[:F].contiguous()
+    post = fe.FramePost(device=local); post.set_profiling(True)
+    step = 4
+    cap = ((H + step - 1) // step) * ((W + step - 1) // step)
+    u8, i32, f32 = torch.uint8, torch.int32, torch.float32
+    z = lambda *shape, dt=u8: torch.zeros(shape, dtype=dt, device=dev)
+    keys, corres, fn, dep, lab, n = z(F, cap, 28), z(F, cap, 28), z(F, cap, 2, dt=f32), z(F, cap, dt=f32), z(F, cap, dt=i32), z(F, dt=i32)
+    KC, LC = arm.cap, LINE_CAP
+    rows = []
+
+    def timed(name, fn_, reps=3):
+        t = 0.0
+        for _ in range(reps):
+            torch.cuda.synchronize(); fn_()
+            t += sum(ms for _, ms, _ in post.stage_times()) / reps
+        return t
+
+    t = timed("object_sampling", lambda: post.sample_objects_dev(dm.data_ptr(), dd.data_ptr(), df.data_ptr(), F, W, H, step, 25.0, keys.data_ptr(),
+                                                                 corres.data_ptr(), fn.data_ptr(), dep.data_ptr(), lab.data_ptr(), cap, n.data_ptr()))
+    kept = int(n.sum().item())
+    samp = dm[:, ::step, ::step]
+    nonzero = int((samp != 0).sum().item()); nsamp = samp.numel()
+    addressed = nsamp * 4 + nonzero * 12 + kept * (72 + 12 + 4)          # mask; depth + flow where the mask is set; records (+ re-read, bitmap)
+    sectors = F * ((H + step - 1) // step) * W * 4 + nonzero * 64 + kept * (72 + 64)   # 32-byte sectors: every sampled mask row in full, one sector
+    rows.append({"stage": "object_sampling", "ms": round(t, 4), "launches": 3, "alg_bytes": int(addressed), "gbs": round(addressed / t / 1e6, 1),
+                 "frac": round(addressed / t / 1e6 / peak, 4), "sector_bytes": int(sectors), "sector_gbs": round(sectors / t / 1e6, 1),
+                 "frac_sectors": round(sectors / t / 1e6 / peak, 4), "samples_kept_per_frame": kept / F,
+                 "note": "every 4th pixel of every 4th row: a 32-byte sector holds two mask samples, so the DRAM traffic of the compulsory "
+                         "sectors (sector_bytes) is 4x the addressed bytes"})
+    if arm.use_line:
+        fk, fidx, fnn = z(F, LC, 68), z(F, LC, dt=i32), z(F, dt=i32)
+        kl1 = arm.d_kls.data_ptr() + LC * 68; nl1 = arm.d_nkl.data_ptr() + 4
+        t = timed("line_filters", lambda: post.filter_lines_dev(dm.data_ptr(), dd.data_ptr(), F, W, H, kl1, nl1, LC, fk.data_ptr(), fidx.data_ptr(),
+                                                                fnn.data_ptr()))
+        rows.append({"stage": "line_filters", "ms": round(t, 4), "launches": 1})
+        obj, nobj, stat, cor = z(F, LC, 68), z(F, dt=i32), z(F, LC, 68), z(F, LC, 68)
+        lfn, inf, sdep, sidx, nst = z(F, LC, 4, dt=f32), z(F, LC, 3, dt=torch.float64), z(F, LC, 2, dt=f32), z(F, LC, dt=i32), z(F, dt=i32)
+        t = timed("line_corres", lambda: post.line_corres_dev(dm.data_ptr(), dd.data_ptr(), df.data_ptr(), F, W, H, fk.data_ptr(), fnn.data_ptr(), LC, 40.0,
+                                                              obj.data_ptr(), nobj.data_ptr(), stat.data_ptr(), cor.data_ptr(), lfn.data_ptr(),
+                                                              inf.data_ptr(), sdep.data_ptr(), sidx.data_ptr(), nst.data_ptr()))
+        rows.append({"stage": "line_corres", "ms": round(t, 4), "launches": 1, "lines_kept_per_frame": float(nst.float().mean().item())})
+    kp1 = arm.d_kps.data_ptr() + KC * 28; nk1 = arm.d_nkp.data_ptr() + 4
+    pst, pcor, pfn, pdep, pidx, npt = z(F, KC, 28), z(F, KC, 28), z(F, KC, 2, dt=f32), z(F, KC, dt=f32), z(F, KC, dt=i32), z(F, dt=i32)
+    t = timed("point_corres", lambda: post.point_corres_dev(dm.data_ptr(), dd.data_ptr(), df.data_ptr(), F, W, H, kp1, nk1, KC, 40.0, pst.data_ptr(),
+                                                            pcor.data_ptr(), pfn.data_ptr(), pdep.data_ptr(), pidx.data_ptr(), npt.data_ptr()))
+    rows.append({"stage": "point_corres", "ms": round(t, 4), "launches": 1, "points_kept_per_frame": float(npt.float().mean().item())})
+    cs, items = z(F, 64 * 48 + 1, dt=i32), z(F, KC, dt=i32)
+    t = timed("grid", lambda: post.grid_dev(F, W, H, kp1, nk1, KC, cs.data_ptr(), items.data_ptr(), 64, 48))
+    rows.append({"stage": "grid", "ms": round(t, 4), "launches": 1})
+    torch.cuda.synchronize()
+    return {"what": "Frame::Frame post-processing on the device over the step's frames (src/Frame.cc:349-389, 482-604, 728-809, 910-925), "
+                    "%d distinct mask / depth / flow plane sets; not inside the timed step" % nsc,
+            "total_ms": round(sum(r["ms"] for r in rows), 4), "stages": rows}
+
+
 def run_gpu(args, stages, cfg):
     import torch
     import torch.distributed as dist
@@ -530,8 +611,11 @@ def run_gpu(args, stages, cfg):
         dist.init_process_group("nccl", device_id=dev)
     pinned = torch.from_numpy(host).pin_memory()
     d_imgs = pinned.to(dev)
-    arm = ResidentArm(fe, torch, dev, local, cfg, stages, F, lead)
-    gather = shard.StatsGather(total, 8, torch.int32, dev)
+    # two arms (handles + buffers) used alternately: step k + 1's extraction does not wait for step k's matching and statistics
+    n_arms = 2 if (args.pipeline and F <= 1024) else 1
+    arms = [ResidentArm(fe, torch, dev, local, cfg, stages, F, lead) for _ in range(n_arms)]
+    gathers = [shard.StatsGather(total, 8, torch.int32, dev) for _ in range(n_arms)]
+    arm = arms[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -539,27 +623,41 @@ def run_gpu(args, stages, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_step(k):
+        a, g = arms[k % n_arms], gathers[k % n_arms]
+        st_ = a.step(d_imgs)
+        with torch.cuda.stream(a.s_tail):
+            g.start(st_)                    # NCCL all-gather of 32 B per frame: the only collective of the path (asynchronous)
+        return a
+
+    def drain():
+        for a, g in zip(arms, gathers):
+            a.wait()
+            g.table()
+
     # ---- device-resident throughput (`value`) ----
     nwarm = max(args.warmup, 3)
-    for _ in range(nwarm):
-        gather.start(arm.step(d_imgs))      # NCCL all-gather of 32 B per frame: the only collective of the path (asynchronous)
-    gather.table()
+    for k in range(nwarm):
+        run_step(k)
+    drain()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    arm.launches = 0
+    for a in arms:
+        a.launches = 0
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 2)]
     evs[0].record()
     for k in range(args.steps):
-        gather.start(arm.step(d_imgs))
-        evs[k + 1].record()
-    table = gather.table()                  # the current stream waits for the last gather
+        a = run_step(k)
+        evs[k + 1].record(a.s_tail)
+    drain()                                 # the current stream waits for both arms and their last gathers
+    table = gathers[(args.steps - 1) % n_arms].table()
     evs[args.steps + 1].record()
     barrier()
     ms = evs[0].elapsed_time(evs[args.steps + 1])
     step_ms = [evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)]
-    n_launch = arm.launches
+    n_launch = sum(a.launches for a in arms)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     mine = torch.tensor([float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms)), ms], dtype=torch.float64, device=dev)
@@ -577,8 +675,11 @@ def run_gpu(args, stages, cfg):
     rank_ms = {"per_rank_step_ms_median": [round(float(x), 3) for x in pr[:, 1]],
                "own_step_ms": {"min": round(float(pr[:, 0].min()), 3), "median": round(float(np.median(pr[:, 1])), 3), "max": round(float(pr[:, 2].max()), 3)},
                "per_rank_total_ms": [round(float(x), 3) for x in pr[:, 3]], "timed_ms_max_over_ranks": round(ms_max, 3),
-               "note": "a rank's own step = CUDA events around its extraction + matching + statistics (the asynchronous gather is not "
-                       "inside); region growing is data dependent, so ranks differ; timed_ms includes the wait for the last gather"}
+               "arms": n_arms,
+               "note": "a rank's own step = interval between the completions (CUDA events on the statistics stream) of consecutive steps; "
+                       "with two arms consecutive steps overlap (extraction of step k+1 behind matching / statistics of step k), so the first "
+                       "interval is longer than the rest; the asynchronous gather is not inside; region growing is data dependent, so ranks "
+                       "differ; timed_ms includes the wait for the last gather"}
 
     # ---- the sharded table must equal what ONE GPU computes for the same frames: rank 0 recomputes the first two frames of every
     #      other rank's shard (with their predecessor) and compares counts and 64-bit result digests with the gathered table ----
@@ -592,8 +693,9 @@ def run_gpu(args, stages, cfg):
                 continue
             small = ResidentArm(fe, torch, dev, local, cfg, stages, nchk, 1, handles=arm.handles())
             imgs_small = torch.from_numpy(synth.sequence(hs_, ss_ + nchk, H, W)).to(dev)
-            got = small.step(imgs_small).cpu().numpy()
+            got = small.step(imgs_small)
             torch.cuda.synchronize()
+            got = got.cpu().numpy()
             for j in range(nchk):
                 checked += 1
                 if not (got[j] == table[ss_ + j]).all():
@@ -607,6 +709,10 @@ def run_gpu(args, stages, cfg):
     peak, peak_src = _peaks()
     facts = _ncu_facts()
     stage_rows = stage_table(arm, d_imgs, cfg, peak, facts.get("stages", {}))
+    post_block = None
+    if rank == 0 and not args.no_post and cfg["baseline"] == 1:
+        post_block = post_stage_rows(fe, torch, dev, local, cfg, arm, peak, F)
+        torch.cuda.empty_cache()
     dom = max(stage_rows, key=lambda r: r["ms"]) if stage_rows else None
     roofline = None
     if dom:
@@ -626,9 +732,11 @@ def run_gpu(args, stages, cfg):
     frame_stats_mean = {"keypoints": float(st[:, 0].mean()), "keylines": float(st[:, 1].mean()),
                         "point_matches": float(st[:, 2].mean()), "line_matches": float(st[:, 3].mean())}
     if not args.no_e2e and full and args.scaling != "strong":
-        for hdl in arm.handles():
-            hdl.set_stream(0)
-        del arm
+        for a in arms:
+            for hdl in a.handles():
+                hdl.set_stream(0)
+        del arm, a
+        arms.clear()
         torch.cuda.empty_cache()
         oc, lc = cfg["orb"], cfg["line"]
         front = fe.FrontEnd(oc["nfeatures"], oc["scale"], oc["nlevels"], oc["ini"], oc["mn"], lc["nfeatures"],
@@ -679,7 +787,7 @@ def run_gpu(args, stages, cfg):
                "config": _config(stages, cfg, F, {"total_frames_per_step": total, "sharding": "shard.shard_with_halo (contiguous blocks)"}),
                "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch, "roofline": roofline,
                "cpu_baseline": cpu, "verified": verified, "latency": latency, "ranks": rank_ms, "sharding_check": shard_check,
-               "stages": stage_rows, "frame_stats_mean": frame_stats_mean}
+               "stages": stage_rows, "post": post_block, "frame_stats_mean": frame_stats_mean}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -767,7 +875,10 @@ def main():
     ap.add_argument("--stages", default="orb,line,match")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=1, help="1: two sets of handles / buffers used alternately so that consecutive steps overlap "
+                                                              "(when a GPU holds <= 1024 frames per step); 0: one set, steps strictly one after another")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-post", action="store_true", help="skip the Frame post-processing stage block (SURVEY 8f rows 1, 2)")
     ap.add_argument("--sweep", action="store_true", help="batch-size sweep {1, 8, 64, 512, 2048} through the host-buffer API (1 GPU)")
     ap.add_argument("--verify", type=int, default=8, help="frames of the last end-to-end batch compared with the oracle (0 = off)")
     args = ap.parse_args()

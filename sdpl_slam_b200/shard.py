@@ -73,6 +73,8 @@ class StatsGather:
         if not self.on:
             self.out[:stats.shape[0]].copy_(stats)
             return
+        if self.work is not None:
+            self.work.wait()                # the previous gather of this object has read `stats` / `pad` before they are rewritten
         src = stats
         if self.ragged:
             self.pad[:stats.shape[0]].copy_(stats)
