@@ -59,7 +59,7 @@ struct LineDev {
   lsd::SlotCtx* ctx; int grow_ta;      // per-task seed-slot contexts of the two-phase schedule; phase-A expansion cap
   uint8_t* g; short* sdx; short* sdy;
   int* err;
-  long long* prof;
+  long long* prof; int prof_detail;
   const double* lgam; int lgam_n;
   const double* nfa_tab;               // [nl][kNfaTabLevels][kNfaTabTri] (lsd::nfa_lookup), filled by k_nfa_table at set-up
   lsd::Rect* rob_rect; lsd::RobEntry* rob; int rob_w, rob_w_run;
@@ -389,7 +389,8 @@ __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::T
   T.pend = D.pend + (size_t)task * D.pend_cap; T.pend_cap = D.pend_cap; T.npend = D.npend + task;
   T.prec = D.prec; T.p = D.p; T.log_nt = O.log_nt; T.density_th = D.density_th; T.log_eps = D.log_eps; T.scale = D.scale;
   T.min_reg = O.min_reg; T.refine = D.refine; T.err = D.err;
-  T.prof = D.prof ? D.prof + (size_t)task * 8 : nullptr;
+  T.prof = D.prof ? D.prof + (size_t)task * 16 : nullptr;
+  T.prof_detail = D.prof_detail;
   T.lgam = D.lgam; T.lgam_n = D.lgam_n;
   T.nfa_tab = D.nfa_tab ? D.nfa_tab + (size_t)o * lsd::kNfaTabLevels * lsd::kNfaTabTri : nullptr;
   T.rob_rect = D.rob_rect + (size_t)task * D.rob_w; T.rob = D.rob + (size_t)task * D.rob_w; T.rob_w = D.rob_w_run;
@@ -1012,7 +1013,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->sdy.reserve(sizeof(short) * D.lbd_frame * B))) return rc;
   if ((rc = o->tmpkl.reserve(sizeof(sdpl_keyline) * (size_t)D.pend_cap * nl * (o->nfeatures ? B : 1)))) return rc;
   if ((rc = o->err.reserve(sizeof(int)))) return rc;
-  if ((rc = o->prof.reserve(sizeof(long long) * 8 * nl * B))) return rc;
+  if ((rc = o->prof.reserve(sizeof(long long) * 16 * nl * B))) return rc;
   if ((rc = o->robrect.reserve(sizeof(lsd::Rect) * (size_t)o->rob_w * nl * B))) return rc;
   if ((rc = o->rob.reserve(sizeof(lsd::RobEntry) * (size_t)o->rob_w * nl * B))) return rc;
   if ((rc = o->nbig.reserve(sizeof(int) * 2 * nl * B))) return rc;
@@ -1075,6 +1076,8 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   if (rc) return rc;
   LineDev& D = o->D;
   D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride; D.serial_mode = o->serial_mode; D.rob_w_run = o->rob_w_run;
+  D.prof_detail = o->timer.enabled ? 1 : 0;
+  if (D.prof_detail) SDPL_CUDA(cudaMemsetAsync(D.prof, 0, sizeof(long long) * 16 * o->nlevels * B, o->stream));
   cudaStream_t st = o->stream;
   const int nl = o->nlevels;
   o->timer.begin(st);
@@ -1461,7 +1464,7 @@ int sdpl_line_debug_grow_profile(sdpl_line* o, int frame, int octave, long long*
   if (!o || o->gw == 0 || frame < 0 || frame >= o->last_B || octave < 0 || octave >= o->nlevels || !out8) return SDPL_ERR_ARG;
   SDPL_CUDA(cudaSetDevice(o->device));
   SDPL_CUDA(cudaStreamSynchronize(o->stream));
-  SDPL_CUDA(cudaMemcpy(out8, o->D.prof + (size_t)(frame * o->nlevels + octave) * 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+  SDPL_CUDA(cudaMemcpy(out8, o->D.prof + (size_t)(frame * o->nlevels + octave) * 16, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
   return SDPL_OK;
 }
 

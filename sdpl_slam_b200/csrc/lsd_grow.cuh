@@ -63,7 +63,8 @@ struct Task {                      // one (frame, level)
   struct RobEntry* rob; Rect* rob_rect; int rob_w;   // re-order buffer (rob_w entries, power of two): metadata + rectangle staging
   const double* lgam; int lgam_n;  // log_gamma(i) for integer i < lgam_n (same formulas, tabulated once per handle)
   const double* nfa_tab;           // nfa(n, k, p / 2^j) of this octave for n <= kNfaTabN, j < kNfaTabLevels (or null): see nfa_lookup
-  long long* prof;                 // optional [8]: cycles in select / speculate / evaluate+commit / re-run, waves, re-runs, dead, seeds
+  int prof_detail;                 // != 0: warp 0 also accumulates prof[8..15] (phase A / B split, growth, rectangle fit, refine cycles, steps)
+  long long* prof;                 // optional [16]: [0..7] = cycles in select / speculate / evaluate+commit / re-run, waves, re-runs, dead, seeds
 };
 
 __device__ __forceinline__ double dist_sq(double x1, double y1, double x2, double y2) { return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1); }

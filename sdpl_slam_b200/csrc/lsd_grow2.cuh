@@ -81,6 +81,7 @@ __device__ __noinline__ bool coop_grow(const Task& T, const bool SPEC, int* cons
 #pragma unroll 1
   while (i < n) {
     const int m = min(4, n - i);
+    if (T.prof_detail && threadIdx.x == 0) T.prof[14] += 1;
     const bool act = j < m;
     const int p = list[i + (act ? j : 0)];
     const int qx = xy_x(p) + ndx, qy = xy_y(p) + ndy;
@@ -287,7 +288,9 @@ __device__ __noinline__ void seed_pipeline_coop(const Task& T, const bool SPEC, 
         sumdx = (float)cs; sumdy = (float)sn;
         __syncwarp();
       }
+      const long long pg0 = clock64();
       const bool ok = coop_grow(T, SPEC, cur, capc, n, i, sumdx, sumdy, ra, prec, stamp, bx0, by0, bx1, by1);
+      if (T.prof_detail && threadIdx.x == 0) T.prof[11] += clock64() - pg0;
       if (state == 0) { R.n1 = n; R.nf = n; } else { if (SPEC) R.n2_orig = n; R.nf = n; }
       if (!ok) { R.ok = 0; break; }
       if (state == 0 ? (n < T.min_reg) : (n < 2)) break;
@@ -311,11 +314,15 @@ __device__ __noinline__ void seed_pipeline_coop(const Task& T, const bool SPEC, 
       R.nf = n;
       if (n < 2) break;
     }
+    const long long pr0 = clock64();
     coop_region2rect_smem(T, sb, cur, n, ra, R.rec);
+    if (T.prof_detail && threadIdx.x == 0) T.prof[12] += clock64() - pr0;
     const double density = (double)n / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
     if (state == 0) {
       if (T.refine <= 0 || density >= T.density_th) { R.has_rect = 1; break; }
+      const long long pt0 = clock64();
       prec = SPEC ? coop_refine_tau<false>(T, cur, n, sx, sy, seed_ang, R.rec.width) : coop_refine_tau<true>(T, cur, n, sx, sy, seed_ang, R.rec.width);
+      if (T.prof_detail && threadIdx.x == 0) T.prof[13] += clock64() - pt0;
       __syncwarp();
       state = 1;
       if (SPEC) { cur = reg + n; capc = cap - n; R.foff = n; stamp = stamp0 | 1u; }   // the first region stays: it is part of E
@@ -548,7 +555,9 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
     const uint32_t stamp = (wave << 11) | ((uint32_t)(K - 1 - tid) << 1);   // bit0 = phase, 10 bits of seed priority
     // ---- phase A: lanes grow seeds for a few expansions, taking new seeds as they settle ----
     phase_a<NW>(T, ctx, S, nsel, cap, ta, wave);
+    const long long ca1 = clock64();
     __syncthreads();                                                                       // (A) every seed has a context
+    if (T.prof_detail && tid == 0) { T.prof[8] += ca1 - c1; T.prof[15] += clock64() - ca1; }
     // ---- the seeds that need phase B, in slot order ----
     {
       // unfinished growths (the long regions) first, then the finished ones that only want their rectangle: the queue is
@@ -571,6 +580,7 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
     // ---- phase B: warps take the queued seeds over, one at a time ----
     {
       const int qn = S.qn;
+      const long long cb0 = clock64();
       while (true) {
         int k = 0;
         if (lane == 0) k = atomicAdd(&S.qhead, 1);
@@ -592,8 +602,11 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
           if (R.has_rect) c.rec = R.rec;
         }
       }
+      if (T.prof_detail && tid == 0) T.prof[9] += clock64() - cb0;
     }
+    const long long cb1 = clock64();
     __syncthreads();                                                                       // (B) every seed of the wave has a result
+    if (T.prof_detail && tid == 0) T.prof[10] += clock64() - cb1;
     int r_ok = 0, r_n1 = 0, r_n2o = 0, r_nf = 0, r_foff = 0, r_rect = 0, r_bx0 = 0, r_by0 = 0, r_bx1 = 0, r_by1 = 0;
     if (have) {
       const SlotCtx& c = ctx[tid];

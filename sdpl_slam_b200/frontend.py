@@ -362,9 +362,10 @@ class Lineextractor(_Profiled):
         return out[:n.value].copy()
 
     def grow_profile(self, octave, frame=0):
-        out = np.zeros(8, np.int64)
+        out = np.zeros(16, np.int64)
         _check(self._L.sdpl_line_debug_grow_profile(self._h, frame, octave, _p(out)))
-        return dict(zip(("select", "speculate", "commit", "rerun", "waves", "reruns", "dead", "seeds"), out.tolist()))
+        return dict(zip(("select", "speculate", "commit", "rerun", "waves", "reruns", "dead", "seeds", "phaseA", "phaseB_busy", "phaseB_wait", "grow",
+                         "rect_fit", "refine_tau", "grow_steps", "phaseA_wait"), out.tolist()))
 
     def set_serial(self, on=True):
         """region-growing schedule: 0/False block-level speculative waves (default), 1/True one seed at a time, 2 re-order buffer,

@@ -20,4 +20,4 @@ for spec in sys.argv[2:]:
         ref = sig
     p = g.grow_profile(0, 0)
     print(spec, "grow ms %.2f" % st["lsd_grow"], "nfa %.2f" % st.get("lsd_nfa", 0), "same output as first:", sig == ref,
-          {k: (round(v / 1.9e3) if k in ("select", "speculate", "commit", "rerun") else v) for k, v in p.items()}, flush=True)
+          {k: (v if k in ("waves", "reruns", "dead", "seeds", "grow_steps") else round(v / 1.9e3)) for k, v in p.items()}, flush=True)
