@@ -276,6 +276,15 @@ int sdpl_post_line_corres_dev(sdpl_post* h, const int32_t* d_mask, const float* 
 int sdpl_post_grid_dev(sdpl_post* h, int nframes, int w, int h_, const sdpl_keypoint* d_kps, const int* d_n_in, int capacity, int grid_cols,
                        int grid_rows, int32_t* d_cell_start, int32_t* d_items, int sync);
 
+/* Frame::GetFeaturesInArea, src/Frame.cc:970-1023, on the grid of sdpl_post_grid_dev: d_queries = [nframes][nq][5] floats {x, y, r,
+ * minLevel, maxLevel} (maxLevel < 0: no upper bound); d_out[(f*nq + q)*max_out ..] = indices of frame f's key points with |dx| < r,
+ * |dy| < r and octave in range, in the order the reference visits them (cells ix-major, iy, then the cell's list);
+ * d_counts[f*nq + q] = how many there are (may exceed max_out).  The window search a projection / grid descriptor search starts
+ * from. */
+int sdpl_post_features_in_area_dev(sdpl_post* h, int nframes, int w, int h_, const sdpl_keypoint* d_kps, int capacity,
+                                   const int32_t* d_cell_start, const int32_t* d_items, int grid_cols, int grid_rows, const float* d_queries,
+                                   int nq, int32_t* d_out, int max_out, int* d_counts, int sync);
+
 /* Order-independent 64-bit digest of per-frame result rows resident on the device: adds, for every frame f, the sum of the
  * hashes of rows [0, min(d_n[f], max_rows)) of its block (row_bytes per row, a multiple of 4; blocks frame_stride bytes apart)
  * to d_digest[f] (DEVICE uint64 array the caller zeroes), asynchronously on `stream` (cudaStream_t as void*).  Used to check

@@ -102,6 +102,8 @@ int orc_post_point_corres(const orc_keypoint* kps, int n, const int32_t* mask, c
 int orc_post_line_corres(const orc_keyline* kls, int n, const int32_t* mask, const float* depth, const float* flow, int w, int h,
                          float th_depth, orc_keyline* obj, int32_t* n_obj, orc_keyline* stat, orc_keyline* corres, float* flow_next,
                          double* inf_line, float* stat_depth, int32_t* src_idx);
+int orc_post_features_in_area(const orc_keypoint* kps, int w, int h, int grid_cols, int grid_rows, const int32_t* cell_start,
+                              const int32_t* items, float x, float y, float r, int minLevel, int maxLevel, int32_t* out, int cap);
 void orc_post_grid(const orc_keypoint* kps, int n, int w, int h, int grid_cols, int grid_rows, int32_t* cell_start, int32_t* items);
 
 #ifdef __cplusplus

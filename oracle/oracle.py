@@ -350,3 +350,12 @@ def post_grid(kps, w, h, grid_cols=64, grid_rows=48):
     L = lib(); L.orc_post_grid.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p] * 2
     L.orc_post_grid(_p(kps), n, w, h, grid_cols, grid_rows, _p(cs), _p(items))
     return cs, items[:cs[-1]]
+
+
+def post_features_in_area(kps, w, h, cell_start, items, x, y, r, min_level=-1, max_level=-1, grid_cols=64, grid_rows=48):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    cs = np.ascontiguousarray(cell_start, np.int32); it = np.ascontiguousarray(items, np.int32)
+    out = np.zeros(max(len(kps), 1), np.int32)
+    L = lib(); L.orc_post_features_in_area.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_float] * 3 + [C.c_int] * 2 + [C.c_void_p, C.c_int]
+    n = L.orc_post_features_in_area(_p(kps), w, h, grid_cols, grid_rows, _p(cs), _p(it), x, y, r, min_level, max_level, _p(out), len(out))
+    return out[:n]

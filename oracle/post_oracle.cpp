@@ -14,6 +14,7 @@
 //   pow(int, 2), sqrt(double)  computed in double, then narrowed to float on assignment              (:371)
 //   j + flow_x                 int + float -> float                                                   (:792)
 #include "oracle.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -185,6 +186,41 @@ void orc_post_grid(const orc_keypoint* kps, int n, int w, int h, int grid_cols, 
     for (int v : grid[c]) items[k++] = v;
   }
   cell_start[grid.size()] = k;
+}
+
+/* Frame::GetFeaturesInArea, src/Frame.cc:970-1023, on the grid of orc_post_grid: indices of the key points inside the square window
+   |dx| < r, |dy| < r around (x, y) with octave in [minLevel, maxLevel] (maxLevel < 0: no upper bound), in the order the reference
+   visits them: cells ix-major, then iy, then push_back order inside a cell.  Returns the count (only cap are written). */
+int orc_post_features_in_area(const orc_keypoint* kps, int w, int h, int grid_cols, int grid_rows, const int32_t* cell_start,
+                              const int32_t* items, float x, float y, float r, int minLevel, int maxLevel, int32_t* out, int cap) {
+  const float mnMinX = 0.f, mnMaxX = (float)w, mnMinY = 0.f, mnMaxY = (float)h;
+  const float wInv = static_cast<float>(grid_cols) / static_cast<float>(mnMaxX - mnMinX);
+  const float hInv = static_cast<float>(grid_rows) / static_cast<float>(mnMaxY - mnMinY);
+  int n = 0;
+  const int nMinCellX = std::max(0, (int)std::floor((x - mnMinX - r) * wInv));
+  if (nMinCellX >= grid_cols) return 0;
+  const int nMaxCellX = std::min(grid_cols - 1, (int)std::ceil((x - mnMinX + r) * wInv));
+  if (nMaxCellX < 0) return 0;
+  const int nMinCellY = std::max(0, (int)std::floor((y - mnMinY - r) * hInv));
+  if (nMinCellY >= grid_rows) return 0;
+  const int nMaxCellY = std::min(grid_rows - 1, (int)std::ceil((y - mnMinY + r) * hInv));
+  if (nMaxCellY < 0) return 0;
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+    for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+      const int c = ix * grid_rows + iy;
+      for (int j = cell_start[c]; j < cell_start[c + 1]; j++) {
+        const orc_keypoint& kpUn = kps[items[j]];
+        if (bCheckLevels) {
+          if (kpUn.octave < minLevel) continue;
+          if (maxLevel >= 0)
+            if (kpUn.octave > maxLevel) continue;
+        }
+        const float distx = kpUn.x - x, disty = kpUn.y - y;
+        if (std::fabs(distx) < r && std::fabs(disty) < r) { if (n < cap) out[n] = items[j]; n++; }
+      }
+    }
+  return n;
 }
 
 }  // extern "C"

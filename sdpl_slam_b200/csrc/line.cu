@@ -853,6 +853,8 @@ struct sdpl_line {
   float lsd_scale, scale;
   std::vector<float> sf, isf;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t side = nullptr;                 // the warp-per-rectangle NFA kernel runs here, beside the per-thread second pass
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
   DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
@@ -1152,13 +1154,20 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   SDPL_CUDA(cudaMemsetAsync(D.nbig, 0, sizeof(int) * 2 * nl * B, st));
   k_lsd_nfa<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
-  k_lsd_nfa_big<<<dim3(64, nl * B), 128, 0, st>>>(D);
+  // the big rectangles (one warp each, few and long: a latency-bound kernel at 6 % occupancy) and the second pass over the small
+  // ones work on disjoint lists: side by side, unless the stages are being timed one after another
+  const bool fork = !o->timer.enabled;
+  cudaStream_t sb = fork ? o->side : st;
+  if (fork) { SDPL_CUDA(cudaEventRecord(o->ev_fork, st)); SDPL_CUDA(cudaStreamWaitEvent(sb, o->ev_fork, 0)); }
+  k_lsd_nfa_big<<<dim3(64, nl * B), 128, 0, sb>>>(D);
   SDPL_LAUNCH_CHECK();
+  if (fork) SDPL_CUDA(cudaEventRecord(o->ev_join, sb));
   if (o->nfa_minb >= 16) k_lsd_nfa_rest<16><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
   else if (o->nfa_minb >= 12) k_lsd_nfa_rest<12><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
   else if (o->nfa_minb >= 10) k_lsd_nfa_rest<10><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
   else k_lsd_nfa_rest<8><<<dim3(kRestBlocks, nl * B), 128, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
+  if (fork) SDPL_CUDA(cudaStreamWaitEvent(st, o->ev_join, 0));
   o->timer.mark(st, "lsd_nfa");
   k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());
   SDPL_LAUNCH_CHECK();
@@ -1239,6 +1248,9 @@ int sdpl_line_create(sdpl_line** out, int nfeatures, int refine, float lsd_scale
   cudaDeviceGetAttribute(&o->sm_count, cudaDevAttrMultiProcessorCount, device);
   SDPL_CUDA(cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking));
   o->stream = o->own_stream;
+  SDPL_CUDA(cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking));
+  SDPL_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming));
+  SDPL_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
   *out = o;
   return SDPL_OK;
 }
@@ -1253,6 +1265,9 @@ void sdpl_line_destroy(sdpl_line* o) {
   if (o->h_stage) cudaFreeHost(o->h_stage);
   o->timer.release();
   if (o->own_stream) cudaStreamDestroy(o->own_stream);
+  if (o->side) cudaStreamDestroy(o->side);
+  if (o->ev_fork) cudaEventDestroy(o->ev_fork);
+  if (o->ev_join) cudaEventDestroy(o->ev_join);
   delete o;
 }
 

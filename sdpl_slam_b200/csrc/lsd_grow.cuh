@@ -1436,14 +1436,14 @@ __device__ __forceinline__ bool double_equal(double a, double b) {
   return (ad / mx) <= (100.0 * 2.220446049250313e-16);
 }
 
-__device__ __forceinline__ double log_gamma_int(const Task& T, int i) { return i < T.lgam_n ? T.lgam[i] : log_gamma((double)i); }
-
-__device__ __noinline__ double nfa(const Task& T, int n, int k, double p) {
-  const double log_nt = T.log_nt;
+// everything nfa() needs from the task goes by value: a `const Task&` parameter of an out-of-line function would force the whole task
+// descriptor of the calling kernel into local memory
+__device__ __noinline__ double nfa_v(const double log_nt, const double* __restrict__ lgam, const int lgam_n, int n, int k, double p) {
+  auto log_gamma_int = [&](int i) { return i < lgam_n ? lgam[i] : log_gamma((double)i); };
   if (n == 0 || k == 0) return -log_nt;
   if (n == k) return -log_nt - (double)n * log10(p);
   const double p_term = p / (1 - p);
-  const double log1term = log_gamma_int(T, n + 1) - log_gamma_int(T, k + 1) - log_gamma_int(T, n - k + 1) + (double)k * log(p) +
+  const double log1term = log_gamma_int(n + 1) - log_gamma_int(k + 1) - log_gamma_int(n - k + 1) + (double)k * log(p) +
                           (double)(n - k) * log(1.0 - p);
   double term = exp(log1term);
   if (double_equal(term, 0)) {
@@ -1479,6 +1479,7 @@ __device__ __noinline__ double nfa(const Task& T, int n, int k, double p) {
   }
   return -log10(bin_tail) - log_nt;
 }
+__device__ __forceinline__ double nfa(const Task& T, int n, int k, double p) { return nfa_v(T.log_nt, T.lgam, T.lgam_n, n, k, p); }
 
 // nfa(n, k, p) depends on two small integers, on p -- which rect_improve only ever halves, starting from T.p, at most ten times --
 // and on the octave's log_nt.  The values for n <= kNfaTabN are therefore tabulated once per handle and geometry BY THIS VERY
@@ -1501,19 +1502,27 @@ __device__ __forceinline__ double nfa_lookup(const Task& T, int n, int k, double
 // traversal gives the oracle's totals.  COOP = false: one thread per rectangle; COOP = true: one warp per rectangle (lanes
 // over rows for tall rectangles, over columns otherwise; the NFA itself is evaluated by lane 0 and broadcast).
 template <bool COOP>
-__device__ __noinline__ double rect_nfa(const Task& T, const Rect& rec) {
+__device__ __forceinline__ double rect_nfa_body(const Task& T, const Rect& rec) {
   const int lane = COOP ? (threadIdx.x & 31) : 0;
   const double hw = rec.width / 2.0;
   const double dyhw = rec.dy * hw, dxhw = rec.dx * hw;
-  double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
-  double vy[4] = {rec.y1 + dxhw, rec.y2 + dxhw, rec.y2 - dxhw, rec.y1 - dxhw};
+  // the four corners, rotated so that the one with the smallest y (then x) comes first.  Everything stays in scalars: an array
+  // indexed by the rotation would live in local memory (the second pass wrote 2.7 MB of it per frame to DRAM)
+  const double vx0 = rec.x1 - dyhw, vx1 = rec.x2 - dyhw, vx2 = rec.x2 + dyhw, vx3 = rec.x1 + dyhw;
+  const double vy0 = rec.y1 + dxhw, vy1 = rec.y2 + dxhw, vy2 = rec.y2 - dxhw, vy3 = rec.y1 - dxhw;
   int off = 0;
-#pragma unroll
-  for (int i = 1; i < 4; ++i)
-    if (vy[i] < vy[off] || (vy[i] == vy[off] && vx[i] < vx[off])) off = i;
-  double px[4], py[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { px[i] = vx[(i + off) & 3]; py[i] = vy[(i + off) & 3]; }
+  {
+    double by = vy0, bx = vx0;
+    if (vy1 < by || (vy1 == by && vx1 < bx)) { off = 1; by = vy1; bx = vx1; }
+    if (vy2 < by || (vy2 == by && vx2 < bx)) { off = 2; by = vy2; bx = vx2; }
+    if (vy3 < by || (vy3 == by && vx3 < bx)) { off = 3; }
+  }
+  const bool o1 = off & 1, o2 = (off & 2) != 0;
+  // element (i + off) & 3: first rotate by one if bit 0 is set, then by two if bit 1 is set
+  const double ax0 = o1 ? vx1 : vx0, ax1 = o1 ? vx2 : vx1, ax2 = o1 ? vx3 : vx2, ax3 = o1 ? vx0 : vx3;
+  const double ay0 = o1 ? vy1 : vy0, ay1 = o1 ? vy2 : vy1, ay2 = o1 ? vy3 : vy2, ay3 = o1 ? vy0 : vy3;
+  const double px[4] = {o2 ? ax2 : ax0, o2 ? ax3 : ax1, o2 ? ax0 : ax2, o2 ? ax1 : ax3};
+  const double py[4] = {o2 ? ay2 : ay0, o2 ? ay3 : ay1, o2 ? ay0 : ay2, o2 ? ay1 : ay3};
   const int c0 = (int)ceil(py[0]), c1 = (int)ceil(py[1]), c2 = (int)ceil(py[2]), c3 = (int)ceil(py[3]);
   const double flstep = (c1 != c0) ? (px[1] - px[0]) / (py[1] - py[0]) : 0.0;
   const double slstep = (c2 != c1) ? (px[2] - px[1]) / (py[2] - py[1]) : 0.0;
@@ -1541,6 +1550,11 @@ __device__ __noinline__ double rect_nfa(const Task& T, const Rect& rec) {
   if (lane == 0) v = nfa_lookup(T, total, alg, rec.p);
   return __shfl_sync(0xffffffffu, v, 0);
 }
+
+// out-of-line copy for the callers with many call sites (rect_improve_rest); the per-thread passes, which call it from ONE place,
+// use the body directly so that neither the rectangle nor the task descriptor has to live in local memory
+template <bool COOP>
+__device__ __noinline__ double rect_nfa(const Task& T, const Rect& rec) { return rect_nfa_body<COOP>(T, rec); }
 
 // rect_improve after its first evaluation (log_nfa = rect_nfa(rec) <= log_eps): the 25 refinement attempts
 template <bool COOP>
@@ -1612,7 +1626,7 @@ __device__ __forceinline__ void write_segment(const Task& T, int i, const Rect& 
 __device__ bool validate_first(const Task& T, int i) {
   const Rect rec = T.pend[i].rec;
   if (T.refine < 2) { write_segment(T, i, rec, true); return true; }
-  const double v = rect_nfa<false>(T, rec);
+  const double v = rect_nfa_body<false>(T, rec);
   if (v > T.log_eps) { write_segment(T, i, rec, true); return true; }
   *reinterpret_cast<double*>(T.pend[i].seg) = v;
   return false;
@@ -1676,7 +1690,7 @@ __device__ void validate_rest_warp(const Task& T, const int* back, int nf, int f
     if (busy) {
       Rect r = rec;
       have = rect_variation(stage, var, r) ? 1 : 0;
-      if (have) v = rect_nfa<false>(T, r);
+      if (have) v = rect_nfa_body<false>(T, r);
     }
     int best = -1;
     double bv = log_nfa;

@@ -302,6 +302,50 @@ __global__ void __launch_bounds__(256) k_grid(const sdpl_keypoint* __restrict__ 
   }
 }
 
+// P6: Frame::GetFeaturesInArea (Frame.cc:970-1023) on the grid of P5.  One warp per query: the cells of the window are visited in
+// the reference's order (ix, then iy, then the cell's list), 32 list entries at a time, and the hits are appended in that order with
+// a ballot -- what the reference's push_back gives.  query = {x, y, r, minLevel, maxLevel} (five floats)
+__global__ void __launch_bounds__(128) k_features_in_area(const sdpl_keypoint* __restrict__ kps, int capacity, const int32_t* __restrict__ cell_start,
+                                                          const int32_t* __restrict__ items, int w, int h, int gcols, int grows,
+                                                          const float* __restrict__ queries, int nq, int32_t* __restrict__ out, int max_out,
+                                                          int* __restrict__ counts) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const float* Q = queries + ((size_t)f * nq + q) * 5;
+  const float x = Q[0], y = Q[1], r = Q[2];
+  const int minLevel = (int)Q[3], maxLevel = (int)Q[4];
+  const float wInv = __fdiv_rn((float)gcols, (float)w), hInv = __fdiv_rn((float)grows, (float)h);
+  const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(x, r), wInv))), x1 = min(gcols - 1, (int)ceilf(__fmul_rn(__fadd_rn(x, r), wInv)));
+  const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(y, r), hInv))), y1 = min(grows - 1, (int)ceilf(__fmul_rn(__fadd_rn(y, r), hInv)));
+  int n = 0;
+  if (!(x0 >= gcols || x1 < 0 || y0 >= grows || y1 < 0)) {
+    const bool check = minLevel > 0 || maxLevel >= 0;
+    const int32_t* cs = cell_start + (size_t)f * (gcols * grows + 1);
+    const int32_t* it = items + (size_t)f * capacity;
+    const sdpl_keypoint* K = kps + (size_t)f * capacity;
+    int32_t* o = out + ((size_t)f * nq + q) * max_out;
+    for (int ix = x0; ix <= x1; ix++) {
+      // the cells (ix, y0 .. y1) are adjacent in the cell array: one contiguous run of the item list
+      const int j0 = cs[ix * grows + y0], j1 = cs[ix * grows + y1 + 1];
+      for (int jb = j0; jb < j1; jb += 32) {
+        const int j = jb + lane;
+        bool hit = false; int idx = 0;
+        if (j < j1) {
+          idx = it[j];
+          const sdpl_keypoint kp = K[idx];
+          const bool lvl = !check || (kp.octave >= minLevel && (maxLevel < 0 || kp.octave <= maxLevel));
+          hit = lvl && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (hit) { const int s = n + __popc(m & ((1u << lane) - 1u)); if (s < max_out) o[s] = idx; }
+        n += __popc(m);
+      }
+    }
+  }
+  if (lane == 0) counts[(size_t)f * nq + q] = n;
+}
+
 }  // namespace sdpl
 
 using namespace sdpl;
@@ -448,6 +492,23 @@ int sdpl_post_grid_dev(sdpl_post* p, int nframes, int w, int h, const sdpl_keypo
                                                                                   p->cellof.as<int32_t>());
   SDPL_LAUNCH_CHECK();
   p->timer.mark(p->stream, "grid");
+  p->launches = g_launches;
+  if (sync) SDPL_CUDA(cudaStreamSynchronize(p->stream));
+  return SDPL_OK;
+}
+
+int sdpl_post_features_in_area_dev(sdpl_post* p, int nframes, int w, int h, const sdpl_keypoint* d_kps, int capacity, const int32_t* d_cell_start,
+                                   const int32_t* d_items, int grid_cols, int grid_rows, const float* d_queries, int nq, int32_t* d_out, int max_out,
+                                   int* d_counts, int sync) {
+  if (!p || nframes < 1 || w < 1 || h < 1 || !d_kps || capacity < 1 || !d_cell_start || !d_items || grid_cols < 1 || grid_rows < 1 || !d_queries ||
+      nq < 1 || !d_out || max_out < 1 || !d_counts) { set_last_error("sdpl_post_features_in_area_dev: bad argument"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(p->device));
+  g_launches = 0;
+  p->timer.begin(p->stream);
+  k_features_in_area<<<dim3(div_up(nq, 4), nframes), 128, 0, p->stream>>>(d_kps, capacity, d_cell_start, d_items, w, h, grid_cols, grid_rows, d_queries, nq,
+                                                                          d_out, max_out, d_counts);
+  SDPL_LAUNCH_CHECK();
+  p->timer.mark(p->stream, "features_in_area");
   p->launches = g_launches;
   if (sync) SDPL_CUDA(cudaStreamSynchronize(p->stream));
   return SDPL_OK;

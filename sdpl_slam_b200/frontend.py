@@ -122,6 +122,7 @@ def load_library(path=None):
     L.sdpl_post_point_corres_dev.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, i, f, vp, vp, vp, vp, vp, vp, i]
     L.sdpl_post_line_corres_dev.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, i, f, vp, vp, vp, vp, vp, vp, vp, vp, vp, i]
     L.sdpl_post_grid_dev.argtypes = [vp, i, i, i, vp, vp, i, i, i, vp, vp, i]
+    L.sdpl_post_features_in_area_dev.argtypes = [vp, i, i, i, vp, i, vp, vp, i, i, vp, i, vp, i, vp, i]
     L.sdpl_rows_digest_dev.argtypes = [vp, i, sz, vp, i, i, C.c_ulonglong, vp, vp]
     if path is None:
         _lib = L
@@ -638,6 +639,14 @@ class FramePost(_Profiled):
         v = C.c_void_p
         _check(self._L.sdpl_post_grid_dev(self._h, nframes, w, h, v(d_kps), v(d_n_in), capacity, grid_cols, grid_rows, v(d_cell_start),
                                           v(d_items), int(sync)))
+
+
+    def features_in_area_dev(self, nframes, w, h, d_kps, capacity, d_cell_start, d_items, d_queries, nq, d_out, max_out, d_counts, grid_cols=64,
+                             grid_rows=48, sync=False):
+        """Frame::GetFeaturesInArea for nq queries {x, y, r, minLevel, maxLevel} per frame (device pointers)."""
+        v = C.c_void_p
+        _check(self._L.sdpl_post_features_in_area_dev(self._h, nframes, w, h, v(d_kps), capacity, v(d_cell_start), v(d_items), grid_cols, grid_rows,
+                                                      v(d_queries), nq, v(d_out), max_out, v(d_counts), int(sync)))
 
 
 def rows_digest_dev(d_rows, row_bytes, frame_stride, d_n, nframes, max_rows, salt, d_digest, cuda_stream=0):

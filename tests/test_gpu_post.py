@@ -112,3 +112,22 @@ def test_feature_post_processing_on_device_resident_extractor_output(frontend, o
         assert (pidx[f, :k].cpu().numpy() == wp["src_idx"]).all()
         wcs, witems = oracle.post_grid(okps, W, H)
         assert (cs[f].cpu().numpy() == wcs).all() and (items[f, :len(witems)].cpu().numpy() == witems).all()
+    # ---- GetFeaturesInArea on the device grid: 64 random windows per frame, hits in the reference's visiting order ----
+    rng = np.random.default_rng(5)
+    NQ, MAXO = 64, 256
+    qs = np.zeros((B, NQ, 5), np.float32)
+    qs[..., 0] = rng.uniform(-30, W + 30, (B, NQ)); qs[..., 1] = rng.uniform(-30, H + 30, (B, NQ)); qs[..., 2] = rng.uniform(2, 80, (B, NQ))
+    qs[..., 3] = rng.integers(-1, 4, (B, NQ)); qs[..., 4] = rng.integers(-1, 8, (B, NQ))
+    dq = _dev(torch, qs); hits, cnt = z(B, NQ, MAXO, dt=i32), z(B, NQ, dt=i32)
+    post.features_in_area_dev(B, W, H, kps.data_ptr(), KC, cs.data_ptr(), items.data_ptr(), dq.data_ptr(), NQ, hits.data_ptr(), MAXO, cnt.data_ptr(),
+                              64, 48, True)
+    hits, cnt = hits.cpu().numpy(), cnt.cpu().numpy()
+    nonempty = 0
+    for f in range(B):
+        okps, _ = oorb(imgs[f]); wcs, witems = oracle.post_grid(okps, W, H)
+        for q in range(NQ):
+            want = oracle.post_features_in_area(okps, W, H, wcs, witems, *[float(v) for v in qs[f, q, :3]], int(qs[f, q, 3]), int(qs[f, q, 4]))
+            assert cnt[f, q] == len(want)
+            k = min(MAXO, len(want)); nonempty += k > 0
+            assert (hits[f, q, :k] == want[:k]).all()
+    assert nonempty > B * NQ // 3

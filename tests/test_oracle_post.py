@@ -91,3 +91,30 @@ def test_grid_equals_numpy(oracle):
     for c in (0, 17, 1000, 3071):
         np.testing.assert_array_equal(items[cs[c]:cs[c + 1]], want[c])
     np.testing.assert_array_equal(np.concatenate(want), items)
+
+
+def test_features_in_area_equals_brute_force(oracle):
+    """Frame::GetFeaturesInArea on the oracle's grid: the hits are exactly the key points inside the open square window with an
+    admissible octave, ordered by (grid column, grid row, index) -- the order the reference's cell loops visit them."""
+    kps, _ = _frame_features(oracle, 8)
+    cs, items = oracle.post_grid(kps, W, H)
+    px = np.round(kps["x"] * (np.float32(64) / np.float32(W))).astype(np.int32); py = np.round(kps["y"] * (np.float32(48) / np.float32(H))).astype(np.int32)
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        x, y, r = np.float32(rng.uniform(-20, W + 20)), np.float32(rng.uniform(-20, H + 20)), np.float32(rng.uniform(1, 60))
+        lo, hi = int(rng.integers(-1, 4)), int(rng.integers(-1, 8))
+        got = oracle.post_features_in_area(kps, W, H, cs, items, float(x), float(y), float(r), lo, hi)
+        inside = (np.abs(kps["x"] - x) < r) & (np.abs(kps["y"] - y) < r)
+        if lo > 0 or hi >= 0:
+            inside &= kps["octave"] >= lo
+            if hi >= 0:
+                inside &= kps["octave"] <= hi
+        # a key point whose grid cell lies outside the cells the window covers is not found (the reference's cell arithmetic rounds
+        # positions to the NEAREST cell but floors / ceils the window): reproduce the cell range
+        wInv, hInv = np.float32(64) / np.float32(W), np.float32(48) / np.float32(H)
+        x0, x1 = max(0, int(np.floor((x - r) * wInv))), min(63, int(np.ceil((x + r) * wInv)))
+        y0, y1 = max(0, int(np.floor((y - r) * hInv))), min(47, int(np.ceil((y + r) * hInv)))
+        inside &= (px >= x0) & (px <= x1) & (py >= y0) & (py <= y1) & (px >= 0) & (px < 64) & (py >= 0) & (py < 48)
+        want = np.nonzero(inside)[0]
+        want = want[np.lexsort((want, py[want], px[want]))]
+        np.testing.assert_array_equal(got, want)
