@@ -113,9 +113,11 @@ int sdpl_line_lsd_segments(sdpl_line* h, int frame, int octave, float* xyxy, int
 /* introspection: rectangles handed to the NFA stage in seed order, 8 doubles each {x1,y1,x2,y2,width,p,accepted,tag} */
 int sdpl_line_debug_pending(sdpl_line* h, int frame, int octave, double* out, int capacity, int* n_out);
 /* introspection: region-growing kernel counters of one (frame, octave): cycles in {select, speculate, evaluate+commit, re-run},
- * then {waves, re-runs, dead seeds, seeds}; with profiling on, [8..15] = thread 0's cycles in {phase A, phase B busy, phase B
+ * then {waves, re-runs, dead seeds, seeds}; after sdpl_line_debug_grow_detail(h, 1), [8..15] = thread 0's cycles in {phase A, phase B busy, phase B
  * barrier wait, region growth, rectangle fits, refine tolerance}, its growth steps and its wait at the phase-A barrier */
 int sdpl_line_debug_grow_profile(sdpl_line* h, int frame, int octave, long long* out16);
+/* switch the detailed counters [8..15] on / off (off by default: they cost about 3 % of the region-growing kernel) */
+int sdpl_line_debug_grow_detail(sdpl_line* h, int on);
 int sdpl_line_last_launches(const sdpl_line* h);
 /* test / tuning knob, LSD region-growing schedule (bits 0-1; bits 8.. an optional size override): 0 = speculative waves of
  * 32*NW seeds, one CTA of NW warps per (frame, octave) (default, NW = 4), 1 = strictly one seed at a time, 2 = speculative with

@@ -8,11 +8,11 @@
  * bit-exact integer/float formulas.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * Parity status: the reference ships no tests/golden vectors for this path and cannot
- * be compiled here (needs OpenCV 3.4 C++).  The oracle is pinned against the outputs of
- * the OpenCV primitives themselves (python cv2 4.13 in the build container, see
- * tests/test_oracle_vs_cv2.py and tests/golden/) -- "parity pinned at the OpenCV
- * primitive boundary, unpinned against a compiled reference binary".
+ * Parity status: PINNED for the extractor / matcher path -- against the reference's own sources compiled unmodified over an
+ * OpenCV stand-in (oracle/refshim -> oracle/_ref/libsdpl_ref.so, tests/test_oracle_vs_ref.py: byte for byte on every BASELINE
+ * geometry) and, at the OpenCV-primitive boundary, against python cv2 4.13 (tests/test_oracle_vs_cv2.py, tests/golden/).
+ * The Frame post-processing functions (post_oracle.cpp) are "parity unpinned": Frame.cc cannot be compiled here; they are
+ * checked against an independent numpy restatement (tests/test_oracle_post.py).
  */
 #ifndef SDPL_ORACLE_H
 #define SDPL_ORACLE_H

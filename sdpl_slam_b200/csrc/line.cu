@@ -57,7 +57,7 @@ struct LineDev {
   uint32_t* hist; int* maxg2; int* ndef; int* task_order;
   int* reg; lsd::Pending* pend; int pend_cap; int* npend;
   lsd::SlotCtx* ctx; int grow_ta;      // per-task seed-slot contexts of the two-phase schedule; phase-A expansion cap
-  uint8_t* g; short* sdx; short* sdy;
+  uint8_t* g; short2* sd;               // LBD: Gaussian octaves; Sobel (dx, dy) pairs of every pixel (one 4-byte gather per sample in k_lbd)
   int* err;
   long long* prof; int prof_detail;
   const double* lgam; int lgam_n;
@@ -318,22 +318,37 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_lsd_sort(LineDev D, int o) 
   const int* g2 = D.g2 + (size_t)f * D.px_frame + O.px_off;
   uint32_t* order = D.order + (size_t)f * D.px_frame + O.px_off;
   const int p0 = chunk * kSortChunk, p1 = min(p0 + kSortChunk, O.npx);
-  for (int pb = p0; pb < p1; pb += 32) {
-    const int p = pb + lane;
-    const int g = p < p1 ? g2[p] : -1;
-    const bool def = g >= 0;
-    const int b = def ? (kBins - 1 - lsd_bin(g, bin_coef)) : -1;      // descending bins
-    const uint32_t act = __ballot_sync(0xffffffffu, def);
-    if (def) {
-      const uint32_t peers = __match_any_sync(act, b);
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      const int leader = __ffs(peers) - 1;
-      uint32_t base = 0;
-      if (lane == leader) { base = c[b]; c[b] = base + __popc(peers); }
-      base = __shfl_sync(peers, base, leader);
-      if (SCATTER) order[base + rank] = (uint32_t)p;
+  // four groups of 32 pixels per trip: the four loads (and the square roots behind them) are in flight together; the ranking
+  // steps then run group after group, which is what keeps the order stable (ncu on the one-group loop: 2400 cycles per trip,
+  // a DRAM round trip in front of every dependent ranking step)
+  for (int pb = p0; pb < p1; pb += 128) {
+    int g[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const int p = pb + 32 * u + lane; g[u] = p < p1 ? g2[p] : -1; }
+    int bq[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) bq[u] = g[u] >= 0 ? (kBins - 1 - lsd_bin(g[u], bin_coef)) : -1;      // descending bins
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int p = pb + 32 * u + lane;
+      const bool def = g[u] >= 0;
+      const int b = bq[u];
+      if (!SCATTER) {                      // counting only: the order inside the group does not matter
+        if (def) atomicAdd(&c[b], 1u);
+        continue;
+      }
+      const uint32_t act = __ballot_sync(0xffffffffu, def);
+      if (def) {
+        const uint32_t peers = __match_any_sync(act, b);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) { base = c[b]; c[b] = base + __popc(peers); }
+        base = __shfl_sync(peers, base, leader);
+        if (SCATTER) order[base + rank] = (uint32_t)p;
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   if (!SCATTER) {
     __syncwarp();
@@ -651,8 +666,7 @@ __global__ void __launch_bounds__(256) k_lbd_blur_sobel(LineDev D) {
   __syncthreads();
   // Sobel 3x3 on the blurred tile: dx(c) = A(c+1) - A(c-1), A = r0 + 2 r1 + r2;  dy(c) = B(c-1) + 2 B(c) + B(c+1), B = r2 - r0
   {
-    short* dxo = D.sdx + (size_t)f * D.lbd_frame + O.lbd_off;
-    short* dyo = D.sdy + (size_t)f * D.lbd_frame + O.lbd_off;
+    short2* sdo = D.sd + (size_t)f * D.lbd_frame + O.lbd_off;
     for (int i = threadIdx.x; i < kLT_H * (kLT_W / 4); i += 256) {
       const int r = i / (kLT_W / 4), m = 1 + (i - r * (kLT_W / 4));
       const int y = y0 + r, x = x0 + 4 * (m - 1);
@@ -670,14 +684,15 @@ __global__ void __launch_bounds__(256) k_lbd_blur_sobel(LineDev D) {
 #pragma unroll
       for (int e = 0; e < 4; e++) { gx[e] = (short)(A[e + 2] - A[e]); gy[e] = (short)(Bv[e] + 2 * Bv[e + 1] + Bv[e + 2]); }
       const size_t q = (size_t)y * W + x;
-      if (x + 3 < W && ((q & 1) == 0)) {
-        *(uint32_t*)(dxo + q) = (uint32_t)(uint16_t)gx[0] | ((uint32_t)(uint16_t)gx[1] << 16);
-        *(uint32_t*)(dxo + q + 2) = (uint32_t)(uint16_t)gx[2] | ((uint32_t)(uint16_t)gx[3] << 16);
-        *(uint32_t*)(dyo + q) = (uint32_t)(uint16_t)gy[0] | ((uint32_t)(uint16_t)gy[1] << 16);
-        *(uint32_t*)(dyo + q + 2) = (uint32_t)(uint16_t)gy[2] | ((uint32_t)(uint16_t)gy[3] << 16);
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) pk[e] = (uint32_t)(uint16_t)gx[e] | ((uint32_t)(uint16_t)gy[e] << 16);
+      if (x + 3 < W && ((q & 1) == 0)) {                      // 8-byte aligned: two pixel pairs
+        *(uint2*)(sdo + q) = make_uint2(pk[0], pk[1]);
+        *(uint2*)(sdo + q + 2) = make_uint2(pk[2], pk[3]);
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; e++) if (x + e < W) { dxo[q + e] = gx[e]; dyo[q + e] = gy[e]; }
+        for (int e = 0; e < 4; e++) if (x + e < W) *(uint32_t*)(sdo + q + e) = pk[e];
       }
     }
   }
@@ -716,8 +731,7 @@ __global__ void __launch_bounds__(256) k_lbd_sobel(LineDev D, int o) {
   const int gx = ((int)r0[xp] - r0[xm]) + 2 * ((int)r1[xp] - r1[xm]) + ((int)r2[xp] - r2[xm]);
   const int gy = ((int)r2[xm] + 2 * r2[x] + r2[xp]) - ((int)r0[xm] + 2 * r0[x] + r0[xp]);
   const size_t q = (size_t)f * D.lbd_frame + O.lbd_off + (size_t)y * w + x;
-  D.sdx[q] = (short)gx;
-  D.sdy[q] = (short)gy;
+  D.sd[q] = make_short2((short)gx, (short)gy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -741,8 +755,7 @@ __global__ void __launch_bounds__(64) k_lbd(LineDev D, const sdpl_keyline* __res
   const int o = min(max(kl.octave, 0), D.nl - 1);
   const OctDev& O = D.O[o];
   const int realWidth = O.lw, realHeight = O.lh;
-  const short* dxImg = D.sdx + (size_t)f * D.lbd_frame + O.lbd_off;
-  const short* dyImg = D.sdy + (size_t)f * D.lbd_frame + O.lbd_off;
+  const short2* sdImg = D.sd + (size_t)f * D.lbd_frame + O.lbd_off;
   const int NB = 9, WB = 7;
   const short imageWidth = (short)(realWidth - 1), imageHeight = (short)(realHeight - 1);
   const short lengthOfLSP = (short)kl.num_pixels;
@@ -767,7 +780,8 @@ __global__ void __launch_bounds__(64) k_lbd(LineDev D, const sdpl_keyline* __res
       tempCor = (short)roundf(sCorY);
       const short yCor = (tempCor < 0) ? 0 : (tempCor > imageHeight) ? imageHeight : tempCor;
       const int q = yCor * realWidth + xCor;
-      const float dx = (float)dxImg[q], dy = (float)dyImg[q];
+      const short2 sdv = __ldg(sdImg + q);
+      const float dx = (float)sdv.x, dy = (float)sdv.y;
       const float gDL = __fadd_rn(__fmul_rn(dx, dL0), __fmul_rn(dy, dL1));
       const float gDO = __fadd_rn(__fmul_rn(dx, dO0), __fmul_rn(dy, dO1));
       if (gDL > 0) pgdLRowSum = __fadd_rn(pgdLRowSum, gDL); else ngdLRowSum = __fsub_rn(ngdLRowSum, gDL);
@@ -857,9 +871,10 @@ struct sdpl_line {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
-  DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sdx, sdy, err, tables, tmpkl;
+  DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sd, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx, nfatab;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
+  int prof_detail = 0;   // sdpl_line_debug_grow_detail: thread 0 of every task accumulates prof[8..15] (costs ~3 % of the grow kernel)
   int nfa_minb = 10;      // second NFA pass compiled for 10 CTAs per SM (48 registers): 6.11 ms at 16, 5.33 at 12, 5.24 at 10, 5.37 at 8 (512 frames)
   int grow_legacy = 0, grow_ta = 16;   // phase-A cap: 16 measured best at 512 frames (4: 51.2, 8: 49.9, 16: 47.6 ms)
   void* h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -1011,8 +1026,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->pend.reserve(sizeof(lsd::Pending) * (size_t)D.pend_cap * nl * B))) return rc;
   if ((rc = o->npend.reserve(sizeof(int) * nl * B))) return rc;
   if ((rc = o->g.reserve(D.g_frame * B))) return rc;
-  if ((rc = o->sdx.reserve(sizeof(short) * D.lbd_frame * B))) return rc;
-  if ((rc = o->sdy.reserve(sizeof(short) * D.lbd_frame * B))) return rc;
+  if ((rc = o->sd.reserve(sizeof(short2) * D.lbd_frame * B))) return rc;
   if ((rc = o->tmpkl.reserve(sizeof(sdpl_keyline) * (size_t)D.pend_cap * nl * (o->nfeatures ? B : 1)))) return rc;
   if ((rc = o->err.reserve(sizeof(int)))) return rc;
   if ((rc = o->prof.reserve(sizeof(long long) * 16 * nl * B))) return rc;
@@ -1052,7 +1066,7 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   D.lvl = o->lvl.as<uint8_t>(); D.scaled = o->scaled.as<uint8_t>(); D.px = o->px.as<lsd::PxA>(); D.ang = o->ang.as<double>(); D.g2 = o->g2.as<int>();
   D.state = o->state.as<uint32_t>(); D.order = o->order.as<uint32_t>(); D.hist = o->hist.as<uint32_t>();
   D.maxg2 = o->maxg2.as<int>(); D.ndef = o->ndef.as<int>(); D.task_order = o->torder.as<int>(); D.reg = o->reg.as<int>(); D.pend = o->pend.as<lsd::Pending>();
-  D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sdx = o->sdx.as<short>(); D.sdy = o->sdy.as<short>();
+  D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sd = o->sd.as<short2>();
   D.err = o->err.as<int>(); D.prof = o->prof.as<long long>(); D.lgam = o->lgam.as<double>(); D.lgam_n = kLgamN;
   D.ctx = o->ctx.as<lsd::SlotCtx>(); D.grow_ta = o->grow_ta;
   D.rob_rect = o->robrect.as<lsd::Rect>(); D.rob = o->rob.as<lsd::RobEntry>(); D.rob_w = o->rob_w;
@@ -1078,7 +1092,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   if (rc) return rc;
   LineDev& D = o->D;
   D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride; D.serial_mode = o->serial_mode; D.rob_w_run = o->rob_w_run;
-  D.prof_detail = o->timer.enabled ? 1 : 0;
+  D.prof_detail = o->prof_detail;
   if (D.prof_detail) SDPL_CUDA(cudaMemsetAsync(D.prof, 0, sizeof(long long) * 16 * o->nlevels * B, o->stream));
   cudaStream_t st = o->stream;
   const int nl = o->nlevels;
@@ -1260,7 +1274,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
   for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
-                    &o->g, &o->sdx, &o->sdy, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx, &o->ctx, &o->nfatab})
+                    &o->g, &o->sd, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx, &o->ctx, &o->nfatab})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
   o->timer.release();
@@ -1475,6 +1489,7 @@ int sdpl_line_debug_pending(sdpl_line* o, int frame, int octave, double* out, in
 }
 
 // introspection: grow-kernel cycle counters of one task: {select, speculate, evaluate+commit, re-run, waves, re-runs, dead, seeds}
+int sdpl_line_debug_grow_detail(sdpl_line* o, int on) { if (!o) return SDPL_ERR_ARG; o->prof_detail = on != 0; return SDPL_OK; }
 int sdpl_line_debug_grow_profile(sdpl_line* o, int frame, int octave, long long* out8) {
   if (!o || o->gw == 0 || frame < 0 || frame >= o->last_B || octave < 0 || octave >= o->nlevels || !out8) return SDPL_ERR_ARG;
   SDPL_CUDA(cudaSetDevice(o->device));

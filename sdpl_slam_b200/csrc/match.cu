@@ -79,9 +79,12 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_partial(const uint8_t* __
     qw[k][0] = a.x; qw[k][1] = a.y; qw[k][2] = a.z; qw[k][3] = a.w;
     qw[k][4] = b.x; qw[k][5] = b.y; qw[k][6] = b.z; qw[k][7] = b.w;
   }
-  Top2 best[kQW];
+  // top-2 per query as packed keys (distance << 23 | train row): one unsigned compare orders by distance, then by row, so an update
+  // is three min / max instructions instead of two compare-and-move chains, and "strict '<' over ascending rows" is the key order
+  // (23 bits of row: match_run_dev rejects problems with more than 8 M train rows)
+  uint32_t k1[kQW], k2[kQW];
 #pragma unroll
-  for (int k = 0; k < kQW; k++) best[k] = Top2{kNoDist, 0xFFFFFFFFu, kNoDist, 0xFFFFFFFFu};
+  for (int k = 0; k < kQW; k++) { k1[k] = 0xFFFFFFFFu; k2[k] = 0xFFFFFFFFu; }
   // this split's train range
   const int per = (nt + nsplit - 1) / nsplit;
   const int tb = s * per, te = min(nt, tb + per);
@@ -90,16 +93,27 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_partial(const uint8_t* __
     uint4 a = __ldg(src), b = __ldg(src + 1);
 #pragma unroll
     for (int k = 0; k < kQW; k++) {
-      const uint32_t d = hamming256(qw[k], a, b);
-      // ascending j inside a lane: strict '<' keeps the lowest index on ties
-      if (d < best[k].d1) { best[k].d2 = best[k].d1; best[k].i2 = best[k].i1; best[k].d1 = d; best[k].i1 = j; }
-      else if (d < best[k].d2) { best[k].d2 = d; best[k].i2 = j; }
+      const uint32_t key = (hamming256(qw[k], a, b) << 23) | (uint32_t)j;
+      const uint32_t lo = min(key, k1[k]), hi = max(key, k1[k]);
+      k1[k] = lo; k2[k] = min(k2[k], hi);
     }
   }
 #pragma unroll
   for (int k = 0; k < kQW; k++) {
-    Top2 m = top2_warp_merge(best[k]);
-    if (lane == 0 && q0 + k < nq) partial[((size_t)p * max_q + q0 + k) * nsplit + s] = m;
+    uint32_t a1 = k1[k], a2 = k2[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const uint32_t b1 = __shfl_xor_sync(0xffffffffu, a1, o), b2 = __shfl_xor_sync(0xffffffffu, a2, o);
+      // two smallest of {a1 <= a2, b1 <= b2}: the lanes hold disjoint rows, so equal keys only occur as the 0xFFFFFFFF filler
+      const uint32_t lo = min(a1, b1), hi = max(a1, b1);
+      a2 = min(hi, min(a2, b2)); a1 = lo;
+    }
+    if (lane == 0 && q0 + k < nq) {
+      Top2 m;
+      m.d1 = a1 == 0xFFFFFFFFu ? kNoDist : (a1 >> 23); m.i1 = a1 == 0xFFFFFFFFu ? 0xFFFFFFFFu : (a1 & 0x7FFFFFu);
+      m.d2 = a2 == 0xFFFFFFFFu ? kNoDist : (a2 >> 23); m.i2 = a2 == 0xFFFFFFFFu ? 0xFFFFFFFFu : (a2 & 0x7FFFFFu);
+      partial[((size_t)p * max_q + q0 + k) * nsplit + s] = m;
+    }
   }
 }
 
@@ -225,6 +239,7 @@ struct sdpl_matcher {
 
 static int match_run_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, size_t q_stride, const uint8_t* d_t, const int* d_nt,
                          size_t t_stride, int npairs, int max_q, int max_t, sdpl_dmatch* d_best, sdpl_dmatch* d_second) {
+  if (max_t > (1 << 23)) { set_last_error("matcher: more than 2^23 train rows per problem (packed top-2 keys hold 23 bits of row)"); return SDPL_ERR_UNSUPPORTED; }
   // choose the train split so that the grid covers the SMs a few times
   int qblocks = div_up(max_q, kWarps * kQW);
   int nsplit = std::max(1, std::min(div_up(4 * m->sm_count, std::max(1, qblocks * npairs)), div_up(max_t, 64)));

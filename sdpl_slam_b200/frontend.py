@@ -83,6 +83,7 @@ def load_library(path=None):
     L.sdpl_line_set_stream.argtypes = [vp, vp]
     L.sdpl_line_set_serial.argtypes = [vp, i]
     L.sdpl_line_debug_grow_profile.argtypes = [vp, i, i, vp]
+    L.sdpl_line_debug_grow_detail.argtypes = [vp, i]
     L.sdpl_line_debug_pending.argtypes = [vp, i, i, vp, i, ip]
     # matcher
     L.sdpl_matcher_create.argtypes = [C.POINTER(vp), i]
@@ -361,6 +362,10 @@ class Lineextractor(_Profiled):
         out = np.zeros((capacity, 8), np.float64); n = C.c_int()
         _check(self._L.sdpl_line_debug_pending(self._h, frame, octave, _p(out), capacity, C.byref(n)))
         return out[:n.value].copy()
+
+    def grow_detail(self, on=True):
+        """detailed region-growing counters (grow_profile's phaseA ... phaseA_wait entries); off by default"""
+        _check(self._L.sdpl_line_debug_grow_detail(self._h, int(bool(on))))
 
     def grow_profile(self, octave, frame=0):
         out = np.zeros(16, np.int64)

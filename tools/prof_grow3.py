@@ -7,7 +7,7 @@ F = int(sys.argv[1])
 imgs = synth.frames(range(F), 375, 1242)
 ref = None
 for spec in sys.argv[2:]:
-    g = fe.Lineextractor(0, 2, 0.8, 2, 2.0, 0); g.set_profiling(True)
+    g = fe.Lineextractor(0, 2, 0.8, 2, 2.0, 0); g.set_profiling(True); g.grow_detail(True)
     if spec == "legacy":
         g.set_serial(4)
     else:

@@ -5,7 +5,7 @@ sys.path.insert(0, '.')
 from sdpl_slam_b200 import frontend as fe, synth
 imgs = synth.sequence(0, 8, 375, 1242)
 for spec in (sys.argv[1:] or ["default"]):
-    g = fe.Lineextractor(0, 2, 0.8, 2, 2.0, 0); g.set_profiling(True)
+    g = fe.Lineextractor(0, 2, 0.8, 2, 2.0, 0); g.set_profiling(True); g.grow_detail(True)
     if spec != "default":
         nw, mb, ta = map(int, spec.split(","))
         g.set_serial(0 | ((nw | (mb << 4)) << 8) | ((ta + 1) << 24))
