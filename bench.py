@@ -612,7 +612,7 @@ def run_gpu(args, stages, cfg):
     pinned = torch.from_numpy(host).pin_memory()
     d_imgs = pinned.to(dev)
     # two arms (handles + buffers) used alternately: step k + 1's extraction does not wait for step k's matching and statistics
-    n_arms = 2 if (args.pipeline and F <= 1024) else 1
+    n_arms = max(1, args.pipeline + 1) if (args.pipeline and F <= 1024) else 1
     arms = [ResidentArm(fe, torch, dev, local, cfg, stages, F, lead) for _ in range(n_arms)]
     gathers = [shard.StatsGather(total, 8, torch.int32, dev) for _ in range(n_arms)]
     arm = arms[0]
@@ -875,7 +875,7 @@ def main():
     ap.add_argument("--stages", default="orb,line,match")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=1, help="1: two sets of handles / buffers used alternately so that consecutive steps overlap "
+    ap.add_argument("--pipeline", type=int, default=1, help="N >= 1: N + 1 sets of handles / buffers used in turn (1: two sets) so that consecutive steps overlap "
                                                               "(when a GPU holds <= 1024 frames per step); 0: one set, steps strictly one after another")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-post", action="store_true", help="skip the Frame post-processing stage block (SURVEY 8f rows 1, 2)")

@@ -874,6 +874,8 @@ struct sdpl_line {
   DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sd, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx, nfatab;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
+  int grow_forced = 0;   // SDPL_GROW given: use it for big batches only (single frames keep the 8-warp variant)
+  int grow_smem = 0;     // tuning: dynamic shared memory requested by the <4,5> variant (caps its CTAs per SM without touching registers)
   int prof_detail = 0;   // sdpl_line_debug_grow_detail: thread 0 of every task accumulates prof[8..15] (costs ~3 % of the grow kernel)
   int nfa_minb = 10;      // second NFA pass compiled for 10 CTAs per SM (48 registers): 6.11 ms at 16, 5.33 at 12, 5.24 at 10, 5.37 at 8 (512 frames)
   int grow_legacy = 0, grow_ta = 16;   // phase-A cap: 16 measured best at 512 frames (4: 51.2, 8: 49.9, 16: 47.6 ms)
@@ -1129,13 +1131,15 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   if (o->serial_mode == 0 && !o->grow_legacy) {
     // two-phase waves (lsd_grow2.cuh).  Warps per task / CTAs per SM as below
     const bool small = nl * B <= o->sm_count;
-    const int nw = o->grow_warps > 0 ? o->grow_warps : (small ? 8 : 4);
-    const int mb = o->grow_minb > 0 ? o->grow_minb : (small ? 1 : 4);
+    const bool forced = o->grow_warps > 0 && !(o->grow_forced && small);
+    const int nw = forced ? o->grow_warps : (small ? 8 : 4);
+    const int mb = forced && o->grow_minb > 0 ? o->grow_minb : (small ? 1 : 4);
     D.grow_ta = o->grow_ta;
     if (nw >= 8 && mb >= 2) k_lsd_grow2<8, 2><<<nl * B, 256, 0, st>>>(D);
     else if (nw >= 8) k_lsd_grow2<8, 1><<<nl * B, 256, 0, st>>>(D);
     else if (nw >= 4 && mb <= 2) k_lsd_grow2<4, 2><<<nl * B, 128, 0, st>>>(D);
     else if (nw >= 4 && mb <= 4) k_lsd_grow2<4, 4><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb == 5) k_lsd_grow2<4, 5><<<nl * B, 128, o->grow_smem, st>>>(D);
     else if (nw >= 4 && mb <= 6) k_lsd_grow2<4, 6><<<nl * B, 128, 0, st>>>(D);
     else if (nw >= 4) k_lsd_grow2<4, 8><<<nl * B, 128, 0, st>>>(D);
     else if (nw >= 2 && mb <= 4) k_lsd_grow2<2, 4><<<nl * B, 64, 0, st>>>(D);
@@ -1265,6 +1269,17 @@ int sdpl_line_create(sdpl_line** out, int nfeatures, int refine, float lsd_scale
   SDPL_CUDA(cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking));
   SDPL_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming));
   SDPL_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
+  if (const char* g = getenv("SDPL_GROW")) {
+    // tuning knob read at creation: "warps,ctas_per_sm,phaseA_cap[,dynamic_smem_bytes]" of the region-growing kernel (big batches)
+    int nw = 0, mb = 0, ta = -1, sm = 0;
+    if (sscanf(g, "%d,%d,%d,%d", &nw, &mb, &ta, &sm) >= 2) {
+      o->grow_warps = std::min(std::max(nw, 1), lsd::kMaxGrowWarps); o->grow_minb = std::max(mb, 1);
+      if (ta >= 0) o->grow_ta = ta;
+      o->grow_smem = std::max(sm, 0);
+      o->grow_forced = 1;
+    }
+  }
+  if (o->grow_smem > 0) SDPL_CUDA(cudaFuncSetAttribute(k_lsd_grow2<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->grow_smem));
   *out = o;
   return SDPL_OK;
 }
