@@ -287,6 +287,22 @@ int sdpl_post_features_in_area_dev(sdpl_post* h, int nframes, int w, int h_, con
                                    const int32_t* d_cell_start, const int32_t* d_items, int grid_cols, int grid_rows, const float* d_queries,
                                    int nq, int32_t* d_out, int max_out, int* d_counts, int sync);
 
+/* The descriptor search a projection match runs on that window (the reference keeps the window search and the
+ * Hamming metric, the ORB-SLAM2 loop around them is not in its tree): d_qdesc = [nframes][nq][32] query descriptors; d_out5 =
+ * [nframes][nq][5] int32 {best key point index, best distance, its octave, second-best distance, its octave} over the window's key
+ * points, ties to the first visited; index -1 / distance 256 when the window is empty. */
+int sdpl_post_search_area_dev(sdpl_post* h, int nframes, int w, int h_, const sdpl_keypoint* d_kps, const uint8_t* d_desc, int capacity,
+                              const int32_t* d_cell_start, const int32_t* d_items, int grid_cols, int grid_rows, const float* d_queries,
+                              const uint8_t* d_qdesc, int nq, int32_t* d_out5, int sync);
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:242-307, for n_points map points: the observed descriptors of point p are
+ * rows d_start[p] .. d_start[p+1] of d_desc (at most 64 per point); d_best_idx[p] = the observation with the least median distance to
+ * the others (first on ties, -1 without observations), d_out_desc[p] = its 32 bytes */
+int sdpl_post_distinctive_descriptors_dev(sdpl_post* h, const uint8_t* d_desc, const int32_t* d_start, int n_points, int32_t* d_best_idx,
+                                          uint8_t* d_out_desc, int sync);
+/* MapPoint::PredictScale, src/MapPoint.cc:385-417: ceil(log(max_distance / current_dist) / log_scale_factor) clamped to [0, n_levels) */
+int sdpl_post_predict_scale_dev(sdpl_post* h, const float* d_max_distance, const float* d_current_dist, int n, float log_scale_factor,
+                                int n_levels, int32_t* d_out, int sync);
+
 /* Order-independent 64-bit digest of per-frame result rows resident on the device: adds, for every frame f, the sum of the
  * hashes of rows [0, min(d_n[f], max_rows)) of its block (row_bytes per row, a multiple of 4; blocks frame_stride bytes apart)
  * to d_digest[f] (DEVICE uint64 array the caller zeroes), asynchronously on `stream` (cudaStream_t as void*).  Used to check

@@ -104,6 +104,10 @@ int orc_post_line_corres(const orc_keyline* kls, int n, const int32_t* mask, con
                          double* inf_line, float* stat_depth, int32_t* src_idx);
 int orc_post_features_in_area(const orc_keypoint* kps, int w, int h, int grid_cols, int grid_rows, const int32_t* cell_start,
                               const int32_t* items, float x, float y, float r, int minLevel, int maxLevel, int32_t* out, int cap);
+void orc_post_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int n_points, int32_t* best_idx, uint8_t* out_desc);
+void orc_post_predict_scale(const float* max_distance, const float* current_dist, int n, float log_scale_factor, int n_levels, int32_t* out);
+void orc_post_search_area(const orc_keypoint* kps, const uint8_t* desc, int w, int h, int grid_cols, int grid_rows, const int32_t* cell_start,
+                          const int32_t* items, float x, float y, float r, int minLevel, int maxLevel, const uint8_t* qdesc, int32_t* out5);
 void orc_post_grid(const orc_keypoint* kps, int n, int w, int h, int grid_cols, int grid_rows, int32_t* cell_start, int32_t* items);
 
 #ifdef __cplusplus

@@ -359,3 +359,29 @@ def post_features_in_area(kps, w, h, cell_start, items, x, y, r, min_level=-1, m
     L = lib(); L.orc_post_features_in_area.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_float] * 3 + [C.c_int] * 2 + [C.c_void_p, C.c_int]
     n = L.orc_post_features_in_area(_p(kps), w, h, grid_cols, grid_rows, _p(cs), _p(it), x, y, r, min_level, max_level, _p(out), len(out))
     return out[:n]
+
+
+def post_distinctive_descriptors(desc, start):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32); start = np.ascontiguousarray(start, np.int32)
+    n = len(start) - 1
+    best, out = np.zeros(n, np.int32), np.zeros((n, 32), np.uint8)
+    L = lib(); L.orc_post_distinctive_descriptors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_post_distinctive_descriptors(_p(desc), _p(start), n, _p(best), _p(out))
+    return best, out
+
+
+def post_predict_scale(max_distance, current_dist, log_scale_factor, n_levels):
+    a = np.ascontiguousarray(max_distance, np.float32); b = np.ascontiguousarray(current_dist, np.float32)
+    out = np.zeros(len(a), np.int32)
+    L = lib(); L.orc_post_predict_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    L.orc_post_predict_scale(_p(a), _p(b), len(a), float(log_scale_factor), int(n_levels), _p(out))
+    return out
+
+
+def post_search_area(kps, desc, w, h, cell_start, items, x, y, r, min_level, max_level, qdesc, grid_cols=64, grid_rows=48):
+    kps = np.ascontiguousarray(kps, KP_DTYPE); desc = np.ascontiguousarray(desc, np.uint8)
+    cs = np.ascontiguousarray(cell_start, np.int32); it = np.ascontiguousarray(items, np.int32); q = np.ascontiguousarray(qdesc, np.uint8)
+    out = np.zeros(5, np.int32)
+    L = lib(); L.orc_post_search_area.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_float] * 3 + [C.c_int] * 2 + [C.c_void_p] * 2
+    L.orc_post_search_area(_p(kps), _p(desc), w, h, grid_cols, grid_rows, _p(cs), _p(it), x, y, r, min_level, max_level, _p(q), _p(out))
+    return out

@@ -223,4 +223,64 @@ int orc_post_features_in_area(const orc_keypoint* kps, int w, int h, int grid_co
   return n;
 }
 
+/* MapPoint::ComputeDistinctiveDescriptors, src/MapPoint.cc:242-307, for n_points map points whose observed descriptors are rows
+   start[p] .. start[p+1] of desc (32 bytes each): all pair distances, per row the median = sorted[(int)(0.5 * (N - 1))] (the row
+   includes the zero self distance), the first row with the least median wins (strict <).  best_idx[p] = its index among the point's
+   observations (-1 for a point without observations), out_desc = its 32 bytes. */
+void orc_post_distinctive_descriptors(const uint8_t* desc, const int32_t* start, int n_points, int32_t* best_idx, uint8_t* out_desc) {
+  for (int p = 0; p < n_points; p++) {
+    const int N = start[p + 1] - start[p];
+    best_idx[p] = -1;
+    if (N <= 0) continue;
+    const uint8_t* d = desc + (size_t)start[p] * 32;
+    std::vector<std::vector<float>> Distances(N, std::vector<float>(N));
+    for (int i = 0; i < N; i++) {
+      Distances[i][i] = 0;
+      for (int j = i + 1; j < N; j++) {
+        const int distij = orc_hamming256(d + 32 * (size_t)i, d + 32 * (size_t)j);
+        Distances[i][j] = (float)distij; Distances[j][i] = (float)distij;
+      }
+    }
+    int BestMedian = 2147483647, BestIdx = 0;
+    for (int i = 0; i < N; i++) {
+      std::vector<int> vDists(Distances[i].begin(), Distances[i].end());
+      std::sort(vDists.begin(), vDists.end());
+      const int median = vDists[(size_t)(0.5 * (N - 1))];
+      if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+    }
+    best_idx[p] = BestIdx;
+    memcpy(out_desc + 32 * (size_t)p, d + 32 * (size_t)BestIdx, 32);
+  }
+}
+
+/* MapPoint::PredictScale, src/MapPoint.cc:385-417: nScale = ceil(log(maxDistance / currentDist) / logScaleFactor) clamped to
+   [0, nLevels - 1]; float arithmetic with std::log(float) as written (Frame.cc / MapPoint.cc have `using namespace std`). */
+void orc_post_predict_scale(const float* max_distance, const float* current_dist, int n, float log_scale_factor, int n_levels, int32_t* out) {
+  for (int i = 0; i < n; i++) {
+    const float ratio = max_distance[i] / current_dist[i];
+    int nScale = (int)std::ceil(std::log(ratio) / log_scale_factor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= n_levels) nScale = n_levels - 1;
+    out[i] = nScale;
+  }
+}
+
+/* The descriptor search a projection match runs on Frame::GetFeaturesInArea (the reference keeps the window search, src/Frame.cc:
+   970-1023, and the descriptor metric; the ORB-SLAM2 loop around them is not in its tree -- SURVEY.md 8f row 4): among the key points
+   of the window around (x, y), the best and second-best Hamming distance to `qdesc`, ties to the first visited.  out5 = {best index,
+   best distance, best octave, second distance, second octave} (index -1 / distance 256 when missing). */
+void orc_post_search_area(const orc_keypoint* kps, const uint8_t* desc, int w, int h, int grid_cols, int grid_rows, const int32_t* cell_start,
+                          const int32_t* items, float x, float y, float r, int minLevel, int maxLevel, const uint8_t* qdesc, int32_t* out5) {
+  std::vector<int32_t> cand(cell_start[grid_cols * grid_rows] + 1);
+  const int n = orc_post_features_in_area(kps, w, h, grid_cols, grid_rows, cell_start, items, x, y, r, minLevel, maxLevel, cand.data(), (int)cand.size());
+  int bestDist = 256, bestIdx = -1, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1;
+  for (int c = 0; c < n; c++) {
+    const int idx = cand[c];
+    const int dist = orc_hamming256(qdesc, desc + 32 * (size_t)idx);
+    if (dist < bestDist) { bestDist2 = bestDist; bestLevel2 = bestLevel; bestDist = dist; bestLevel = kps[idx].octave; bestIdx = idx; }
+    else if (dist < bestDist2) { bestDist2 = dist; bestLevel2 = kps[idx].octave; }
+  }
+  out5[0] = bestIdx; out5[1] = bestDist; out5[2] = bestLevel; out5[3] = bestDist2; out5[4] = bestLevel2;
+}
+
 }  // extern "C"

@@ -346,6 +346,130 @@ __global__ void __launch_bounds__(128) k_features_in_area(const sdpl_keypoint* _
   if (lane == 0) counts[(size_t)f * nq + q] = n;
 }
 
+__device__ __forceinline__ int hamming32(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
+         __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// P7: the descriptor search of a projection match on the window of P6: one warp per query walks the window in the reference's
+// visiting order, 32 candidates at a time; every lane keeps the best / second best of its candidates as (distance << 22 | visiting
+// rank) keys (strict '<' over the visiting order = smallest key), the lanes' pairs are merged with shuffles
+__global__ void __launch_bounds__(128) k_search_area(const sdpl_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc, int capacity,
+                                                     const int32_t* __restrict__ cell_start, const int32_t* __restrict__ items, int w, int h, int gcols,
+                                                     int grows, const float* __restrict__ queries, const uint8_t* __restrict__ qdesc, int nq,
+                                                     int32_t* __restrict__ out5) {
+  const int f = blockIdx.y, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  const float* Q = queries + ((size_t)f * nq + q) * 5;
+  const float x = Q[0], y = Q[1], r = Q[2];
+  const int minLevel = (int)Q[3], maxLevel = (int)Q[4];
+  const uint4* qd = (const uint4*)(qdesc + ((size_t)f * nq + q) * 32);
+  const uint4 q0 = __ldg(qd), q1 = __ldg(qd + 1);
+  const float wInv = __fdiv_rn((float)gcols, (float)w), hInv = __fdiv_rn((float)grows, (float)h);
+  const int x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(x, r), wInv))), x1 = min(gcols - 1, (int)ceilf(__fmul_rn(__fadd_rn(x, r), wInv)));
+  const int y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(y, r), hInv))), y1 = min(grows - 1, (int)ceilf(__fmul_rn(__fadd_rn(y, r), hInv)));
+  // key = distance (9 bits) << 22 | visiting rank (22 bits); payload = key point index
+  uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu; int i1 = -1, i2 = -1;
+  if (!(x0 >= gcols || x1 < 0 || y0 >= grows || y1 < 0)) {
+    const bool check = minLevel > 0 || maxLevel >= 0;
+    const int32_t* cs = cell_start + (size_t)f * (gcols * grows + 1);
+    const int32_t* it = items + (size_t)f * capacity;
+    const sdpl_keypoint* K = kps + (size_t)f * capacity;
+    const uint8_t* Dd = desc + (size_t)f * capacity * 32;
+    int visited = 0;
+    for (int ix = x0; ix <= x1; ix++) {
+      const int j0 = cs[ix * grows + y0], j1 = cs[ix * grows + y1 + 1];
+      for (int jb = j0; jb < j1; jb += 32) {
+        const int j = jb + lane;
+        if (j < j1) {
+          const int idx = it[j];
+          const sdpl_keypoint kp = K[idx];
+          const bool lvl = !check || (kp.octave >= minLevel && (maxLevel < 0 || kp.octave <= maxLevel));
+          if (lvl && fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r) {
+            const uint4* dp = (const uint4*)(Dd + (size_t)idx * 32);
+            const uint32_t key = ((uint32_t)hamming32(q0, q1, __ldg(dp), __ldg(dp + 1)) << 22) | (uint32_t)(visited + j - jb);
+            if (key < k1) { k2 = k1; i2 = i1; k1 = key; i1 = idx; } else if (key < k2) { k2 = key; i2 = idx; }
+          }
+        }
+        visited += min(32, j1 - jb);       // ranks follow the position in the visiting order (hits and misses alike)
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const uint32_t b1 = __shfl_xor_sync(0xffffffffu, k1, o), b2 = __shfl_xor_sync(0xffffffffu, k2, o);
+    const int j1 = __shfl_xor_sync(0xffffffffu, i1, o), j2 = __shfl_xor_sync(0xffffffffu, i2, o);
+    // two smallest of {k1 <= k2, b1 <= b2} (keys are unique: the rank is)
+    uint32_t n1, n2; int m1, m2;
+    if (b1 < k1) { n1 = b1; m1 = j1; if (k1 < b2) { n2 = k1; m2 = i1; } else { n2 = b2; m2 = j2; } }
+    else { n1 = k1; m1 = i1; if (b1 < k2) { n2 = b1; m2 = j1; } else { n2 = k2; m2 = i2; } }
+    k1 = n1; i1 = m1; k2 = n2; i2 = m2;
+  }
+  if (lane == 0) {
+    int32_t* o = out5 + ((size_t)f * nq + q) * 5;
+    const sdpl_keypoint* K = kps + (size_t)f * capacity;
+    o[0] = i1; o[1] = i1 >= 0 ? (int)(k1 >> 22) : 256; o[2] = i1 >= 0 ? K[i1].octave : -1;
+    o[3] = i2 >= 0 ? (int)(k2 >> 22) : 256; o[4] = i2 >= 0 ? K[i2].octave : -1;
+  }
+}
+
+// P8: MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:242-307): one warp per map point with N <= 64 observations.  Row i of the
+// distance matrix sits in the lanes (columns lane, lane + 32); its median is the element of rank (int)(0.5 (N - 1)) under the order
+// (distance, column), found by counting; the first row with the least median wins.
+__global__ void __launch_bounds__(128) k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ start, int n_points,
+                                                     int32_t* __restrict__ best_idx, uint8_t* __restrict__ out_desc, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (p >= n_points) return;
+  const int s0 = start[p], N = start[p + 1] - s0;
+  if (N <= 0) { if (lane == 0) best_idx[p] = -1; return; }
+  if (N > 64) { if (lane == 0) { best_idx[p] = -1; atomicExch(err, SDPL_ERR_OVERFLOW); } return; }
+  const uint4* D4 = (const uint4*)(desc + (size_t)s0 * 32);
+  const int c0 = lane, c1 = lane + 32;
+  uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
+  if (c0 < N) { a0 = __ldg(D4 + 2 * c0); a1 = __ldg(D4 + 2 * c0 + 1); }
+  if (c1 < N) { b0 = __ldg(D4 + 2 * c1); b1 = __ldg(D4 + 2 * c1 + 1); }
+  const int kth = (int)(0.5 * (double)(N - 1));
+  int bestMedian = 0x7fffffff, bestI = 0;
+  for (int i = 0; i < N; i++) {
+    // descriptor i to every lane
+    const int src = i & 31;
+    uint4 r0, r1;
+    const uint4 s_lo0 = i < 32 ? a0 : b0, s_lo1 = i < 32 ? a1 : b1;
+    r0.x = __shfl_sync(0xffffffffu, s_lo0.x, src); r0.y = __shfl_sync(0xffffffffu, s_lo0.y, src);
+    r0.z = __shfl_sync(0xffffffffu, s_lo0.z, src); r0.w = __shfl_sync(0xffffffffu, s_lo0.w, src);
+    r1.x = __shfl_sync(0xffffffffu, s_lo1.x, src); r1.y = __shfl_sync(0xffffffffu, s_lo1.y, src);
+    r1.z = __shfl_sync(0xffffffffu, s_lo1.z, src); r1.w = __shfl_sync(0xffffffffu, s_lo1.w, src);
+    const int d0 = c0 < N ? hamming32(r0, r1, a0, a1) : 1 << 20, d1 = c1 < N ? hamming32(r0, r1, b0, b1) : 1 << 20;
+    // rank of my two elements among the N of the row, order (distance, column)
+    int rk0 = 0, rk1 = 0;
+    for (int j = 0; j < N; j++) {
+      const int dj = j < 32 ? __shfl_sync(0xffffffffu, d0, j) : __shfl_sync(0xffffffffu, d1, j - 32);
+      rk0 += (dj < d0) || (dj == d0 && j < c0);
+      rk1 += (dj < d1) || (dj == d1 && j < c1);
+    }
+    const uint32_t hit0 = __ballot_sync(0xffffffffu, c0 < N && rk0 == kth), hit1 = __ballot_sync(0xffffffffu, c1 < N && rk1 == kth);
+    int median;
+    if (hit0) median = __shfl_sync(0xffffffffu, d0, __ffs(hit0) - 1); else median = __shfl_sync(0xffffffffu, d1, __ffs(hit1) - 1);
+    if (median < bestMedian) { bestMedian = median; bestI = i; }
+  }
+  if (lane == 0) best_idx[p] = bestI;
+  if (lane < 8) ((uint32_t*)(out_desc + (size_t)p * 32))[lane] = ((const uint32_t*)(desc + (size_t)(s0 + bestI) * 32))[lane];
+}
+
+// P9: MapPoint::PredictScale (MapPoint.cc:385-417)
+__global__ void k_predict_scale(const float* __restrict__ max_distance, const float* __restrict__ current_dist, int n, float log_sf, int n_levels,
+                                int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ratio = __fdiv_rn(max_distance[i], current_dist[i]);
+  // std::log(float) of the reference: the double logarithm rounded to float is the correctly rounded value
+  int s = (int)ceilf(__fdiv_rn((float)log((double)ratio), log_sf));
+  s = s < 0 ? 0 : (s >= n_levels ? n_levels - 1 : s);
+  out[i] = s;
+}
+
 }  // namespace sdpl
 
 using namespace sdpl;
@@ -509,6 +633,59 @@ int sdpl_post_features_in_area_dev(sdpl_post* p, int nframes, int w, int h, cons
                                                                           d_out, max_out, d_counts);
   SDPL_LAUNCH_CHECK();
   p->timer.mark(p->stream, "features_in_area");
+  p->launches = g_launches;
+  if (sync) SDPL_CUDA(cudaStreamSynchronize(p->stream));
+  return SDPL_OK;
+}
+
+int sdpl_post_search_area_dev(sdpl_post* p, int nframes, int w, int h, const sdpl_keypoint* d_kps, const uint8_t* d_desc, int capacity,
+                              const int32_t* d_cell_start, const int32_t* d_items, int grid_cols, int grid_rows, const float* d_queries,
+                              const uint8_t* d_qdesc, int nq, int32_t* d_out5, int sync) {
+  if (!p || nframes < 1 || w < 1 || h < 1 || !d_kps || !d_desc || capacity < 1 || !d_cell_start || !d_items || grid_cols < 1 || grid_rows < 1 ||
+      !d_queries || !d_qdesc || nq < 1 || !d_out5) { set_last_error("sdpl_post_search_area_dev: bad argument"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(p->device));
+  g_launches = 0;
+  p->timer.begin(p->stream);
+  k_search_area<<<dim3(div_up(nq, 4), nframes), 128, 0, p->stream>>>(d_kps, d_desc, capacity, d_cell_start, d_items, w, h, grid_cols, grid_rows, d_queries,
+                                                                     d_qdesc, nq, d_out5);
+  SDPL_LAUNCH_CHECK();
+  p->timer.mark(p->stream, "search_area");
+  p->launches = g_launches;
+  if (sync) SDPL_CUDA(cudaStreamSynchronize(p->stream));
+  return SDPL_OK;
+}
+
+int sdpl_post_distinctive_descriptors_dev(sdpl_post* p, const uint8_t* d_desc, const int32_t* d_start, int n_points, int32_t* d_best_idx,
+                                          uint8_t* d_out_desc, int sync) {
+  if (!p || !d_desc || !d_start || n_points < 1 || !d_best_idx || !d_out_desc) { set_last_error("sdpl_post_distinctive_descriptors_dev: bad argument"); return SDPL_ERR_ARG; }
+  SDPL_CUDA(cudaSetDevice(p->device));
+  int rc;
+  if ((rc = p->stage[11].reserve(sizeof(int)))) return rc;
+  SDPL_CUDA(cudaMemsetAsync(p->stage[11].p, 0, sizeof(int), p->stream));
+  g_launches = 0;
+  p->timer.begin(p->stream);
+  k_distinctive<<<div_up(n_points, 4), 128, 0, p->stream>>>(d_desc, d_start, n_points, d_best_idx, d_out_desc, p->stage[11].as<int>());
+  SDPL_LAUNCH_CHECK();
+  p->timer.mark(p->stream, "distinctive_descriptors");
+  p->launches = g_launches;
+  if (sync) {
+    int e = 0;
+    SDPL_CUDA(cudaMemcpyAsync(&e, p->stage[11].p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    SDPL_CUDA(cudaStreamSynchronize(p->stream));
+    if (e) { set_last_error("sdpl_post_distinctive_descriptors_dev: a map point has more than 64 observations"); return SDPL_ERR_OVERFLOW; }
+  }
+  return SDPL_OK;
+}
+
+int sdpl_post_predict_scale_dev(sdpl_post* p, const float* d_max_distance, const float* d_current_dist, int n, float log_scale_factor, int n_levels,
+                                int32_t* d_out, int sync) {
+  if (!p || !d_max_distance || !d_current_dist || n < 1 || !(log_scale_factor > 0.f) || n_levels < 1 || !d_out) {
+    set_last_error("sdpl_post_predict_scale_dev: bad argument"); return SDPL_ERR_ARG;
+  }
+  SDPL_CUDA(cudaSetDevice(p->device));
+  g_launches = 0;
+  k_predict_scale<<<div_up(n, 256), 256, 0, p->stream>>>(d_max_distance, d_current_dist, n, log_scale_factor, n_levels, d_out);
+  SDPL_LAUNCH_CHECK();
   p->launches = g_launches;
   if (sync) SDPL_CUDA(cudaStreamSynchronize(p->stream));
   return SDPL_OK;

@@ -124,6 +124,9 @@ def load_library(path=None):
     L.sdpl_post_line_corres_dev.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, i, f, vp, vp, vp, vp, vp, vp, vp, vp, vp, i]
     L.sdpl_post_grid_dev.argtypes = [vp, i, i, i, vp, vp, i, i, i, vp, vp, i]
     L.sdpl_post_features_in_area_dev.argtypes = [vp, i, i, i, vp, i, vp, vp, i, i, vp, i, vp, i, vp, i]
+    L.sdpl_post_search_area_dev.argtypes = [vp, i, i, i, vp, vp, i, vp, vp, i, i, vp, vp, i, vp, i]
+    L.sdpl_post_distinctive_descriptors_dev.argtypes = [vp, vp, vp, i, vp, vp, i]
+    L.sdpl_post_predict_scale_dev.argtypes = [vp, vp, vp, i, f, i, vp, i]
     L.sdpl_rows_digest_dev.argtypes = [vp, i, sz, vp, i, i, C.c_ulonglong, vp, vp]
     if path is None:
         _lib = L
@@ -652,6 +655,24 @@ class FramePost(_Profiled):
         v = C.c_void_p
         _check(self._L.sdpl_post_features_in_area_dev(self._h, nframes, w, h, v(d_kps), capacity, v(d_cell_start), v(d_items), grid_cols, grid_rows,
                                                       v(d_queries), nq, v(d_out), max_out, v(d_counts), int(sync)))
+
+
+    def search_area_dev(self, nframes, w, h, d_kps, d_desc, capacity, d_cell_start, d_items, d_queries, d_qdesc, nq, d_out5, grid_cols=64, grid_rows=48,
+                        sync=False):
+        """best / second-best Hamming distance of nq query descriptors per frame inside their GetFeaturesInArea windows"""
+        v = C.c_void_p
+        _check(self._L.sdpl_post_search_area_dev(self._h, nframes, w, h, v(d_kps), v(d_desc), capacity, v(d_cell_start), v(d_items), grid_cols, grid_rows,
+                                                 v(d_queries), v(d_qdesc), nq, v(d_out5), int(sync)))
+
+    def distinctive_descriptors_dev(self, d_desc, d_start, n_points, d_best_idx, d_out_desc, sync=False):
+        """MapPoint::ComputeDistinctiveDescriptors for n_points map points (CSR of observed descriptors)"""
+        v = C.c_void_p
+        _check(self._L.sdpl_post_distinctive_descriptors_dev(self._h, v(d_desc), v(d_start), n_points, v(d_best_idx), v(d_out_desc), int(sync)))
+
+    def predict_scale_dev(self, d_max_distance, d_current_dist, n, log_scale_factor, n_levels, d_out, sync=False):
+        v = C.c_void_p
+        _check(self._L.sdpl_post_predict_scale_dev(self._h, v(d_max_distance), v(d_current_dist), n, float(log_scale_factor), n_levels, v(d_out),
+                                                   int(sync)))
 
 
 def rows_digest_dev(d_rows, row_bytes, frame_stride, d_n, nframes, max_rows, salt, d_digest, cuda_stream=0):

@@ -131,3 +131,62 @@ def test_feature_post_processing_on_device_resident_extractor_output(frontend, o
             k = min(MAXO, len(want)); nonempty += k > 0
             assert (hits[f, q, :k] == want[:k]).all()
     assert nonempty > B * NQ // 3
+    # ---- the descriptor search on those windows: query descriptors = noisy copies of descriptors of the frame ----
+    qd = np.zeros((B, NQ, 32), np.uint8)
+    hd = desc.cpu().numpy()
+    for f in range(B):
+        pick = rng.integers(0, int(nk[f]), NQ)
+        qd[f] = hd[f, pick]
+        qs[f, :, 0] = kps[f].cpu().numpy().view(KP).reshape(-1)["x"][pick] + rng.uniform(-6, 6, NQ)
+        qs[f, :, 1] = kps[f].cpu().numpy().view(KP).reshape(-1)["y"][pick] + rng.uniform(-6, 6, NQ)
+        for i in range(NQ):
+            for b in rng.choice(256, 9, replace=False):
+                qd[f, i, b >> 3] ^= np.uint8(1 << (b & 7))
+    qs[..., 2] = rng.uniform(8, 40, (B, NQ))
+    dq = _dev(torch, qs); dqd = _dev(torch, qd); out5 = z(B, NQ, 5, dt=i32)
+    post.search_area_dev(B, W, H, kps.data_ptr(), desc.data_ptr(), KC, cs.data_ptr(), items.data_ptr(), dq.data_ptr(), dqd.data_ptr(), NQ, out5.data_ptr(),
+                         64, 48, True)
+    out5 = out5.cpu().numpy(); found = 0
+    for f in range(B):
+        okps, odesc = oorb(imgs[f]); wcs, witems = oracle.post_grid(okps, W, H)
+        for q in range(NQ):
+            want = oracle.post_search_area(okps, odesc, W, H, wcs, witems, *[float(v) for v in qs[f, q, :3]], int(qs[f, q, 3]), int(qs[f, q, 4]), qd[f, q])
+            assert (out5[f, q] == want).all(), (f, q, out5[f, q], want)
+            found += want[0] >= 0 and want[1] <= 9
+    assert found > B * NQ // 4
+
+
+def test_distinctive_descriptors_and_predict_scale(frontend, oracle):
+    import torch
+    rng = np.random.default_rng(12)
+    sizes = rng.integers(0, 65, 3000)
+    sizes[:4] = (0, 1, 2, 64)
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    desc = np.repeat(base, sizes, axis=0)
+    flips = rng.integers(0, 256, (len(desc), 24)); nflip = rng.integers(0, 25, len(desc))
+    for i in range(len(desc)):
+        for b in set(flips[i, :nflip[i]].tolist()):
+            desc[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    post = frontend.FramePost()
+    dd, ds = _dev(torch, desc), _dev(torch, start)
+    best = torch.zeros(len(sizes), dtype=torch.int32, device="cuda"); out = torch.zeros((len(sizes), 32), dtype=torch.uint8, device="cuda")
+    post.distinctive_descriptors_dev(dd.data_ptr(), ds.data_ptr(), len(sizes), best.data_ptr(), out.data_ptr(), True)
+    wb, wo = oracle.post_distinctive_descriptors(desc, start)
+    assert (best.cpu().numpy() == wb).all()
+    has = sizes > 0
+    assert (out.cpu().numpy()[has] == wo[has]).all()
+    # more than 64 observations of one point is reported, not truncated
+    big = np.array([0, 65], np.int32); dbig = _dev(torch, rng.integers(0, 256, (65, 32), dtype=np.uint8))
+    with pytest.raises(frontend.SdplError):
+        dstart_big = _dev(torch, big)
+        post.distinctive_descriptors_dev(dbig.data_ptr(), dstart_big.data_ptr(), 1, best.data_ptr(), out.data_ptr(), True)
+    maxd = rng.uniform(1, 80, 100000).astype(np.float32); cur = rng.uniform(0.5, 90, 100000).astype(np.float32)
+    lsf = float(np.float32(np.log(np.float32(1.2))))
+    got = torch.zeros(len(maxd), dtype=torch.int32, device="cuda")
+    dmax, dcur = _dev(torch, maxd), _dev(torch, cur)
+    post.predict_scale_dev(dmax.data_ptr(), dcur.data_ptr(), len(maxd), lsf, 8, got.data_ptr(), True)
+    want = oracle.post_predict_scale(maxd, cur, lsf, 8)
+    got = got.cpu().numpy()
+    # logf of the C library vs the rounded double logarithm: equal except (rarely) when log(ratio) / log(1.2) sits on an integer
+    assert (got != want).mean() < 1e-4 and np.abs(got - want).max() <= 1

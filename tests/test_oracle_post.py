@@ -118,3 +118,28 @@ def test_features_in_area_equals_brute_force(oracle):
         want = np.nonzero(inside)[0]
         want = want[np.lexsort((want, py[want], px[want]))]
         np.testing.assert_array_equal(got, want)
+
+
+def test_distinctive_descriptor_and_predict_scale_equal_numpy(oracle):
+    rng = np.random.default_rng(11)
+    sizes = [1, 2, 3, 7, 20, 64, 0, 33]
+    start = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    base = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    desc = np.zeros((start[-1], 32), np.uint8)
+    for p, n in enumerate(sizes):
+        for i in range(n):
+            d = base[p].copy()
+            for b in rng.choice(256, int(rng.integers(0, 40)), replace=False):
+                d[b >> 3] ^= np.uint8(1 << (b & 7))
+            desc[start[p] + i] = d
+    best, out = oracle.post_distinctive_descriptors(desc, start)
+    for p, n in enumerate(sizes):
+        if n == 0:
+            assert best[p] == -1; continue
+        D = np.unpackbits(desc[start[p]:start[p + 1], None, :] ^ desc[None, start[p]:start[p + 1], :], axis=2).sum(2)
+        med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+        assert best[p] == int(np.argmin(med)) and (out[p] == desc[start[p] + best[p]]).all()
+    maxd = rng.uniform(1, 80, 5000).astype(np.float32); cur = rng.uniform(0.5, 90, 5000).astype(np.float32)
+    got = oracle.post_predict_scale(maxd, cur, np.float32(np.log(np.float32(1.2))), 8)
+    want = np.clip(np.ceil(np.log((maxd / cur).astype(np.float64)) / np.float64(np.float32(np.log(np.float32(1.2))))), 0, 7).astype(np.int32)
+    assert (got != want).mean() < 1e-3 and np.abs(got - want).max() <= 1        # float vs double log: only on exact level boundaries
