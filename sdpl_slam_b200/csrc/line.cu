@@ -874,6 +874,7 @@ struct sdpl_line {
   DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sd, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx, nfatab;
   int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
+  int grow_warps_small = 16, grow_ta_small = -1;  // small batches (tasks <= SMs): warps per task, phase-A cap (-1: grow_ta)
   int grow_forced = 0;   // SDPL_GROW given: use it for big batches only (single frames keep the 8-warp variant)
   int grow_smem = 0;     // tuning: dynamic shared memory requested by the <4,5> variant (caps its CTAs per SM without touching registers)
   int prof_detail = 0;   // sdpl_line_debug_grow_detail: thread 0 of every task accumulates prof[8..15] (costs ~3 % of the grow kernel)
@@ -1132,10 +1133,11 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     // two-phase waves (lsd_grow2.cuh).  Warps per task / CTAs per SM as below
     const bool small = nl * B <= o->sm_count;
     const bool forced = o->grow_warps > 0 && !(o->grow_forced && small);
-    const int nw = forced ? o->grow_warps : (small ? 8 : 4);
+    const int nw = forced ? o->grow_warps : (small ? o->grow_warps_small : 4);
     const int mb = forced && o->grow_minb > 0 ? o->grow_minb : (small ? 1 : 4);
-    D.grow_ta = o->grow_ta;
-    if (nw >= 8 && mb >= 2) k_lsd_grow2<8, 2><<<nl * B, 256, 0, st>>>(D);
+    D.grow_ta = (small && !forced && o->grow_ta_small >= 0) ? o->grow_ta_small : o->grow_ta;
+    if (nw >= 16) k_lsd_grow2<16, 1><<<nl * B, 512, 0, st>>>(D);
+    else if (nw >= 8 && mb >= 2) k_lsd_grow2<8, 2><<<nl * B, 256, 0, st>>>(D);
     else if (nw >= 8) k_lsd_grow2<8, 1><<<nl * B, 256, 0, st>>>(D);
     else if (nw >= 4 && mb <= 2) k_lsd_grow2<4, 2><<<nl * B, 128, 0, st>>>(D);
     else if (nw >= 4 && mb <= 4) k_lsd_grow2<4, 4><<<nl * B, 128, 0, st>>>(D);
@@ -1273,11 +1275,15 @@ int sdpl_line_create(sdpl_line** out, int nfeatures, int refine, float lsd_scale
     // tuning knob read at creation: "warps,ctas_per_sm,phaseA_cap[,dynamic_smem_bytes]" of the region-growing kernel (big batches)
     int nw = 0, mb = 0, ta = -1, sm = 0;
     if (sscanf(g, "%d,%d,%d,%d", &nw, &mb, &ta, &sm) >= 2) {
-      o->grow_warps = std::min(std::max(nw, 1), lsd::kMaxGrowWarps); o->grow_minb = std::max(mb, 1);
+      o->grow_warps = std::min(std::max(nw, 1), lsd::kMaxGrowWarps2); o->grow_minb = std::max(mb, 1);
       if (ta >= 0) o->grow_ta = ta;
       o->grow_smem = std::max(sm, 0);
       o->grow_forced = 1;
     }
+  }
+  if (const char* g = getenv("SDPL_GROW_SMALL")) {      // the same for small batches (every task has an SM to itself): "warps,phaseA_cap"
+    int nw = 0, ta = -1;
+    if (sscanf(g, "%d,%d", &nw, &ta) >= 1) { o->grow_warps_small = std::min(std::max(nw, 1), lsd::kMaxGrowWarps2); if (ta >= 0) o->grow_ta_small = ta; }
   }
   if (o->grow_smem > 0) SDPL_CUDA(cudaFuncSetAttribute(k_lsd_grow2<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->grow_smem));
   *out = o;
@@ -1504,7 +1510,7 @@ int sdpl_line_debug_pending(sdpl_line* o, int frame, int octave, double* out, in
 }
 
 // introspection: grow-kernel cycle counters of one task: {select, speculate, evaluate+commit, re-run, waves, re-runs, dead, seeds}
-int sdpl_line_debug_grow_detail(sdpl_line* o, int on) { if (!o) return SDPL_ERR_ARG; o->prof_detail = on != 0; return SDPL_OK; }
+int sdpl_line_debug_grow_detail(sdpl_line* o, int on) { if (!o) return SDPL_ERR_ARG; o->prof_detail = on; return SDPL_OK; }
 int sdpl_line_debug_grow_profile(sdpl_line* o, int frame, int octave, long long* out8) {
   if (!o || o->gw == 0 || frame < 0 || frame >= o->last_B || octave < 0 || octave >= o->nlevels || !out8) return SDPL_ERR_ARG;
   SDPL_CUDA(cudaSetDevice(o->device));

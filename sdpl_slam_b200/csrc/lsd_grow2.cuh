@@ -18,6 +18,8 @@
 //            sequential result by induction over the scan order; in the common case one step costs one round of loads and one
 //            polynomial arctangent for ~3 expansions instead of ~3 dependent rounds.  Rectangle fits and refine statistics were
 //            already warp-cooperative; the sequential re-runs use the same routine without stamps.
+// (A re-run of a doubtful seed is a region of 5.5 pixels on average -- profiles/r2_rerun_statistics.txt -- and still costs 7 - 10 us;
+// letting ONE lane grow it before the warp takes over was measured slower, 8.0 -> 8.7 ms per frame of re-runs, and was removed.)
 // Results of a seed live in a per-slot context in global memory (SlotCtx) instead of the registers of "its" thread, so any
 // warp can finish any seed and the commit rounds read them back.
 #pragma once
@@ -26,7 +28,8 @@
 namespace sdpl {
 namespace lsd {
 
-constexpr int kCtxSlots = 256;              // seed slots per task (>= seeds per wave)
+constexpr int kCtxSlots = 512;              // seed slots per task (>= seeds per wave)
+constexpr int kMaxGrowWarps2 = 16;          // warps per task of the two-phase schedule (512-seed waves)
 
 // position of the (k+1)-th set bit of m (k < popc(m)): five popc steps instead of the software loop behind __fns
 __device__ __forceinline__ int nth_set_bit(uint32_t m, int k) {
@@ -81,7 +84,7 @@ __device__ __noinline__ bool coop_grow(const Task& T, const bool SPEC, int* cons
 #pragma unroll 1
   while (i < n) {
     const int m = min(4, n - i);
-    if (T.prof_detail && threadIdx.x == 0) T.prof[14] += 1;
+    if (T.prof_detail == 1 && threadIdx.x == 0) T.prof[14] += 1;
     const bool act = j < m;
     const int p = list[i + (act ? j : 0)];
     const int qx = xy_x(p) + ndx, qy = xy_y(p) + ndy;
@@ -292,7 +295,7 @@ __device__ __noinline__ void seed_pipeline_coop(const Task& T, const bool SPEC, 
       }
       const long long pg0 = clock64();
       const bool ok = coop_grow(T, SPEC, cur, capc, n, i, sumdx, sumdy, ra, prec, stamp, bx0, by0, bx1, by1);
-      if (T.prof_detail && threadIdx.x == 0) T.prof[11] += clock64() - pg0;
+      if (T.prof_detail == 1 && threadIdx.x == 0) T.prof[11] += clock64() - pg0;
       if (state == 0) { R.n1 = n; R.nf = n; } else { if (SPEC) R.n2_orig = n; R.nf = n; }
       if (!ok) { R.ok = 0; break; }
       if (state == 0 ? (n < T.min_reg) : (n < 2)) break;
@@ -318,13 +321,13 @@ __device__ __noinline__ void seed_pipeline_coop(const Task& T, const bool SPEC, 
     }
     const long long pr0 = clock64();
     coop_region2rect_smem(T, sb, cur, n, ra, R.rec);
-    if (T.prof_detail && threadIdx.x == 0) T.prof[12] += clock64() - pr0;
+    if (T.prof_detail == 1 && threadIdx.x == 0) T.prof[12] += clock64() - pr0;
     const double density = (double)n / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
     if (state == 0) {
       if (T.refine <= 0 || density >= T.density_th) { R.has_rect = 1; break; }
       const long long pt0 = clock64();
       prec = SPEC ? coop_refine_tau<false>(T, cur, n, sx, sy, seed_ang, R.rec.width) : coop_refine_tau<true>(T, cur, n, sx, sy, seed_ang, R.rec.width);
-      if (T.prof_detail && threadIdx.x == 0) T.prof[13] += clock64() - pt0;
+      if (T.prof_detail == 1 && threadIdx.x == 0) T.prof[13] += clock64() - pt0;
       __syncwarp();
       state = 1;
       if (SPEC) { cur = reg + n; capc = cap - n; R.foff = n; stamp = stamp0 | 1u; }   // the first region stays: it is part of E
@@ -681,6 +684,12 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
           divmod_w(dw, seed_k, ssy, ssx);
           seed_pipeline_coop(T, false, S.sb[warp], seed_k, ssx, ssy, T.reg_serial, T.npx, 0u, 0, 0, 0.f, 0.f, 0.0, 0, 0, 0, 0, Q);
           has = Q.has_rect;
+          if (T.prof_detail == 2 && lane == ks_lane) {          // re-run statistics: pixels grown first / re-grown, rectangles
+            atomicAdd((unsigned long long*)&T.prof[11], (unsigned long long)Q.n1);
+            atomicAdd((unsigned long long*)&T.prof[12], (unsigned long long)Q.n2_orig + (unsigned long long)Q.nf);
+            atomicAdd((unsigned long long*)&T.prof[13], (unsigned long long)Q.has_rect);
+            atomicMax((unsigned long long*)&T.prof[14], (unsigned long long)Q.n1);
+          }
           if (lane == ks_lane) {
             if (has) append_rect(T, npend, Q.rec, (int)((wave << 11) | (tid << 1) | 1), my_seed, Q.nf);
             S.rb[0] = Q.bx0; S.rb[1] = Q.by0; S.rb[2] = Q.bx1; S.rb[3] = Q.by1;

@@ -368,7 +368,7 @@ class Lineextractor(_Profiled):
 
     def grow_detail(self, on=True):
         """detailed region-growing counters (grow_profile's phaseA ... phaseA_wait entries); off by default"""
-        _check(self._L.sdpl_line_debug_grow_detail(self._h, int(bool(on))))
+        _check(self._L.sdpl_line_debug_grow_detail(self._h, int(on)))
 
     def grow_profile(self, octave, frame=0):
         out = np.zeros(16, np.int64)

@@ -68,7 +68,7 @@ def test_speculative_equals_sequential(frontend):
 
 def test_benchmarked_grow_variants_match_oracle(frontend, oracle):
     """The schedule bench.py times: a batch big enough that the automatic choice is the many-CTAs-per-SM variant
-    (k_lsd_grow_block<4, 4> once frames x octaves exceeds the SM count), every frame compared with the oracle; then the
+    (k_lsd_grow2<4, 4> once frames x octaves exceeds the SM count), every frame compared with the oracle; then the
     NW x MINB variants pinned through set_serial on a sub-batch, byte-identical to the verified output."""
     seeds = range(1000, 1096)
     imgs = synth.frames(seeds, 375, 1242)
