@@ -1,7 +1,10 @@
 """GPU parity: CUDA line front-end (LSD + KeyLine + LBD through the C ABI) vs the CPU oracle on the same seeded frames.
 Bar (BASELINE.json north_star): line sets / octaves / pixel counts identical, endpoints within 1e-3 px, descriptors
-bit-exact wherever the keyline agrees.  The double-precision transcendental calls (cos/sin/log/exp) are CUDA's on the GPU
-and glibc's in the oracle, so float equality of endpoints is reported and required for >= 99.5 % of the lines."""
+bit-exact wherever the keyline agrees.  Since sin / cos are the shared strict-IEEE implementation (include/sdpl_trig.h) and the
+log-gamma table comes from the host, the only transcendental left to the two C libraries is the double atan2 behind KeyLine::angle:
+observed state = every key line float-identical and every LBD row identical on all frames of this file and on the 96-frame batch
+(0 of 96 frames differ); the assertions keep a margin for a last-bit atan2 difference (>= 99.5 % of the lines float-equal, the LBD
+rows of the others within 8 of 256 bits)."""
 import numpy as np
 import pytest
 
@@ -25,10 +28,10 @@ def _compare_lines(kg, dg, kr, dr):
     for name in FLOAT_FIELDS:
         same &= kg[name] == kr[name]
     np.testing.assert_array_equal(dg[same], dr[same])
-    # descriptors of lines whose floats differ in the last bit may differ in a few bits only
+    # descriptors of lines whose floats differ in the last bit may differ in a few bits only (round 1 allowed 32; none observed)
     if (~same).any():
         bits = np.unpackbits(dg[~same] ^ dr[~same], axis=1).sum(1)
-        assert bits.max() <= 32
+        assert bits.max() <= 8
     return float(same.mean())
 
 
