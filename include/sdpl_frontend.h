@@ -119,9 +119,9 @@ int sdpl_line_debug_grow_profile(sdpl_line* h, int frame, int octave, long long*
 /* switch the detailed counters [8..15] on / off (off by default: they cost about 3 % of the region-growing kernel) */
 int sdpl_line_debug_grow_detail(sdpl_line* h, int on);
 int sdpl_line_last_launches(const sdpl_line* h);
-/* test / tuning knob, LSD region-growing schedule (bits 0-1; bits 8.. an optional size override): 0 = speculative waves of
- * 32*NW seeds, one CTA of NW warps per (frame, octave) (default, NW = 4), 1 = strictly one seed at a time, 2 = speculative with
- * dynamic lane scheduling and a re-order buffer (experimental), 3 = single-warp waves of 32 seeds; all give identical results */
+/* test / tuning knob, LSD region-growing schedule (bits 0-1; further bits select kernel variants, see line.cu): 0 = speculative waves,
+ * one CTA of several warps per (frame, octave) (default), 1 = strictly one seed at a time, 3 = single-warp waves of 32 seeds; all give
+ * identical results; 2 is not a schedule any more (SDPL_ERR_ARG) */
 int sdpl_line_set_serial(sdpl_line* h, int on);
 
 /* ------------------------------------------------------------------------------------------------

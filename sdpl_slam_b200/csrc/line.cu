@@ -62,7 +62,6 @@ struct LineDev {
   long long* prof; int prof_detail;
   const double* lgam; int lgam_n;
   const double* nfa_tab;               // [nl][kNfaTabLevels][kNfaTabTri] (lsd::nfa_lookup), filled by k_nfa_table at set-up
-  lsd::Rect* rob_rect; lsd::RobEntry* rob; int rob_w, rob_w_run;
   int* nbig; int* bigidx;
   double rho, prec, p, density_th, log_eps, scale;
   int refine, serial_mode;
@@ -408,7 +407,6 @@ __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::T
   T.prof_detail = D.prof_detail;
   T.lgam = D.lgam; T.lgam_n = D.lgam_n;
   T.nfa_tab = D.nfa_tab ? D.nfa_tab + (size_t)o * lsd::kNfaTabLevels * lsd::kNfaTabTri : nullptr;
-  T.rob_rect = D.rob_rect + (size_t)task * D.rob_w; T.rob = D.rob + (size_t)task * D.rob_w; T.rob_w = D.rob_w_run;
 }
 
 // L5 scheduling.  A task's run time follows its number of candidate seeds, and tasks differ by 2x within a batch; CTAs are
@@ -427,12 +425,11 @@ __global__ void k_lsd_task_rank(LineDev D, int ntask) {
 }
 
 __global__ void __launch_bounds__(32) k_lsd_grow(LineDev D) {
-  __shared__ lsd::RobShared S;
+  __shared__ int sel[32];
   const int task = D.task_order[blockIdx.x], f = task / D.nl, o = task % D.nl;
   lsd::Task T;
   make_task(D, f, o, T);
-  if (D.serial_mode == 2) lsd::grow_task_rob(T, S);               // 2: dynamic lane scheduling + re-order buffer (experimental)
-  else lsd::grow_task(T, D.serial_mode == 1, S.sel);               // 3: 32-seed lock-step waves, 1: one seed at a time
+  lsd::grow_task(T, D.serial_mode == 1, sel);                      // 3: 32-seed lock-step waves, 1: one seed at a time
 }
 
 // default schedule: waves of 32*NW seeds, one CTA of NW warps per task.  MINB = CTAs per SM the register budget is cut for.
@@ -872,8 +869,8 @@ struct sdpl_line {
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
   DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sd, err, tables, tmpkl;
-  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, robrect, rob, nbig, bigidx, ctx, nfatab;
-  int rob_w = 2048, rob_w_run = 2048, grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
+  DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, nbig, bigidx, ctx, nfatab;
+  int grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
   int grow_warps_small = 16, grow_ta_small = -1;  // small batches (tasks <= SMs): warps per task, phase-A cap (-1: grow_ta)
   int grow_forced = 0;   // SDPL_GROW given: use it for big batches only (single frames keep the 8-warp variant)
   int grow_smem = 0;     // tuning: dynamic shared memory requested by the <4,5> variant (caps its CTAs per SM without touching registers)
@@ -1033,8 +1030,6 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   if ((rc = o->tmpkl.reserve(sizeof(sdpl_keyline) * (size_t)D.pend_cap * nl * (o->nfeatures ? B : 1)))) return rc;
   if ((rc = o->err.reserve(sizeof(int)))) return rc;
   if ((rc = o->prof.reserve(sizeof(long long) * 16 * nl * B))) return rc;
-  if ((rc = o->robrect.reserve(sizeof(lsd::Rect) * (size_t)o->rob_w * nl * B))) return rc;
-  if ((rc = o->rob.reserve(sizeof(lsd::RobEntry) * (size_t)o->rob_w * nl * B))) return rc;
   if ((rc = o->nbig.reserve(sizeof(int) * 2 * nl * B))) return rc;
   if ((rc = o->ctx.reserve(sizeof(lsd::SlotCtx) * (size_t)lsd::kCtxSlots * nl * B))) return rc;
   if ((rc = o->bigidx.reserve(sizeof(int) * (size_t)D.pend_cap * nl * B))) return rc;
@@ -1072,7 +1067,6 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sd = o->sd.as<short2>();
   D.err = o->err.as<int>(); D.prof = o->prof.as<long long>(); D.lgam = o->lgam.as<double>(); D.lgam_n = kLgamN;
   D.ctx = o->ctx.as<lsd::SlotCtx>(); D.grow_ta = o->grow_ta;
-  D.rob_rect = o->robrect.as<lsd::Rect>(); D.rob = o->rob.as<lsd::RobEntry>(); D.rob_w = o->rob_w;
   D.nbig = o->nbig.as<int>(); D.bigidx = o->bigidx.as<int>();
   D.B = B;
   {
@@ -1094,7 +1088,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   int rc = line_setup(o, w, h, B);
   if (rc) return rc;
   LineDev& D = o->D;
-  D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride; D.serial_mode = o->serial_mode; D.rob_w_run = o->rob_w_run;
+  D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride; D.serial_mode = o->serial_mode;
   D.prof_detail = o->prof_detail;
   if (D.prof_detail) SDPL_CUDA(cudaMemsetAsync(D.prof, 0, sizeof(long long) * 16 * o->nlevels * B, o->stream));
   cudaStream_t st = o->stream;
@@ -1295,7 +1289,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
   for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
-                    &o->g, &o->sd, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->robrect, &o->rob, &o->nbig, &o->bigidx, &o->ctx, &o->nfatab})
+                    &o->g, &o->sd, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->nbig, &o->bigidx, &o->ctx, &o->nfatab})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);
   o->timer.release();
@@ -1348,21 +1342,18 @@ int sdpl_line_stage_times(sdpl_line* o, float* ms, const char** names, int* laun
   cudaSetDevice(o->device);
   return o->timer.read(ms, names, launches, cap);
 }
-// test / tuning knob: region-growing schedule (bits 0-1). 0 = speculative waves of 32*NW seeds, one CTA of NW warps per task
-// (default, NW = 4; bits 8.. override NW), 1 = strictly one seed at a time (no speculation), 2 = speculative with dynamic lane
-// scheduling and a re-order buffer (experimental: measured slower on B200; bits 8.. override the buffer size),
-// 3 = single-warp waves of 32 seeds.  All give identical results.
+// test / tuning knob: region-growing schedule (bits 0-1).  0 = speculative waves, one CTA of NW warps per task (default: the two-phase
+// schedule of lsd_grow2.cuh; bit 2 selects the round-1 per-lane schedule instead), 1 = strictly one seed at a time (no speculation),
+// 3 = single-warp waves of 32 seeds.  Bits 8-11 / 12-15: warps per task / CTAs per SM of mode 0; bits 3-7: CTAs per SM the second
+// NFA pass is compiled for; bits 24-30: phase-A expansion cap + 1.  All give identical results.  (Mode 2, a re-order-buffer schedule
+// of round 1, was measured 3x slower than the waves and has been removed.)
 int sdpl_line_set_serial(sdpl_line* o, int on) {
-  if (!o || on < 0) return SDPL_ERR_ARG;
-  // bits 0-1: schedule; bits 8..: re-order buffer size override (power of two, <= allocated), for tuning
-  const int w0 = (on >> 8) & 0xffff;
-  if (w0 && (on & 3) == 2 && (w0 < 1 || w0 > 2048 || (w0 & (w0 - 1)))) return SDPL_ERR_ARG;
+  if (!o || on < 0 || (on & 3) == 2) return SDPL_ERR_ARG;
   o->serial_mode = on & 3;
   if ((on >> 3) & 31) o->nfa_minb = (on >> 3) & 31;    // bits 3-7: CTAs per SM the second NFA pass is compiled for (tuning)
   o->grow_legacy = (on >> 2) & 1;                    // bit 2: the round-1 per-lane schedule instead of the two-phase one
   if ((on >> 24) & 0x7f) o->grow_ta = ((on >> 24) & 0x7f) - 1;   // bits 24-30: phase-A expansion cap + 1
   const int w = (on >> 8) & 0xffff;
-  if (w && o->serial_mode == 2) o->rob_w_run = std::max(w, 32);
   if (w && o->serial_mode == 0) { o->grow_warps = std::min(w & 15, lsd::kMaxGrowWarps); if (w >> 4) o->grow_minb = w >> 4; }
   return SDPL_OK;
 }

@@ -45,7 +45,6 @@ struct __align__(8) Pending {      // a rectangle waiting for / after NFA valida
   int seed, npix;                  // seed pixel index and number of pixels finally marked (introspection)
 };
 
-struct RobEntry;
 struct Task {                      // one (frame, level)
   int w, h, npx;
   const PxA* px;
@@ -60,7 +59,6 @@ struct Task {                      // one (frame, level)
   double prec, p, log_nt, density_th, log_eps, scale /* lsd scale as a double, (double)0.8f */;
   int min_reg, refine;
   int* err;
-  struct RobEntry* rob; Rect* rob_rect; int rob_w;   // re-order buffer (rob_w entries, power of two): metadata + rectangle staging
   const double* lgam; int lgam_n;  // log_gamma(i) for integer i < lgam_n (same formulas, tabulated once per handle)
   const double* nfa_tab;           // nfa(n, k, p / 2^j) of this octave for n <= kNfaTabN, j < kNfaTabLevels (or null): see nfa_lookup
   int prof_detail;                 // != 0: warp 0 also accumulates prof[8..15] (phase A / B split, growth, rectangle fit, refine cycles, steps)
@@ -1051,363 +1049,6 @@ __device__ void grow_task_block(const Task& T, BlockShared& S) {
   if (tid == 0 && T.prof) {
     T.prof[0] = t_sel; T.prof[1] = t_spec; T.prof[2] = t_commit - t_redo; T.prof[3] = t_redo; T.prof[4] = wave; T.prof[5] = n_redo;
     T.prof[6] = n_round; T.prof[7] = n_seed;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same algorithm with DYNAMIC lane scheduling and a RE-ORDER BUFFER.  Instead of waiting for the slowest of 32 seeds,
-// every lane grows one seed at a time and, when it finishes, parks the result in a ring of rob_w entries (metadata and
-// rectangle in global memory, pixel list in the lane's own ring segment) and immediately takes the next seed from a small
-// shared-memory queue of upcoming seeds.  Seeds carry a sequence number; ownership priority is the sequence number
-// (stamp = (0x3FFFFFFF - seq) << 1 | phase, so an earlier seed always has the larger stamp) and retirement is strictly
-// in sequence order from `head`, 32 entries per round (lane d retires entry head+d), with the same validate / commit /
-// re-run rules as grow_task.  The per-seed pipeline is a resumable state machine, so long regions and long rectangle
-// fits never stall the other lanes: a long region at the head only delays retirement, not the growth of later seeds.
-// ------------------------------------------------------------------------------------------------
-constexpr int kRobQ = 64;                       // seeds pre-selected per refill
-struct __align__(16) RobEntry { int seed, base, nE, foff, nf, meta, pad0, pad1; };   // meta: bit0-1 stat, bit2 has_rect, bits 8.. owner lane
-struct RobShared {
-  int q_seed[kRobQ];
-  int q_head, q_n;               // consumed / available seeds of the queue
-  uint32_t q_seq0;               // sequence number of q_seed[0]
-  unsigned int freed[32];        // per lane: list ints released by retirement (running total)
-  int sel[32];
-};
-enum { PH_IDLE = 0, PH_START, PH_GROW, PH_RECT_A, PH_RECT_B, PH_RECT_C, PH_REFSTAT, PH_REDUCE, PH_DONE, PH_ABORT };
-enum { CTX_FIRST = 0, CTX_SECOND, CTX_REDUCE };
-
-__device__ __forceinline__ int ld_meta(const RobEntry* e) { return *(const volatile int*)&e->meta; }
-
-__device__ void grow_task_rob(const Task& T, RobShared& S) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t lt = (1u << lane) - 1u;
-  const int w = T.w, h = T.h;
-  int* const seg = T.reg_spec + (size_t)lane * T.lane_cap;     // this lane's list ring (lane_cap is a power of two)
-  const unsigned int mask = (unsigned int)T.lane_cap - 1u;
-  const uint32_t robm = (uint32_t)T.rob_w - 1u;
-  int cursor = 0, npend = 0;
-  uint32_t head = 0, next_seq = 0;
-  if (lane == 0) { S.q_head = 0; S.q_n = 0; S.q_seq0 = 0; }
-  S.freed[lane] = 0u;
-  __syncwarp();
-  // per-lane seed state
-  int seed = -1, phase = PH_IDLE, ctx = CTX_FIRST, i = 0, n = 0, n1 = 0, n2o = 0, has_rect = 0, cnt = 0, nxt = -1;
-  unsigned int alloc = 0, base = 0, cb = 0;      // ring allocation total, list base of the seed in flight, base of the current list
-  uint32_t seq = 0, stamp = 0;
-  float sumdx = 0.f, sumdy = 0.f;
-  double ra = 0, prec_cur = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, xc = 0, yc = 0, rad_sq = 0, ang_c = 0;
-  Rect rec;
-  long long t_sel = 0, t_spec = 0, t_commit = 0, t_redo = 0, n_redo = 0, n_dead = 0, n_tick = 0;
-  constexpr int kUnits = 24;
-#define SEG(k) seg[((k)) & mask]
-  while (true) {
-    long long c0 = clock64();
-    // ---- refill the seed queue with the next free seeds, in order ----
-    {
-      int qh = S.q_head, qn = S.q_n;
-      if (qh >= qn && cursor < T.ndef) {
-        const int want = min(kRobQ, T.rob_w - (int)(next_seq - head));
-        int nsel = 0;
-        while (nsel < want && cursor < T.ndef) {
-          const int idx = cursor + lane;
-          const int p = idx < T.ndef ? (int)T.order[idx] : -1;
-          const bool fr = p >= 0 && !(ld_state(T.state + (p >= 0 ? p : 0)) & kUsed);
-          const uint32_t m = __ballot_sync(0xffffffffu, fr);
-          const int c = __popc(m);
-          const int take = min(c, want - nsel);
-          const int rank = __popc(m & lt);
-          if (fr && rank < take) S.q_seed[nsel + rank] = p;
-          if (c > take) cursor += (int)__fns(m, 0, take) + 1;
-          else cursor += 32;
-          nsel += take;
-        }
-        // entries of the new seeds start as "running"
-        for (int k = lane; k < nsel; k += 32) *(volatile int*)&T.rob[(next_seq + (uint32_t)k) & robm].meta = 0;
-        __syncwarp();
-        if (lane == 0) { S.q_head = 0; S.q_n = nsel; S.q_seq0 = next_seq; }
-        next_seq += (uint32_t)nsel;
-        __syncwarp();
-      }
-    }
-    {
-      const bool busy = phase != PH_IDLE;
-      if (next_seq == head && !__any_sync(0xffffffffu, busy)) break;     // nothing in flight and no seeds left
-    }
-    long long c1 = clock64(); t_sel += c1 - c0;
-    n_tick++;
-    // ---- every lane works for kUnits units: take a seed when idle, advance it, park it when finished.
-    //      All global loads of a unit are issued in one convergent block (one memory latency per unit for the whole
-    //      warp, whatever phases its lanes are in); the phase-specific arithmetic follows in divergent branches. ----
-#pragma unroll 1
-    for (int u = 0; u < kUnits; u++) {
-      // stage 0: an idle lane takes the next seed of the queue
-      if (phase == PH_IDLE) {
-        int k = -1;
-        if (S.q_head < S.q_n) k = atomicAdd(&S.q_head, 1);
-        if (k >= 0 && k < S.q_n) {
-          seed = S.q_seed[k]; seq = S.q_seq0 + (uint32_t)k;
-          stamp = (0x3FFFFFFFu - seq) << 1;
-          base = alloc; cb = base;
-          n1 = 0; n2o = 0; has_rect = 0; ctx = CTX_FIRST; prec_cur = T.prec;
-          n = 0; i = 0; nxt = seed;
-          phase = PH_START;
-        }
-      }
-      // stage 1: loads.  `nxt` is the list element at position i (the seed for PH_START)
-      const bool step = (phase == PH_START) || (phase >= PH_GROW && phase <= PH_REFSTAT && i < n);
-      const bool grow = phase == PH_GROW && step;
-      const int p = step ? nxt : 0;
-      const int py = p / w, px = p - py * w;
-      uint32_t st[9];
-      PxA pa[9];
-#pragma unroll
-      for (int k = 0; k < 9; k++) {
-        const int yy = py - 1 + k / 3, xx = px - 1 + k % 3;
-        const bool in = (k == 4) ? (step && !grow) : (grow && yy >= 0 && yy < h && xx >= 0 && xx < w);
-        const int q = yy * w + xx;
-        st[k] = (in && (grow || phase == PH_START)) ? ld_state(T.state + q) : kUsed;
-        if (in && (grow || phase == PH_START || phase == PH_REFSTAT)) pa[k] = T.px[q]; else pa[k].ang = kNotDef;
-      }
-      const int g2v = (step && (phase == PH_RECT_A || phase == PH_RECT_B)) ? T.g2[p] : 0;
-      const int n_start = n;
-      int pf = -1;
-      if (step && phase != PH_START && i + 1 < n_start) pf = SEG(cb + i + 1);     // next list element, off the critical path
-      // stage 2: arithmetic
-      if (phase == PH_START) {
-        // start of region_grow: the seed itself (first growth: stamp phase 0, re-growth: phase 1)
-        if (st[4] > stamp || (alloc - S.freed[lane]) + (cb - base) + 64u > (unsigned int)T.lane_cap) { phase = PH_ABORT; n = 0; }
-        else {
-          claim_max(&T.state[seed], stamp);
-          SEG(cb) = seed; n = 1; i = 0; nxt = seed;
-          ra = pa[4].ang;
-          sumdx = (float)sdpl_cos(ra); sumdy = (float)sdpl_sin(ra);
-          phase = PH_GROW;
-        }
-      } else if (phase == PH_GROW) {
-        if (step) {
-          const unsigned int room = (unsigned int)T.lane_cap - (alloc - S.freed[lane]) - (cb - base);
-          int first = -1;
-#pragma unroll
-          for (int k = 0; k < 9; k++) {
-            if (k == 4 || phase != PH_GROW) continue;
-            const uint32_t s = st[k];
-            if (s & kUsed) continue;
-            if (s == stamp) continue;
-            if (!aligned_angle(pa[k].ang, ra, prec_cur)) continue;
-            if (s > stamp || (unsigned int)n + 1u >= room) { phase = PH_ABORT; continue; }
-            const int q = (py - 1 + k / 3) * w + (px - 1 + k % 3);
-            claim_max(&T.state[q], stamp);
-            if (first < 0) first = q;
-            SEG(cb + n) = q; n++;
-            sumdx = __fadd_rn(sumdx, pa[k].c);
-            sumdy = __fadd_rn(sumdy, pa[k].s);
-            ra = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
-          }
-          i++;
-          nxt = (i < n_start) ? pf : first;       // the queue was empty: the first pixel just appended is next
-        } else {
-          // growth finished
-          if (ctx == CTX_FIRST) n1 = n; else n2o = n;
-          if ((ctx == CTX_FIRST) ? (n1 < T.min_reg) : (n < 2)) { phase = PH_DONE; }
-          else { phase = PH_RECT_A; i = 0; a0 = 0; a1 = 0; a2 = 0; nxt = SEG(cb); }
-        }
-      } else if (phase == PH_RECT_A) {          // region2rect: weighted centroid
-        if (step) {
-          const double wgt = modgrad_of(g2v);
-          a0 += (double)px * wgt; a1 += (double)py * wgt; a2 += wgt;
-          i++; nxt = pf;
-        } else {
-          rec.x = a0 / a2; rec.y = a1 / a2;
-          phase = PH_RECT_B; i = 0; a0 = 0; a1 = 0; a2 = 0; nxt = SEG(cb);
-        }
-      } else if (phase == PH_RECT_B) {          // get_theta: inertia matrix
-        if (step) {
-          const double dx = (double)px - rec.x, dy = (double)py - rec.y, wgt = modgrad_of(g2v);
-          a0 += dy * dy * wgt; a1 += dx * dx * wgt; a2 -= dx * dy * wgt;
-          i++; nxt = pf;
-        } else {
-          const double Ixx = a0, Iyy = a1, Ixy = a2;
-          const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
-          double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)(lambda - Ixx), (float)Ixy)
-                                                 : (double)fast_atan2_deg((float)Ixy, (float)(lambda - Iyy));
-          theta *= kDegToRad;
-          if (angle_diff(theta, ra) > T.prec) theta += kPI;
-          rec.theta = theta; rec.dx = sdpl_cos(theta); rec.dy = sdpl_sin(theta);
-          phase = PH_RECT_C; i = 0; a0 = 0; a1 = 0; a2 = 0; a3 = 0; nxt = SEG(cb);
-        }
-      } else if (phase == PH_RECT_C) {          // projections -> rectangle
-        if (step) {
-          const double rdx = (double)px - rec.x, rdy = (double)py - rec.y;
-          const double l = rdx * rec.dx + rdy * rec.dy;
-          const double ww = -rdx * rec.dy + rdy * rec.dx;
-          if (l > a1) a1 = l; else if (l < a0) a0 = l;
-          if (ww > a3) a3 = ww; else if (ww < a2) a2 = ww;
-          i++; nxt = pf;
-        } else {
-          rec.x1 = rec.x + a0 * rec.dx; rec.y1 = rec.y + a0 * rec.dy;
-          rec.x2 = rec.x + a1 * rec.dx; rec.y2 = rec.y + a1 * rec.dy;
-          rec.width = a3 - a2;
-          rec.prec = T.prec; rec.p = T.p;
-          if (rec.width < 1.0) rec.width = 1.0;
-          const double density = (double)n / (dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
-          if (ctx == CTX_FIRST) {
-            if (T.refine <= 0 || density >= T.density_th) { has_rect = 1; phase = PH_DONE; }
-            else {
-              xc = (double)(seed % w); yc = (double)(seed / w); ang_c = T.px[seed].ang;
-              phase = PH_REFSTAT; i = 0; a0 = 0; a1 = 0; cnt = 0; nxt = SEG(cb);
-            }
-          } else if (density >= T.density_th) { has_rect = 1; phase = PH_DONE; }
-          else {
-            if (ctx == CTX_SECOND) {
-              xc = (double)(seed % w); yc = (double)(seed / w);
-              const double r1 = dist_sq(xc, yc, rec.x1, rec.y1), r2 = dist_sq(xc, yc, rec.x2, rec.y2);
-              rad_sq = r1 > r2 ? r1 : r2;
-              ctx = CTX_REDUCE;
-            }
-            rad_sq *= 0.75 * 0.75;
-            phase = PH_REDUCE; i = 0;
-          }
-        }
-      } else if (phase == PH_REFSTAT) {         // refine: angle statistics near the seed
-        if (step) {
-          if (dist(xc, yc, (double)px, (double)py) < rec.width) {
-            const double d = angle_diff_signed(pa[4].ang, ang_c);
-            a0 += d; a1 += d * d; ++cnt;
-          }
-          i++; nxt = pf;
-        } else {
-          const double mean_angle = a0 / (double)cnt;
-          prec_cur = 2.0 * sqrt((a1 - 2.0 * mean_angle * a0) / (double)cnt + mean_angle * mean_angle);
-          // re-grow from the seed with the new tolerance, list placed behind the first region
-          cb = base + (unsigned int)n1; ctx = CTX_SECOND; stamp |= 1u;
-          n = 0; i = 0; nxt = seed;
-          phase = PH_START;
-        }
-      } else if (phase == PH_REDUCE) {          // reduce_region_radius: one shrink pass (rare; plain loads)
-        if (i < n) {
-          const int q = SEG(cb + i);
-          if (dist_sq(xc, yc, (double)(q % w), (double)(q / w)) > rad_sq) { SEG(cb + i) = SEG(cb + n - 1); SEG(cb + n - 1) = q; --n; }
-          else i++;
-        } else {
-          if (n < 2) phase = PH_DONE;
-          else { phase = PH_RECT_A; i = 0; a0 = 0; a1 = 0; a2 = 0; nxt = SEG(cb); }
-        }
-      }
-      // ---- park a finished seed in the re-order buffer; the lane is free again ----
-      if (phase == PH_DONE || phase == PH_ABORT) {
-        RobEntry* e = T.rob + (seq & robm);
-        const int nE = (ctx == CTX_FIRST) ? n : n1 + max(n2o, n);
-        e->seed = seed; e->base = (int)base; e->nE = nE; e->foff = (ctx == CTX_FIRST) ? 0 : n1; e->nf = n;
-        const int hr = (phase == PH_DONE) ? has_rect : 0;
-        if (hr) T.rob_rect[seq & robm] = rec;
-        __threadfence_block();
-        *(volatile int*)&e->meta = (phase == PH_DONE ? 1 : 2) | (hr << 2) | (lane << 8);
-        alloc += (unsigned int)nE;
-        phase = PH_IDLE; seed = -1;
-      }
-    }
-    __syncwarp();
-    long long c2 = clock64(); t_spec += c2 - c1;
-    // ---- retire finished entries in sequence order, 32 per round; lane d handles entry head + d ----
-    while (true) {
-      const uint32_t inflight = next_seq - head;
-      RobEntry* e = T.rob + ((head + (uint32_t)lane) & robm);
-      const int meta = (uint32_t)lane < inflight ? ld_meta(e) : 0;
-      const uint32_t finm = __ballot_sync(0xffffffffu, (meta & 3) != 0);
-      const int ncons = (finm == 0xffffffffu) ? 32 : (__ffs(~finm) - 1);     // consecutive finished entries from head
-      if (ncons == 0) break;
-      const uint32_t allm = ncons >= 32 ? 0xffffffffu : ((1u << ncons) - 1u);
-      uint32_t handled = 0;
-      const bool mine = lane < ncons;
-      int eseed = 0, enE = 0, efoff = 0, enf = 0, eowner = 0;
-      unsigned int ebase = 0;
-      if (mine) {
-        const int4 v = __ldcg((const int4*)e);
-        eseed = v.x; ebase = (unsigned int)v.y; enE = v.z; efoff = v.w;
-        enf = __ldcg(&e->nf);
-        eowner = meta >> 8;
-      }
-      const bool edone = mine && (meta & 3) == 1;
-      const bool ehas = mine && ((meta >> 2) & 1);
-      const uint32_t key = 0x3FFFFFFFu - (head + (uint32_t)lane);
-      const int* eseg = T.reg_spec + (size_t)eowner * T.lane_cap;
-#define ESEG(k) eseg[(ebase + (unsigned int)(k)) & mask]
-      bool retired = false;
-      while (handled != allm) {
-        bool dead = false, good = false;
-        if (mine && !retired) {
-          dead = (ld_state(T.state + eseed) & kUsed) != 0;
-          if (!dead && edone) {
-            int ok = 1;
-            for (int k = 0; k < enE; k++) ok &= ((ld_state(T.state + ESEG(k)) >> 1) == key);
-            good = ok != 0;
-          }
-        }
-        const uint32_t deadm = __ballot_sync(0xffffffffu, dead), goodm = __ballot_sync(0xffffffffu, good);
-        const uint32_t pendm = allm & ~handled;
-        const uint32_t bad = pendm & ~deadm & ~goodm;
-        const int kstar = bad ? __ffs(bad) - 1 : 32;
-        const uint32_t below = kstar >= 32 ? 0xffffffffu : ((1u << kstar) - 1u);
-        const bool do_commit = good && ((below >> lane) & 1u);
-        const bool do_drop = dead && ((below >> lane) & 1u);
-        n_dead += __popc(deadm & below & pendm);
-        if (do_commit || do_drop) {
-          // release everything this seed still owns speculatively, then mark the final set
-          for (int k = 0; k < enE; k++) {
-            const int q = ESEG(k);
-            if ((ld_state(T.state + q) >> 1) == key) T.state[q] = 0u;
-          }
-          if (do_commit) {
-            for (int k = 0; k < enf; k++) T.state[ESEG(efoff + k)] = kUsed;
-          }
-          retired = true;
-        }
-        const bool rect = do_commit && ehas;
-        const uint32_t rectm = __ballot_sync(0xffffffffu, rect);
-        if (rect) append_rect(T, npend + __popc(rectm & lt), T.rob_rect[(head + (uint32_t)lane) & robm], (int)(((head + lane) << 1) | 0u), eseed, enf);
-        npend += __popc(rectm);
-        __syncwarp();
-        if (kstar < ncons) {
-          long long c3 = clock64();
-          int has = 0;
-          if (lane == kstar) {
-            // drop the stamps of the failed attempt, then re-run non-speculatively (exact sequential semantics)
-            for (int k = 0; k < enE; k++) {
-              const int q = ESEG(k);
-              if ((ld_state(T.state + q) >> 1) == key) T.state[q] = 0u;
-            }
-            if (!(ld_state(T.state + eseed) & kUsed)) {
-              SeedResult R;
-              process_seed<false>(T, eseed, T.reg_serial, T.npx, 0u, R);
-              has = R.has_rect;
-              if (has) append_rect(T, npend, R.rec, (int)(((head + lane) << 1) | 1u), eseed, R.nf);
-            }
-            retired = true;
-          }
-          has = __shfl_sync(0xffffffffu, has, kstar);
-          npend += has;
-          n_redo++;
-          __syncwarp();
-          t_redo += clock64() - c3;
-          handled |= below | (1u << kstar);
-          handled &= allm;
-        } else {
-          handled = allm;
-        }
-      }
-#undef ESEG
-      if (mine) { *(volatile int*)&e->meta = 0; atomicAdd(&S.freed[eowner], (unsigned int)enE); }
-      head += (uint32_t)ncons;
-      __syncwarp();
-      if (ncons < 32) break;
-    }
-    t_commit += clock64() - c2;
-  }
-#undef SEG
-  if (lane == 0) *T.npend = min(npend, T.pend_cap);
-  if (lane == 0 && T.prof) {
-    T.prof[0] = t_sel; T.prof[1] = t_spec; T.prof[2] = t_commit - t_redo; T.prof[3] = t_redo; T.prof[4] = n_tick; T.prof[5] = n_redo;
-    T.prof[6] = n_dead; T.prof[7] = next_seq;
   }
 }
 

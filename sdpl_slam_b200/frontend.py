@@ -377,8 +377,8 @@ class Lineextractor(_Profiled):
                          "rect_fit", "refine_tau", "grow_steps", "phaseA_wait"), out.tolist()))
 
     def set_serial(self, on=True):
-        """region-growing schedule: 0/False block-level speculative waves (default), 1/True one seed at a time, 2 re-order buffer,
-        3 single-warp waves; `on | (n << 8)` overrides the number of warps per task (mode 0) or the buffer size (mode 2)"""
+        """region-growing schedule: 0/False block-level speculative waves (default), 1/True one seed at a time, 3 single-warp waves;
+        `on | ((warps | ctas_per_sm << 4) << 8)` pins the kernel variant of mode 0, bit 2 selects the round-1 schedule"""
         _check(self._L.sdpl_line_set_serial(self._h, int(on)))
 
     def lsd_segments(self, octave, frame=0, capacity=65536):

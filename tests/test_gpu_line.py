@@ -56,11 +56,12 @@ def test_line_parity(frontend, oracle, seed, h, w):
 
 
 def test_speculative_equals_sequential(frontend):
-    """All region-growing schedules (speculative waves, one seed at a time, re-order buffer) must give byte-identical output."""
+    """All region-growing schedules (two-phase waves, the round-1 waves, single-warp waves, one seed at a time, 8- and 1-warp CTAs)
+    must give byte-identical output."""
     for seed, (h, w) in ((11, (375, 1242)), (12, (240, 416)), (13, (480, 640))):
         img = synth.frame(seed, h, w)
         outs = []
-        for mode in (0, 1, 2, 3, 0 | (8 << 8), 0 | (1 << 8)):
+        for mode in (0, 1, 4, 3, 0 | (8 << 8), 0 | (1 << 8)):
             g = frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 0)
             g.set_serial(mode)
             k, d = g(img)
