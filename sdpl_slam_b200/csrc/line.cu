@@ -478,7 +478,8 @@ __global__ void __launch_bounds__(128) k_nfa_table(LineDev D, double* __restrict
 
 // small rectangles: one thread each; rectangles whose scan visits more than kBigRect pixels are queued for the warp kernel
 constexpr double kBigRect = 384.0;
-__global__ void __launch_bounds__(64) k_lsd_nfa(LineDev D) {
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) k_lsd_nfa(LineDev D) {
   const int task = blockIdx.y;
   const int f = task / D.nl, o = task % D.nl;
   const int np = D.npend[task];
@@ -741,7 +742,8 @@ __constant__ unsigned char c_comb[32][2] = {{0, 1}, {0, 2}, {0, 3}, {0, 4}, {0, 
                                             {2, 3}, {2, 4}, {2, 5}, {2, 6}, {2, 7}, {2, 8}, {3, 4}, {3, 5}, {3, 6}, {3, 7}, {3, 8},
                                             {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
 
-__global__ void __launch_bounds__(64) k_lbd(LineDev D, const sdpl_keyline* __restrict__ kls, int capacity, const int* __restrict__ n_arr,
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) k_lbd(LineDev D, const sdpl_keyline* __restrict__ kls, int capacity, const int* __restrict__ n_arr,
                                             uint8_t* __restrict__ desc, float* __restrict__ fdesc) {
   __shared__ float rows[63][8];
   __shared__ float des[72];
@@ -1166,7 +1168,12 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   SDPL_LAUNCH_CHECK();
   o->timer.mark(st, "lsd_grow");
   SDPL_CUDA(cudaMemsetAsync(D.nbig, 0, sizeof(int) * 2 * nl * B, st));
-  k_lsd_nfa<<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
+  {
+    const int nb = getenv("SDPL_NFA1_MINB") ? atoi(getenv("SDPL_NFA1_MINB")) : 24;   // 80 registers at 12 CTAs/SM: 4.61 ms NFA stage; 64 at 16: 4.51; 40 at 24: 4.42
+    if (nb >= 24) k_lsd_nfa<24><<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
+    else if (nb >= 16) k_lsd_nfa<16><<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
+    else k_lsd_nfa<12><<<dim3(div_up(D.pend_cap, 64), nl * B), 64, 0, st>>>(D);
+  }
   SDPL_LAUNCH_CHECK();
   // the big rectangles (one warp each, few and long: a latency-bound kernel at 6 % occupancy) and the second pass over the small
   // ones work on disjoint lists: side by side, unless the stages are being timed one after another
@@ -1211,7 +1218,12 @@ static int line_lbd_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, int h
   }
   o->timer.mark(st, "lbd_sobel");
   if (max_lines > 0) {
-    k_lbd<<<dim3(std::min(max_lines, 256), B), 64, 0, st>>>(D, d_kls, capacity, d_n, d_desc, d_fdesc);
+    // CTAs per SM the band kernel is compiled for: 96 registers at 10 (2.39 ms per 512 frames), 64 at 16 (1.92 ms: the gathers want
+    // resident warps more than the cold normalisation code wants registers), 40 at 24 (1.95 ms)
+    const int lb = getenv("SDPL_LBD_MINB") ? atoi(getenv("SDPL_LBD_MINB")) : 16;
+    if (lb >= 24) k_lbd<24><<<dim3(std::min(max_lines, 256), B), 64, 0, st>>>(D, d_kls, capacity, d_n, d_desc, d_fdesc);
+    else if (lb >= 16) k_lbd<16><<<dim3(std::min(max_lines, 256), B), 64, 0, st>>>(D, d_kls, capacity, d_n, d_desc, d_fdesc);
+    else k_lbd<10><<<dim3(std::min(max_lines, 256), B), 64, 0, st>>>(D, d_kls, capacity, d_n, d_desc, d_fdesc);
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "lbd_bands");

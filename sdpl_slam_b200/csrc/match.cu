@@ -57,7 +57,8 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
 }
 
 // partial[(p*max_q + q)*nsplit + s]
-__global__ void __launch_bounds__(kWarps * 32) k_match_partial(const uint8_t* __restrict__ q, const int* __restrict__ nq_arr,
+template <int MINB>
+__global__ void __launch_bounds__(kWarps * 32, MINB) k_match_partial(const uint8_t* __restrict__ q, const int* __restrict__ nq_arr,
                                                                size_t q_stride, const uint8_t* __restrict__ t,
                                                                const int* __restrict__ nt_arr, size_t t_stride, int max_q,
                                                                int max_t, int nsplit, Top2* __restrict__ partial) {
@@ -247,8 +248,15 @@ static int match_run_dev(sdpl_matcher* m, const uint8_t* d_q, const int* d_nq, s
   int rc = m->partial.reserve(sizeof(Top2) * (size_t)npairs * max_q * nsplit);
   if (rc) return rc;
   m->timer.begin(m->stream);
-  k_match_partial<<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q, max_t, nsplit,
-                                                                                 m->partial.as<Top2>());
+  {
+    const int mbk = getenv("SDPL_MATCH_MINB") ? atoi(getenv("SDPL_MATCH_MINB")) : 4;   // 78 registers at 3 CTAs/SM: 2.80 ms per 512 point problems; 64 at 4: 2.67; 48 at 5: 3.25
+    if (mbk >= 5) k_match_partial<5><<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q, max_t,
+                                                                                               nsplit, m->partial.as<Top2>());
+    else if (mbk == 4) k_match_partial<4><<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q,
+                                                                                                    max_t, nsplit, m->partial.as<Top2>());
+    else k_match_partial<3><<<dim3(qblocks, nsplit, npairs), kWarps * 32, 0, m->stream>>>(d_q, d_nq, q_stride, d_t, d_nt, t_stride, max_q, max_t, nsplit,
+                                                                                          m->partial.as<Top2>());
+  }
   SDPL_LAUNCH_CHECK();
   m->timer.mark(m->stream, "match_partial");
   k_match_merge<<<dim3(div_up(max_q, 256), npairs), 256, 0, m->stream>>>(m->partial.as<Top2>(), d_nq, max_q, nsplit, d_best, d_second);
