@@ -18,8 +18,9 @@
 //            sequential result by induction over the scan order; in the common case one step costs one round of loads and one
 //            polynomial arctangent for ~3 expansions instead of ~3 dependent rounds.  Rectangle fits and refine statistics were
 //            already warp-cooperative; the sequential re-runs use the same routine without stamps.
-// (A re-run of a doubtful seed is a region of 5.5 pixels on average -- profiles/r2_rerun_statistics.txt -- and still costs 7 - 10 us;
-// letting ONE lane grow it before the warp takes over was measured slower, 8.0 -> 8.7 ms per frame of re-runs, and was removed.)
+// (Of the ~1000 re-run rounds of a frame ~730 find their seed taken by the commits of the same round; the ~280 real re-runs grow 20 pixels
+// on average and cost 40 k cycles each -- profiles/r2_rerun_statistics.txt.  Letting ONE lane grow such a region before the warp takes
+// over was measured slower, 8.0 -> 8.7 ms per frame of re-runs, and was removed.)
 // Results of a seed live in a per-slot context in global memory (SlotCtx) instead of the registers of "its" thread, so any
 // warp can finish any seed and the commit rounds read them back.
 #pragma once
@@ -296,6 +297,7 @@ __device__ __noinline__ void seed_pipeline_coop(const Task& T, const bool SPEC, 
       const long long pg0 = clock64();
       const bool ok = coop_grow(T, SPEC, cur, capc, n, i, sumdx, sumdy, ra, prec, stamp, bx0, by0, bx1, by1);
       if (T.prof_detail == 1 && threadIdx.x == 0) T.prof[11] += clock64() - pg0;
+      if (T.prof_detail == 2 && !SPEC && lane == 0) atomicAdd((unsigned long long*)&T.prof[10], (unsigned long long)(clock64() - pg0));
       if (state == 0) { R.n1 = n; R.nf = n; } else { if (SPEC) R.n2_orig = n; R.nf = n; }
       if (!ok) { R.ok = 0; break; }
       if (state == 0 ? (n < T.min_reg) : (n < 2)) break;
@@ -562,7 +564,7 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
     phase_a<NW>(T, ctx, S, nsel, cap, ta, wave);
     const long long ca1 = clock64();
     __syncthreads();                                                                       // (A) every seed has a context
-    if (T.prof_detail && tid == 0) { T.prof[8] += ca1 - c1; T.prof[15] += clock64() - ca1; }
+    if (T.prof_detail == 1 && tid == 0) { T.prof[8] += ca1 - c1; T.prof[15] += clock64() - ca1; }
     // ---- the seeds that need phase B, in slot order ----
     {
       // unfinished growths (the long regions) first, then the finished ones that only want their rectangle: the queue is
@@ -607,11 +609,11 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
           if (R.has_rect) c.rec = R.rec;
         }
       }
-      if (T.prof_detail && tid == 0) T.prof[9] += clock64() - cb0;
+      if (T.prof_detail == 1 && tid == 0) T.prof[9] += clock64() - cb0;
     }
     const long long cb1 = clock64();
     __syncthreads();                                                                       // (B) every seed of the wave has a result
-    if (T.prof_detail && tid == 0) T.prof[10] += clock64() - cb1;
+    if (T.prof_detail == 1 && tid == 0) T.prof[10] += clock64() - cb1;
     int r_ok = 0, r_n1 = 0, r_n2o = 0, r_nf = 0, r_foff = 0, r_rect = 0, r_bx0 = 0, r_by0 = 0, r_bx1 = 0, r_by1 = 0;
     if (have) {
       const SlotCtx& c = ctx[tid];
@@ -675,14 +677,18 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
         // the whole warp of ks re-runs that seed with exact sequential semantics.  The commits just made may have taken the
         // seed: then the sequential algorithm skips it
         const int ks_lane = ks & 31;
+        const long long q0 = clock64();
         const int seed_k = __shfl_sync(FULL, my_seed, ks_lane);
         const bool taken = (ld_state(T.state + seed_k) & kUsed) != 0;
         int has = 0;
+        if (T.prof_detail == 2 && lane == ks_lane) { atomicAdd((unsigned long long*)&T.prof[8], (unsigned long long)(clock64() - q0)); if (taken) atomicAdd((unsigned long long*)&T.prof[15], 1ull); }
         if (!taken) {
           SeedResult Q;
           int ssy, ssx;
           divmod_w(dw, seed_k, ssy, ssx);
+          const long long q1 = clock64();
           seed_pipeline_coop(T, false, S.sb[warp], seed_k, ssx, ssy, T.reg_serial, T.npx, 0u, 0, 0, 0.f, 0.f, 0.0, 0, 0, 0, 0, Q);
+          if (T.prof_detail == 2 && lane == ks_lane) atomicAdd((unsigned long long*)&T.prof[9], (unsigned long long)(clock64() - q1));
           has = Q.has_rect;
           if (T.prof_detail == 2 && lane == ks_lane) {          // re-run statistics: pixels grown first / re-grown, rectangles
             atomicAdd((unsigned long long*)&T.prof[11], (unsigned long long)Q.n1);
