@@ -344,7 +344,7 @@ class ResidentArm:
     frame in front), ORB || lines on two streams, F matching problems (frame t against frame t-1) on two more, per-frame
     statistics + result digests."""
 
-    def __init__(self, fe, torch, dev, local, cfg, stages, F, lead, handles=None):
+    def __init__(self, fe, torch, dev, local, cfg, stages, F, lead, handles=None, streams=None):
         self.fe, self.torch, self.dev, self.cfg, self.F, self.lead = fe, torch, dev, cfg, F, lead
         oc, lc = cfg["orb"], cfg["line"]
         self.use_line = "line" in stages and lc is not None
@@ -373,7 +373,11 @@ class ResidentArm:
             self.d_nmap = torch.full((F,), cfg["n_map"], dtype=i32, device=dev)
         self.stats = z(F, 8, dt=i32)          # n_kp, n_lines, n_pt_matches, n_ln_matches, 2 x 64-bit digests (points, lines)
         self.dig = z(2, F, dt=torch.int64)     # [0]: points, [1]: lines
-        self.s_line, self.s_orb, self.s_match, self.s_lmatch, self.s_tail = (torch.cuda.Stream(device=dev, priority=0) for _ in range(5))
+        if streams:          # shared with another arm (as the two slots of sdpl_frontend share its streams): only the buffers are the arm's own
+            self.s_line, self.s_orb, self.s_match, self.s_lmatch = streams
+            self.s_tail = torch.cuda.Stream(device=dev, priority=0)
+        else:
+            self.s_line, self.s_orb, self.s_match, self.s_lmatch, self.s_tail = (torch.cuda.Stream(device=dev, priority=0) for _ in range(5))
         self.launches = 0
         self.bind()
 
@@ -384,6 +388,9 @@ class ResidentArm:
 
     def handles(self):
         return self.orb, self.mat, self.line, self.lmat
+
+    def streams(self):
+        return self.s_line, self.s_orb, self.s_match, self.s_lmatch
 
     def pair_counts(self):
         """(sum over the F problems of nq * nt) for the point and the line matcher of the last step (host read)."""
@@ -611,9 +618,15 @@ def run_gpu(args, stages, cfg):
         dist.init_process_group("nccl", device_id=dev)
     pinned = torch.from_numpy(host).pin_memory()
     d_imgs = pinned.to(dev)
-    # two arms (handles + buffers) used alternately: step k + 1's extraction does not wait for step k's matching and statistics
-    n_arms = max(1, args.pipeline + 1) if (args.pipeline and F <= 1024) else 1
-    arms = [ResidentArm(fe, torch, dev, local, cfg, stages, F, lead) for _ in range(n_arms)]
+    # two sets of output buffers used alternately, so that step k + 1's extraction does not wait for step k's matching and statistics.
+    # --pipeline 1 (default): ONE set of handles and streams, as the two slots of sdpl_frontend_submit / collect (the extractor streams run
+    # step after step, the matchers and statistics of step k beside the extraction of step k + 1); --pipeline 2: two complete sets of
+    # handles (two region-growing kernels may then run side by side: measured slower)
+    n_arms = 2 if (args.pipeline and F <= 1024) else 1
+    arms = [ResidentArm(fe, torch, dev, local, cfg, stages, F, lead)]
+    if n_arms == 2:
+        arms.append(ResidentArm(fe, torch, dev, local, cfg, stages, F, lead) if args.pipeline >= 2 else
+                    ResidentArm(fe, torch, dev, local, cfg, stages, F, lead, handles=arms[0].handles(), streams=arms[0].streams()))
     gathers = [shard.StatsGather(total, 8, torch.int32, dev) for _ in range(n_arms)]
     arm = arms[0]
 
@@ -875,8 +888,8 @@ def main():
     ap.add_argument("--stages", default="orb,line,match")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=1, help="N >= 1: N + 1 sets of handles / buffers used in turn (1: two sets) so that consecutive steps overlap "
-                                                              "(when a GPU holds <= 1024 frames per step); 0: one set, steps strictly one after another")
+    ap.add_argument("--pipeline", type=int, default=1, help="1: two sets of output buffers on one set of handles / streams, consecutive steps overlap "
+                                                              "(when a GPU holds <= 1024 frames per step); 2: two complete sets of handles; 0: steps strictly one after another")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-post", action="store_true", help="skip the Frame post-processing stage block (SURVEY 8f rows 1, 2)")
     ap.add_argument("--sweep", action="store_true", help="batch-size sweep {1, 8, 64, 512, 2048} through the host-buffer API (1 GPU)")
