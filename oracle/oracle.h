@@ -11,8 +11,13 @@
  * Parity status: PINNED for the extractor / matcher path -- against the reference's own sources compiled unmodified over an
  * OpenCV stand-in (oracle/refshim -> oracle/_ref/libsdpl_ref.so, tests/test_oracle_vs_ref.py: byte for byte on every BASELINE
  * geometry) and, at the OpenCV-primitive boundary, against python cv2 4.13 (tests/test_oracle_vs_cv2.py, tests/golden/).
- * The Frame post-processing functions (post_oracle.cpp) are "parity unpinned": Frame.cc cannot be compiled here; they are
- * checked against an independent numpy restatement (tests/test_oracle_post.py).
+ * The Frame post-processing functions (post_oracle.cpp) are PINNED as well, for everything Frame::Frame itself runs: the same
+ * library holds src/Frame.cc compiled unmodified, and test_frame_post_processing_equals_reference_frame_constructor compares every
+ * vector the reference's constructor leaves behind (line filters, point / line correspondences, object sampling, grid,
+ * GetFeaturesInArea) byte for byte.  Only the three functions restated from src/MapPoint.cc (distinctive descriptor, PredictScale)
+ * and the window descriptor search are "parity unpinned": MapPoint.cc is not part of the reference's own build (CMakeLists.txt:62
+ * lists no such file, ORBmatcher.h does not exist), so no compiled form of it exists anywhere; they are checked against an
+ * independent numpy restatement (tests/test_oracle_post.py).
  */
 #ifndef SDPL_ORACLE_H
 #define SDPL_ORACLE_H

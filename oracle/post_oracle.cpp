@@ -3,9 +3,13 @@
 // one loop of the constructor, statement by statement, with std::vector push_back semantics replaced by output arrays in the
 // same order.  Inputs are the reference's own per-frame planes: maskSEM (CV_32S), imDepth (CV_32F), imFlow (CV_32FC2).
 //
-// Parity status: Frame.cc cannot be compiled here (it pulls in g2o, Eigen, OpenCV highgui / xfeatures2d / flann through Frame.h),
-// so these restatements are "parity unpinned" against a compiled reference; they are checked against an independent numpy
-// restatement (tests/test_oracle_post.py) and read side by side with the cited lines.
+// Parity status: PINNED for every function that restates Frame.cc -- oracle/refshim compiles src/Frame.cc unmodified (Frame.h's
+// Eigen / xfeatures2d / flann / Converter includes are satisfied by minimal stand-ins, nothing of them is used on this path) and
+// tests/test_oracle_vs_ref.py::test_frame_post_processing_equals_reference_frame_constructor runs the reference's own constructor on
+// synthetic image / mask / depth / flow planes and compares all of its output vectors with the functions below, byte for byte.
+// The functions restated from src/MapPoint.cc (orc_post_distinctive_descriptors, orc_post_predict_scale) and the window descriptor
+// search (orc_post_search_area) stay "parity unpinned": MapPoint.cc is dead code in the reference (not in CMakeLists.txt, includes
+// a header that does not exist), so they are checked against an independent numpy restatement (tests/test_oracle_post.py) only.
 //
 // C++ conversions the code below relies on (all as written in Frame.cc, which has `using namespace std`, :24):
 //   int x = kp.pt.x            float -> int truncates toward zero                                   (:353-356, :488-489, :519-522)

@@ -166,6 +166,62 @@ def matcher_stored_knn(q, t1, t2, k):
     return train, img, dist
 
 
+class RefFrame:
+    """The reference's own Frame constructor (src/Frame.cc:236-907, compiled unmodified) on one image and its mask / depth / flow planes:
+    runs the reference's ORBextractor and Lineextractor and then the constructor's loops; exposes the public result vectors."""
+
+    def __init__(self, gray, depth, flow, mask, orb=(2000, 1.2, 8, 20, 7), line=(0, 2, 0.8, 2, 2.0), th_depth=40.0, th_depth_obj=25.0,
+                 use_sample_fea=0):
+        from . import oracle as orc
+        L = lib()
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.ref_frame_construct.restype = vp
+        L.ref_frame_construct.argtypes = [vp, vp, vp, vp, ci, ci, ci, cf, ci, ci, ci, ci, ci, cf, ci, cf, cf, cf, ci]
+        L.ref_frame_destroy.argtypes = [vp]
+        L.ref_frame_counts.argtypes = [vp, vp]
+        L.ref_frame_points.argtypes = [vp] * 6
+        L.ref_frame_lines.argtypes = [vp] * 7
+        L.ref_frame_objects.argtypes = [vp] * 6
+        L.ref_frame_grid.argtypes = [vp] * 3
+        L.ref_frame_features_in_area.argtypes = [vp, cf, cf, cf, ci, ci, vp, ci]
+        self._L = L
+        g = np.ascontiguousarray(gray, np.uint8); d = np.ascontiguousarray(depth, np.float32)
+        f = np.ascontiguousarray(flow, np.float32); m = np.ascontiguousarray(mask, np.int32)
+        h, w = g.shape
+        self._keep = (g, d, f, m)
+        self._h = L.ref_frame_construct(g.ctypes.data, d.ctypes.data, f.ctypes.data, m.ctypes.data, w, h, orb[0], orb[1], orb[2], orb[3], orb[4],
+                                        line[0], line[1], line[2], line[3], line[4], th_depth, th_depth_obj, use_sample_fea)
+        c = np.zeros(6, np.int32); L.ref_frame_counts(self._h, c.ctypes.data)
+        n, nl, ns, nsl, no, _ = [int(v) for v in c]
+        KP, KL = orc.KP_DTYPE, orc.KL_DTYPE
+        z = lambda k, dt: np.zeros(max(k, 1), dt)
+        keys, stat, cor, fn, sd = z(n, KP), z(ns, KP), z(ns, KP), np.zeros((max(ns, 1), 2), np.float32), z(ns, np.float32)
+        L.ref_frame_points(self._h, keys.ctypes.data, stat.ctypes.data, cor.ctypes.data, fn.ctypes.data, sd.ctypes.data)
+        self.mvKeys, self.mvStatKeysTmp, self.mvCorres, self.mvFlowNext, self.mvStatDepthTmp = keys[:n], stat[:ns], cor[:ns], fn[:ns], sd[:ns]
+        fl, sl, cl = z(nl, KL), z(nsl, KL), z(nsl, KL)
+        lfn, inf, lsd = np.zeros((max(nsl, 1), 4), np.float32), np.zeros((max(nsl, 1), 3), np.float64), np.zeros((max(nsl, 1), 2), np.float32)
+        L.ref_frame_lines(self._h, fl.ctypes.data, sl.ctypes.data, cl.ctypes.data, lfn.ctypes.data, inf.ctypes.data, lsd.ctypes.data)
+        self.mvKeys_Line, self.mvStatKeysLineTmp, self.mvCorresLine = fl[:nl], sl[:nsl], cl[:nsl]
+        self.mvFlowNext_Line, self.mvInfiniteLinesCorr, self.mvStatDepthLineTmp = lfn[:nsl], inf[:nsl], lsd[:nsl]
+        ok, oc, ofn, od, ol = z(no, KP), z(no, KP), np.zeros((max(no, 1), 2), np.float32), z(no, np.float32), z(no, np.int32)
+        L.ref_frame_objects(self._h, ok.ctypes.data, oc.ctypes.data, ofn.ctypes.data, od.ctypes.data, ol.ctypes.data)
+        self.mvObjKeys, self.mvObjCorres, self.mvObjFlowNext, self.mvObjDepth, self.vSemObjLabel = ok[:no], oc[:no], ofn[:no], od[:no], ol[:no]
+        cs, items = np.zeros(64 * 48 + 1, np.int32), np.zeros(max(n, 1), np.int32)
+        L.ref_frame_grid(self._h, cs.ctypes.data, items.ctypes.data)
+        self.grid_cell_start, self.grid_items = cs, items[:cs[-1]]
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        out = np.zeros(max(len(self.mvKeys), 1), np.int32)
+        n = self._L.ref_frame_features_in_area(self._h, float(x), float(y), float(r), int(minLevel), int(maxLevel), out.ctypes.data, len(out))
+        return out[:n]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.ref_frame_destroy(h)
+            self._h = None
+
+
 def matcher_match(q, t):
     q, t = np.ascontiguousarray(q, np.uint8), np.ascontiguousarray(t, np.uint8)
     train, dist = np.zeros(len(q), np.int32), np.zeros(len(q), np.float32)

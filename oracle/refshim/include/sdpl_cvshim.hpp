@@ -95,6 +95,9 @@ template <typename T> inline Point_<T>& operator*=(Point_<T>& a, float b) {
 template <typename T> inline Point_<T>& operator*=(Point_<T>& a, double b) {
   a.x = saturate_cast<T>(a.x * b); a.y = saturate_cast<T>(a.y * b); return a;
 }
+template <typename T> inline Point_<T> operator+(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x + b.x, a.y + b.y); }
+template <typename T> inline Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x - b.x, a.y - b.y); }
+template <typename T> inline Point_<T> operator*(const Point_<T>& a, double b) { return Point_<T>(saturate_cast<T>(a.x * b), saturate_cast<T>(a.y * b)); }
 typedef Point_<int> Point2i;
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
@@ -253,6 +256,10 @@ class Mat {
   static MatExprZeros zeros(int r, int c, int type) { MatExprZeros e = {r, c, type}; return e; }
   void push_back(const Mat& m);
   Mat t() const { shim_unsupported("Mat::t"); }
+  Mat col(int) const { shim_unsupported("Mat::col"); }
+  Mat row(int) const { shim_unsupported("Mat::row"); }
+  Mat reshape(int, int = 0) const { shim_unsupported("Mat::reshape"); }
+  Mat cross(const Mat&) const { shim_unsupported("Mat::cross"); }
   Mat& setTo(const Scalar&) { shim_unsupported("Mat::setTo"); }
   void convertTo(Mat& dst, int type) const;
 
@@ -264,6 +271,8 @@ class Mat {
 inline Mat operator*(const Mat&, const Mat&) { shim_unsupported("Mat*Mat"); }
 inline Mat operator+(const Mat&, const Mat&) { shim_unsupported("Mat+Mat"); }
 inline Mat operator/(const Mat&, double) { shim_unsupported("Mat/scalar"); }
+inline Mat operator-(const Mat&, const Mat&) { shim_unsupported("Mat-Mat"); }
+inline Mat operator-(const Mat&) { shim_unsupported("-Mat"); }
 
 template <typename T> struct DepthOf;
 template <> struct DepthOf<uchar> { enum { value = CV_8U }; };

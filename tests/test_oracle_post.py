@@ -1,6 +1,7 @@
 """CPU: the Frame post-processing oracle (oracle/post_oracle.cpp, restating src/Frame.cc:349-389, 482-604, 728-809, 910-925) against
-an independent numpy restatement of the same loops on synthetic planes.  Frame.cc itself cannot be compiled here (g2o / Eigen /
-OpenCV contrib through Frame.h), so this is the pin these functions have: two restatements written separately must agree."""
+an independent numpy restatement of the same loops on synthetic planes: two restatements written separately must agree.  The pin
+against the reference's own compiled Frame.cc is tests/test_oracle_vs_ref.py::test_frame_post_processing_equals_reference_frame_constructor;
+this file also covers the functions restated from src/MapPoint.cc, which has no compiled form (not part of the reference's build)."""
 import numpy as np
 
 from sdpl_slam_b200 import synth

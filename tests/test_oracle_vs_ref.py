@@ -1,5 +1,5 @@
 """Pins the ORACLE (oracle/*.cpp) against the reference's OWN code: oracle/_ref/libsdpl_ref.so is
-/root/reference/src/{ORBextractor,Lineextractor}.cc and 3rdparty/line_descriptor/src/{LSDDetector_custom,
+/root/reference/src/{ORBextractor,Lineextractor,Frame}.cc and 3rdparty/line_descriptor/src/{LSDDetector_custom,
 binary_descriptor_custom,binary_descriptor_matcher}.cpp compiled UNMODIFIED against the OpenCV stand-in in
 oracle/refshim/ (recipe: oracle/refshim/Makefile).  The OpenCV primitives under it are oracle/cvprim.cpp and
 oracle/lsd_oracle.cpp, themselves pinned bit-exact against cv2 in test_oracle_vs_cv2.py.
@@ -183,6 +183,57 @@ def test_stored_train_set_indices_follow_the_reference(ref, oracle):
     assert (dist[:, 0] == want["distance"][:, 0]).all()
     assert (train[:40, 0] == np.arange(40)).all() and (train[40:, 0] == 300 + np.arange(40)).all()     # rows of the concatenation
     assert (img[:40, 0] == 0).all() and (img[40:, 0] == 1).all()
+
+
+@pytest.mark.parametrize("h,w,seed", [(375, 1242, 3), (240, 416, 4)])
+def test_frame_post_processing_equals_reference_frame_constructor(ref, oracle, h, w, seed):
+    """src/Frame.cc compiled unmodified: the reference's own Frame constructor on a synthetic image and its mask / depth / flow planes
+    against oracle/post_oracle.cpp applied to the reference's key points / key lines -- the pin for SURVEY 8f rows 1, 2 and the grid /
+    window search of row 4.  Everything the constructor leaves in its public vectors is compared byte for byte.  The key lines fed to the
+    oracle's post-processing are the reference extractor's own (KeyLine::angle is glibc's atan2f there, see the module docstring; all other
+    fields equal the oracle extractor's, which is asserted first)."""
+    img = synth.frame(seed, h, w)
+    mask, depth, flow = synth.scene_planes(seed, h, w)
+    F = ref.RefFrame(img, depth, flow, mask, orb=(1000, 1.2, 8, 20, 7), th_depth=40.0, th_depth_obj=25.0)
+    # the extractors inside the constructor are the reference's: their raw output is what the oracle's extractors give
+    okps, _ = oracle.OrbOracle(1000, 1.2, 8, 20, 7)(img)
+    okls, _ = ref.RefLineextractor(0, 2, 0.8, 2, 2.0, 0)(img)
+    okls = okls.view(oracle.KL_DTYPE)
+    mine, _ = oracle.LineOracle(0, 2, 0.8, 2, 2.0, 0)(img)
+    assert len(mine) == len(okls) and all((mine[f] == okls[f]).all() for f in okls.dtype.names if f != "angle")
+    assert F.mvKeys.tobytes() == okps.tobytes()
+    # Frame.cc:349-389 -- the two erase loops on mvKeys_Line
+    filt, _ = oracle.post_filter_lines(okls, mask, depth)
+    assert 0 < len(filt) < len(okls) and F.mvKeys_Line.tobytes() == filt.tobytes()
+    # Frame.cc:482-512, 728-745 -- static point correspondences and depths
+    p = oracle.post_point_corres(okps, mask, depth, flow, 40.0)
+    assert len(p["stat"]) > 50
+    assert F.mvStatKeysTmp.tobytes() == p["stat"].tobytes() and F.mvCorres.tobytes() == p["corres"].tobytes()
+    assert F.mvFlowNext.tobytes() == p["flow_next"].tobytes() and F.mvStatDepthTmp.tobytes() == p["depth"].tobytes()
+    # Frame.cc:513-604, 746-763 -- line correspondences on the FILTERED list
+    l = oracle.post_line_corres(filt, mask, depth, flow, 40.0)
+    assert len(l["stat"]) > 3
+    assert F.mvStatKeysLineTmp.tobytes() == l["stat"].tobytes()
+    for name in oracle.KL_DTYPE.names:
+        if name in ("sx_oct", "sy_oct", "ex_oct", "ey_oct"):
+            continue            # left uninitialised by the reference (Frame.cc:566-582)
+        assert (F.mvCorresLine[name] == l["corres"][name]).all(), name
+    assert F.mvFlowNext_Line.tobytes() == l["flow_next"].tobytes() and F.mvStatDepthLineTmp.tobytes() == l["depth"].tobytes()
+    assert F.mvInfiniteLinesCorr.tobytes() == l["inf_line"].tobytes()
+    # Frame.cc:769-809 -- semi-dense object sampling
+    o = oracle.post_sample_objects(mask, depth, flow, 4, 25.0)
+    assert len(o["keys"]) > 100
+    assert F.mvObjKeys.tobytes() == o["keys"].tobytes() and F.mvObjCorres.tobytes() == o["corres"].tobytes()
+    assert F.mvObjFlowNext.tobytes() == o["flow_next"].tobytes() and F.mvObjDepth.tobytes() == o["depth"].tobytes()
+    assert (F.vSemObjLabel == o["label"]).all()
+    # Frame.cc:910-925, 1023-1035 -- grid; :970-1023 -- GetFeaturesInArea
+    cs, items = oracle.post_grid(okps, w, h)
+    assert (F.grid_cell_start == cs).all() and (F.grid_items == items).all()
+    rng = np.random.default_rng(seed)
+    for _ in range(60):
+        x, y, r = float(rng.uniform(-20, w + 20)), float(rng.uniform(-20, h + 20)), float(rng.uniform(1, 70))
+        lo, hi = int(rng.integers(-1, 4)), int(rng.integers(-1, 8))
+        assert (F.GetFeaturesInArea(x, y, r, lo, hi) == oracle.post_features_in_area(okps, w, h, cs, items, x, y, r, lo, hi)).all()
 
 
 _HEAP_SCRIPT = r"""
