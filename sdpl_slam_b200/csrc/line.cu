@@ -1136,7 +1136,8 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     else if (nw >= 8 && mb >= 2) k_lsd_grow2<8, 2><<<nl * B, 256, 0, st>>>(D);
     else if (nw >= 8) k_lsd_grow2<8, 1><<<nl * B, 256, 0, st>>>(D);
     else if (nw >= 4 && mb <= 2) k_lsd_grow2<4, 2><<<nl * B, 128, 0, st>>>(D);
-    else if (nw >= 4 && mb <= 4) k_lsd_grow2<4, 4><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb == 3) k_lsd_grow2<4, 3><<<nl * B, 128, 0, st>>>(D);
+    else if (nw >= 4 && mb <= 4) k_lsd_grow2<4, 4><<<nl * B, 128, o->grow_smem, st>>>(D);
     else if (nw >= 4 && mb == 5) k_lsd_grow2<4, 5><<<nl * B, 128, o->grow_smem, st>>>(D);
     else if (nw >= 4 && mb <= 6) k_lsd_grow2<4, 6><<<nl * B, 128, 0, st>>>(D);
     else if (nw >= 4) k_lsd_grow2<4, 8><<<nl * B, 128, 0, st>>>(D);
@@ -1291,7 +1292,10 @@ int sdpl_line_create(sdpl_line** out, int nfeatures, int refine, float lsd_scale
     int nw = 0, ta = -1;
     if (sscanf(g, "%d,%d", &nw, &ta) >= 1) { o->grow_warps_small = std::min(std::max(nw, 1), lsd::kMaxGrowWarps2); if (ta >= 0) o->grow_ta_small = ta; }
   }
-  if (o->grow_smem > 0) SDPL_CUDA(cudaFuncSetAttribute(k_lsd_grow2<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->grow_smem));
+  if (o->grow_smem > 0) {
+    SDPL_CUDA(cudaFuncSetAttribute(k_lsd_grow2<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->grow_smem));
+    SDPL_CUDA(cudaFuncSetAttribute(k_lsd_grow2<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, o->grow_smem));
+  }
   *out = o;
   return SDPL_OK;
 }

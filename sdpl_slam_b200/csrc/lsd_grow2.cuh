@@ -358,7 +358,7 @@ template <int NW>
 struct Block2Shared {
   int sel[32 * NW];
   int q[32 * NW];                        // seed slots waiting for phase B
-  uint32_t deadm[NW], goodm[NW], rectm[NW];
+  uint32_t deadm[NW], goodm[NW], rectm[NW], simplem[NW], cdeadm[NW];
   int nsel, cursor, has, qn, qhead;
   int anext;                             // phase A: next seed slot to hand to an idle lane
   int rb[4];                             // bounding box written by the last re-run
@@ -635,34 +635,49 @@ __device__ void grow_task_block2(const Task& T, SlotCtx* const ctx, const int ta
         const bool own = owns_all_coop_xy(T, need && !d0 && r_ok, my_reg, r_n1 + r_n2o, stamp >> 1);
         if (need) verdict = d0 ? 2 : (own ? 1 : 3);
       }
+      uint32_t sv_seed = kUsed;
       if (mine) {
         if (verdict == 3) {
           // lost a pixel (or never finished): that is permanent; only "my seed was taken meanwhile" can still change
-          dead = (ld_state(T.state + my_seed) & kUsed) != 0;
+          sv_seed = ld_state(T.state + my_seed);
+          dead = (sv_seed & kUsed) != 0;
           if (dead) verdict = 2;
         }
         dead = verdict == 2; good = verdict == 1;
       }
+      // a seed whose own pixel carries the stamp of an earlier seed o of this wave is taken as soon as o commits -- provided o
+      // commits every pixel it stamped (no refinement: final list = first region).  Seeing that here, instead of one loop trip
+      // later, saves the trip: three of four doubtful seeds are of this kind (profiles/r2_rerun_statistics.txt)
       const uint32_t dm = __ballot_sync(FULL, dead), gm = __ballot_sync(FULL, good);
       const uint32_t rm = __ballot_sync(FULL, good && r_rect);
-      if (lane == 0) { S.deadm[warp] = dm; S.goodm[warp] = gm; S.rectm[warp] = rm; }
+      const uint32_t sm = __ballot_sync(FULL, good && r_foff == 0 && r_n2o == 0 && r_nf == r_n1);
+      if (lane == 0) { S.deadm[warp] = dm; S.goodm[warp] = gm; S.rectm[warp] = rm; S.simplem[warp] = sm; }
       __syncthreads();                                                                     // (1) verdicts published
+      {
+        bool cd = false;
+        if (mine && verdict == 3 && !(sv_seed & kUsed) && (sv_seed >> 11) == wave && !(sv_seed & 1u)) {
+          const int o = K - 1 - (int)((sv_seed >> 1) & 0x3ffu);
+          cd = o >= 0 && o < tid && ((S.goodm[o >> 5] & S.simplem[o >> 5]) >> (o & 31)) & 1u;
+        }
+        const uint32_t cm = __ballot_sync(FULL, cd);
+        if (lane == 0) S.cdeadm[warp] = cm;
+      }
+      __syncthreads();                                                                     // (1b) conditionally dead seeds published
       // first unsettled seed that is neither dead nor provably good; rectangles of the good seeds before it, in seed order
       int ks = nsel, before = 0, total = 0;
-      for (int v = 0; v < NW; v++) {
+      for (int v = settled >> 5; v < NW; v++) {
         const int first = v * 32;
-        if (first >= nsel || first + 32 <= settled) continue;
+        if (first >= nsel) break;
         uint32_t pm = FULL;
         if (settled > first) pm &= ~((1u << (settled - first)) - 1u);
         if (nsel < first + 32) pm &= (1u << (nsel - first)) - 1u;
-        if (ks == nsel) {
-          const uint32_t bad = pm & ~S.deadm[v] & ~S.goodm[v];
-          if (bad) { ks = first + __ffs(bad) - 1; pm &= (1u << (ks - first)) - 1u; }
-          const uint32_t rr = S.rectm[v] & pm;
-          total += __popc(rr);
-          if (v < warp) before += __popc(rr);
-          else if (v == warp) before += __popc(rr & lt);
-        }
+        const uint32_t bad = pm & ~S.deadm[v] & ~S.goodm[v] & ~S.cdeadm[v];
+        if (bad) { ks = first + __ffs(bad) - 1; pm &= (1u << (ks - first)) - 1u; }
+        const uint32_t rr = S.rectm[v] & pm;
+        total += __popc(rr);
+        if (v < warp) before += __popc(rr);
+        else if (v == warp) before += __popc(rr & lt);
+        if (bad) break;
       }
       const bool do_commit = mine && good && tid < ks;
       mark_used_coop_xy(T, do_commit, my_reg + r_foff, r_nf);
