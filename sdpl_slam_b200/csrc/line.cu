@@ -53,7 +53,7 @@ struct LineDev {
   const uint8_t* in;
   unsigned long long lvl_frame, px_frame, lbd_frame, g_frame, sc_frame, hist_frame, reg_frame;
   uint8_t *lvl, *scaled;
-  lsd::PxA* px; double* ang; int* g2; uint32_t* state; uint32_t* order;
+  lsd::PxRec* px; double* ang; int* g2; uint32_t* order;
   uint32_t* hist; int* maxg2; int* ndef; int* task_order;
   int* reg; lsd::Pending* pend; int pend_cap; int* npend;
   lsd::SlotCtx* ctx; int grow_ta;      // per-task seed-slot contexts of the two-phase schedule; phase-A expansion cap
@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
   if (x < O.sw && y < O.sh) {
     const uint8_t* img = D.scaled + (size_t)f * D.sc_frame + O.sc_off;
     const size_t q = (size_t)f * D.px_frame + O.px_off + (size_t)y * O.sw + x;
-    lsd::PxA a; a.ang = lsd::kNotDef; a.c = 0.f; a.s = 0.f;
+    lsd::PxRec a; a.state = 0u; a.deg = lsd::kNotDefDeg; a.c = 0.f; a.s = 0.f;
+    double ang = lsd::kNotDef;
     if (x < O.sw - 1 && y < O.sh - 1) {
       const uint8_t* r0 = img + (size_t)y * O.sc_stride + x;
       const uint8_t* r1 = r0 + O.sc_stride;
@@ -262,8 +263,9 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
       g2 = gx * gx + gy * gy;
       const double norm = sqrt((double)g2 / 4.0);
       if (norm > D.rho) {
-        a.ang = (double)fast_atan2_deg((float)gx, (float)-gy) * lsd::kDegToRad;
-        const double af = (double)(float)a.ang;
+        a.deg = fast_atan2_deg((float)gx, (float)-gy);
+        ang = (double)a.deg * lsd::kDegToRad;
+        const double af = (double)(float)ang;
         double sn_, cs_; sdpl_sincos(af, &sn_, &cs_);
         a.c = (float)cs_; a.s = (float)sn_;
       } else {
@@ -273,9 +275,8 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
       g2 = -1;
     }
     D.px[q] = a;
-    D.ang[q] = a.ang;
+    D.ang[q] = ang;
     D.g2[q] = g2;
-    D.state[q] = 0u;
   }
   // block maximum of the defined gradient magnitudes
   int m = g2;
@@ -395,7 +396,7 @@ __device__ __forceinline__ void make_task(const LineDev& D, int f, int o, lsd::T
   const size_t pb = (size_t)f * D.px_frame + O.px_off;
   const int task = f * D.nl + o;
   T.w = O.sw; T.h = O.sh; T.npx = O.npx;
-  T.px = D.px + pb; T.ang = D.ang + pb; T.g2 = D.g2 + pb; T.state = D.state + pb; T.order = D.order + pb;
+  T.px.p = D.px + pb; T.ang = D.ang + pb; T.g2 = D.g2 + pb; T.state.p = D.px + pb; T.order = D.order + pb;
   T.ndef = D.ndef[task];
   T.reg_spec = D.reg + (size_t)f * D.reg_frame + O.reg_off;
   T.lane_cap = O.lane_cap;
@@ -870,7 +871,7 @@ struct sdpl_line {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int gw = 0, gh = 0, gB = 0;
   LineDev D;
-  DevBuf lvl, scaled, px, ang, g2, state, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sd, err, tables, tmpkl;
+  DevBuf lvl, scaled, px, ang, g2, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sd, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, nbig, bigidx, ctx, nfatab;
   int grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
   int grow_warps_small = 16, grow_ta_small = -1;  // small batches (tasks <= SMs): warps per task, phase-A cap (-1: grow_ta)
@@ -1015,10 +1016,9 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   int rc;
   if ((rc = o->lvl.reserve(D.lvl_frame * B))) return rc;
   if ((rc = o->scaled.reserve(D.sc_frame * B))) return rc;
-  if ((rc = o->px.reserve(sizeof(lsd::PxA) * D.px_frame * B))) return rc;
+  if ((rc = o->px.reserve(sizeof(lsd::PxRec) * D.px_frame * B))) return rc;
   if ((rc = o->ang.reserve(sizeof(double) * D.px_frame * B))) return rc;
   if ((rc = o->g2.reserve(sizeof(int) * D.px_frame * B))) return rc;
-  if ((rc = o->state.reserve(sizeof(uint32_t) * D.px_frame * B))) return rc;
   if ((rc = o->order.reserve(sizeof(uint32_t) * D.px_frame * B))) return rc;
   if ((rc = o->hist.reserve(sizeof(uint32_t) * D.hist_frame * B))) return rc;
   if ((rc = o->maxg2.reserve(sizeof(int) * nl * B))) return rc;
@@ -1063,8 +1063,8 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
     O.ex_ofs = i32 + exo_at[l]; O.ey_ofs = i32 + eyo_at[l];
     O.ex_c1 = u16 + exc_at[l]; O.ey_c1 = u16 + eyc_at[l];
   }
-  D.lvl = o->lvl.as<uint8_t>(); D.scaled = o->scaled.as<uint8_t>(); D.px = o->px.as<lsd::PxA>(); D.ang = o->ang.as<double>(); D.g2 = o->g2.as<int>();
-  D.state = o->state.as<uint32_t>(); D.order = o->order.as<uint32_t>(); D.hist = o->hist.as<uint32_t>();
+  D.lvl = o->lvl.as<uint8_t>(); D.scaled = o->scaled.as<uint8_t>(); D.px = o->px.as<lsd::PxRec>(); D.ang = o->ang.as<double>(); D.g2 = o->g2.as<int>();
+  D.order = o->order.as<uint32_t>(); D.hist = o->hist.as<uint32_t>();
   D.maxg2 = o->maxg2.as<int>(); D.ndef = o->ndef.as<int>(); D.task_order = o->torder.as<int>(); D.reg = o->reg.as<int>(); D.pend = o->pend.as<lsd::Pending>();
   D.npend = o->npend.as<int>(); D.g = o->g.as<uint8_t>(); D.sd = o->sd.as<short2>();
   D.err = o->err.as<int>(); D.prof = o->prof.as<long long>(); D.lgam = o->lgam.as<double>(); D.lgam_n = kLgamN;
@@ -1304,7 +1304,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   if (!o) return;
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
-  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->state, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
+  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
                     &o->g, &o->sd, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->nbig, &o->bigidx, &o->ctx, &o->nfatab})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);

@@ -34,6 +34,31 @@ constexpr double kLn10 = 2.30258509299404568402;
 constexpr uint32_t kUsed = 0x80000000u;
 
 struct __align__(16) PxA { double ang; float c, s; };   // level-line angle (rad) or kNotDef; cos/sin of float(angle)
+// What the kernels keep per pixel, one 16-byte record = one load per neighbour test: the state word (bit31 = used, low bits =
+// speculative stamp), the level-line angle as the FLOAT DEGREES fastAtan2 returned (the double radians the algorithm works with
+// are (double)deg * kDegToRad, the very product ll_angle forms -- recomputed on load, bit-identical) or kNotDefDeg, and the
+// cos / sin of float(angle).  Round 1 / 2 had a 16-byte {double, float, float} record plus a separate state array: two sectors
+// per test instead of one.
+struct __align__(16) PxRec { uint32_t state; float deg; float c, s; };
+constexpr float kNotDefDeg = -1024.f;
+__device__ __forceinline__ double rec_angle(float deg) { return deg == kNotDefDeg ? kNotDef : (double)deg * kDegToRad; }
+struct PxArr {                     // T.px[q] -> PxA by value (angle rebuilt); T.px.cs(q) -> cos / sin
+  const PxRec* p;
+  __device__ __forceinline__ PxA operator[](int q) const {
+    const PxRec* r = p + q;
+    const float deg = r->deg;
+    const float2 cs = *reinterpret_cast<const float2*>(&r->c);
+    PxA a; a.ang = rec_angle(deg); a.c = cs.x; a.s = cs.y;
+    return a;
+  }
+  __device__ __forceinline__ double ang(int q) const { return rec_angle(p[q].deg); }
+  __device__ __forceinline__ float2 cs(int q) const { return *reinterpret_cast<const float2*>(&p[q].c); }
+};
+struct StateArr {                  // T.state + q / T.state[q]: the state word of record q
+  PxRec* p;
+  __device__ __forceinline__ uint32_t* operator+(int q) const { return &p[q].state; }
+  __device__ __forceinline__ uint32_t& operator[](int q) const { return p[q].state; }
+};
 
 struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
 
@@ -47,10 +72,10 @@ struct __align__(8) Pending {      // a rectangle waiting for / after NFA valida
 
 struct Task {                      // one (frame, level)
   int w, h, npx;
-  const PxA* px;
-  const double* ang;               // the angles alone, densely packed: what the neighbourhood loads and the NFA scans read
+  PxArr px;                        // the per-pixel records (see PxRec): T.px[q] / T.state[q] are views of the same array
+  const double* ang;               // the angles alone, densely packed: what the NFA scans read
   const int* g2;                   // gx^2+gy^2 ; modgrad = sqrt(g2/4.0)
-  uint32_t* state;                 // bit31 = used (committed) ; low bits = speculative stamp
+  StateArr state;                  // bit31 = used (committed) ; low bits = speculative stamp
   const uint32_t* order;           // defined pixels by descending bin, row-major inside a bin
   int ndef;
   int* reg_spec; int lane_cap;     // 32 lane segments of lane_cap ints
@@ -91,6 +116,17 @@ __device__ __forceinline__ uint32_t ld_state(const uint32_t* p) {
   asm volatile("ld.relaxed.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// state word + pixel record in one 16-byte load / state word + angle in one 8-byte load (the state word with ld_state's semantics)
+__device__ __forceinline__ void ld_rec(const PxRec* p, uint32_t& st, PxA& a) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("ld.relaxed.cta.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "l"(p) : "memory");
+  st = r0; a.ang = rec_angle(__uint_as_float(r1)); a.c = __uint_as_float(r2); a.s = __uint_as_float(r3);
+}
+__device__ __forceinline__ void ld_rec_angle(const PxRec* p, uint32_t& st, double& ang) {
+  uint32_t r0, r1;
+  asm volatile("ld.relaxed.cta.global.v2.u32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "l"(p) : "memory");
+  st = r0; ang = rec_angle(__uint_as_float(r1));
+}
 __device__ __forceinline__ void claim_max(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.cta.global.max.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -106,7 +142,7 @@ __device__ bool region_grow(const Task& T, int seed, int* reg, int cap, int& n_o
   const int w = T.w, h = T.h;
   int n = 1;
   reg[0] = seed;
-  double ra = T.px[seed].ang;
+  double ra = T.px.ang(seed);
   float sumdx = (float)sdpl_cos(ra), sumdy = (float)sdpl_sin(ra);
   if (SPEC) {
     if (ld_state(T.state + seed) > stamp) { n_out = n; return false; }
@@ -261,14 +297,14 @@ __device__ void process_seed(const Task& T, int seed, int* reg, int cap, uint32_
   double density = (double)n1 / (dist(R.rec.x1, R.rec.y1, R.rec.x2, R.rec.y2) * R.rec.width);
   if (density >= T.density_th) { R.has_rect = 1; return; }
   const double xc = (double)(seed % T.w), yc = (double)(seed / T.w);
-  const double ang_c = T.px[seed].ang;
+  const double ang_c = T.px.ang(seed);
   double sum = 0, s_sum = 0;
   int cnt = 0;
   for (int i = 0; i < n1; ++i) {
     const int q = reg[i];
     if (!SPEC) T.state[q] = 0;
     if (dist(xc, yc, (double)(q % T.w), (double)(q / T.w)) < R.rec.width) {
-      const double d = angle_diff_signed(T.px[q].ang, ang_c);
+      const double d = angle_diff_signed(T.px.ang(q), ang_c);
       sum += d;
       s_sum += d * d;
       ++cnt;
@@ -624,7 +660,7 @@ __device__ __forceinline__ double coop_refine_tau(const Task& T, const int* list
       const int qp = list[e];
       const int q = xy_lin(qp, w);
       if (UNMARK) T.state[q] = 0;
-      if (dist((double)sx, (double)sy, (double)xy_x(qp), (double)xy_y(qp)) < width) { d = angle_diff_signed(T.px[q].ang, seed_ang); use = 1; }
+      if (dist((double)sx, (double)sy, (double)xy_x(qp), (double)xy_y(qp)) < width) { d = angle_diff_signed(T.px.ang(q), seed_ang); use = 1; }
     }
     const uint32_t um = __ballot_sync(0xffffffffu, use);
     const int m = min(32, n - b);
@@ -644,7 +680,7 @@ __device__ void process_seed_coop(const Task& T, const int seed, int* const reg,
   int bx0 = sx, bx1 = sx, by0 = sy, by1 = sy;
   int state = 0, n = 0;
   double prec = T.prec, ra = 0, rad_sq = 0;
-  const double seed_ang = T.px[seed].ang;
+  const double seed_ang = T.px.ang(seed);
   // neighbour handled by this lane (lanes 0..8 except 4)
   const int ndx = (lane % 3) - 1, ndy = (lane / 3) - 1;
   const bool nlane = lane < 9 && lane != 4;
@@ -751,7 +787,7 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
   int n = 0, capc = cap;
   double prec = T.prec, ra = 0, rad_sq = 0;
   uint32_t stamp = stamp0;
-  const double seed_ang = active ? T.px[seed].ang : 0.0;
+  const double seed_ang = active ? T.px.ang(seed) : 0.0;
 #pragma unroll 1
   while (__any_sync(0xffffffffu, phase != P_DONE)) {
     if (phase == P_GROW) {
@@ -786,7 +822,7 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
             if (k == 4) continue;
             const int q = rofs[k / 3] + cofs[k % 3];
             st[k] = ld_state(T.state + q);
-            ang[k] = T.px[q].ang;            // (not the dense T.ang: this load also brings the cos/sin of the neighbour into L1)
+            ang[k] = T.px.ang(q);            // (not the dense T.ang: this load also brings the cos/sin of the neighbour into L1)
           }
           if (i + 1 < n_start) nxt = cur[i + 1];
           // candidates: free, not mine yet, gradient defined; `foreign` = carries the stamp of an earlier seed of the wave
@@ -818,7 +854,7 @@ __device__ void speculate_wave(const Task& T, const bool active, const int seed,
             if (((foreign >> k) & 1u) || n >= capc) { aborted = true; break; }
             const int q = qy * w + qx;
             claim_max(&T.state[q], stamp);
-            const float2 cs = *reinterpret_cast<const float2*>(&T.px[q].c);
+            const float2 cs = T.px.cs(q);
             const int qp = xy_pack(qx, qy);
             if (n == i + 1) nxt = qp;
             cur[n++] = qp;

@@ -93,7 +93,7 @@ __device__ __noinline__ bool coop_grow(const Task& T, const bool SPEC, int* cons
     const int q = inb ? qy * w + qx : 0;
     uint32_t sv = kUsed;
     PxA pa; pa.ang = kNotDef; pa.c = 0.f; pa.s = 0.f;
-    if (inb) { sv = ld_state(T.state + q); pa = T.px[q]; }
+    if (inb) ld_rec(T.px.p + q, sv, pa);
     i += m;
     bool cand = inb && !(sv & kUsed) && pa.ang != kNotDef;
     if (SPEC) cand = cand && sv != stamp;
@@ -275,7 +275,7 @@ __device__ __noinline__ void seed_pipeline_coop(const Task& T, const bool SPEC, 
   int capc = cap;
   double prec = T.prec, rad_sq = 0;
   uint32_t stamp = stamp0;
-  const double seed_ang = T.px[seed].ang;
+  const double seed_ang = T.px.ang(seed);
 #pragma unroll 1
   while (true) {
     if (state <= 1) {
@@ -414,7 +414,7 @@ __device__ __forceinline__ void phase_a(const Task& T, SlotCtx* const ctx, Block
             claim_max(&T.state[seed], stamp);
             nxt = xy_pack(sx, sy);
             cur[0] = nxt; n = 1;
-            ra = T.px[seed].ang;
+            ra = T.px.ang(seed);
             double sn, cs;
             sincos_call(ra, &sn, &cs);
             sumdx = (float)cs; sumdy = (float)sn;
@@ -445,8 +445,7 @@ __device__ __forceinline__ void phase_a(const Task& T, SlotCtx* const ctx, Block
       for (int k = 0; k < 9; k++) {
         if (k == 4) continue;
         const int q = rofs[k / 3] + cofs[k % 3];
-        st[k] = ld_state(T.state + q);
-        ang[k] = T.px[q].ang;
+        ld_rec_angle(T.px.p + q, st[k], ang[k]);
       }
       if (i + 1 < n_start) nxt = cur[i + 1];
       uint32_t cand = 0, foreign = 0;
@@ -475,7 +474,7 @@ __device__ __forceinline__ void phase_a(const Task& T, SlotCtx* const ctx, Block
         if (((foreign >> k) & 1u) || n >= cap) { settled = 2; break; }
         const int q = qy * w + qx;
         claim_max(&T.state[q], stamp);
-        const float2 csq = *reinterpret_cast<const float2*>(&T.px[q].c);
+        const float2 csq = T.px.cs(q);
         const int qp = xy_pack(qx, qy);
         if (n == i + 1) nxt = qp;
         cur[n++] = qp;
