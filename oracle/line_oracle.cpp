@@ -186,7 +186,7 @@ struct orc_line {
 extern "C" {
 
 orc_line* orc_line_create(int nfeatures, int refine, float lsd_scale, int nlevels, float scale, int extractor) {
-  if (nlevels < 1 || extractor != 0) return nullptr;
+  if (nlevels < 1 || (extractor != 0 && extractor != 1)) return nullptr;
   orc_line* o = new orc_line{nfeatures, refine, nlevels, extractor, lsd_scale, scale, {}, {}, {}};
   // LSDDetectorC::ComputePyramid scale tables, LSDDetector_custom.cpp:79-90
   o->sf.resize(nlevels); o->isf.resize(nlevels);
@@ -221,7 +221,9 @@ int orc_line_extract(orc_line* o, const uint8_t* img, int w, int h, int stride, 
   for (int oct = 0; oct < o->nlevels; oct++) {
     const PaddedLevel& L = pyr[oct];
     std::vector<float>& seg = o->last_segments[oct];
-    int n = lsd_detect(L.roi(), L.w, L.h, L.stride(), o->refine, (double)o->lsd_scale, 0.6, 2.0, 22.5, 0.0, 0.8, 1024, 0, seg);
+    // extractor 0: LSDDetectorC::detectImpl (LSDDetector_custom.cpp:254-369); 1: detectImpl_ED (:386-461), same key-line construction
+    int n = o->extractor == 1 ? ed_detect(L.roi(), L.w, L.h, L.stride(), seg, nullptr)
+                              : lsd_detect(L.roi(), L.w, L.h, L.stride(), o->refine, (double)o->lsd_scale, 0.6, 2.0, 22.5, 0.0, 0.8, 1024, 0, seg);
     if (n < 0) return -1;
     const float octaveScale = (float)std::pow((double)o->scale, (double)oct);
     for (int k = 0; k < n; k++) {

@@ -35,6 +35,10 @@ struct PaddedLevel {
 // level 0 = copy + border, level l = INTER_LINEAR resize of level l-1 interior + border (isolated)
 void build_padded_pyramid(const uint8_t* img, int w, int h, int stride, const std::vector<float>& inv_scale,
                           std::vector<PaddedLevel>& levels);
+// EDLines back-end (ed_oracle.cpp): lines of one padded level, optional intermediates for the tests
+struct EdDebug { std::vector<uint8_t> smooth, edge; std::vector<int> seg_px, seg_off; int err = 0; };
+int ed_detect(const uint8_t* roi, int w, int h, int stride, std::vector<float>& seg, EdDebug* dbg);
+
 
 // OpenCV LineSegmentDetector restatement (lsd_oracle.cpp)
 int lsd_detect(const uint8_t* img, int w, int h, int stride, int refine, double scale, double sigma_scale, double quant,

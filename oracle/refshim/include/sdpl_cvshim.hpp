@@ -209,6 +209,7 @@ class Mat {
   uchar* data;
   MatStep step;
 
+  int roi_x = 0, roi_y = 0, whole_cols = 0, whole_rows = 0;   // position of a ROI inside its parent buffer (OpenCV: locateROI)
   Mat() : rows(0), cols(0), data(0), type_(0), parent_(false) {}
   Mat(const MatExprZeros& e) : rows(0), cols(0), data(0), type_(0), parent_(false) { *this = e; }
   Mat& operator=(const MatExprZeros& e) {
@@ -218,6 +219,15 @@ class Mat {
   }
   Mat(int r, int c, int type) : rows(0), cols(0), data(0), type_(0), parent_(false) { create(r, c, type); }
   Mat(Size s, int type) : rows(0), cols(0), data(0), type_(0), parent_(false) { create(s.height, s.width, type); }
+  // filled with a scalar (ED_Lib: edge / segment images); only what a one-channel 8- or 16-bit image needs
+  Mat(int r, int c, int type, const Scalar& v) : rows(0), cols(0), data(0), type_(0), parent_(false) { create(r, c, type); fill_(v); }
+  Mat(Size s, int type, const Scalar& v) : rows(0), cols(0), data(0), type_(0), parent_(false) { create(s.height, s.width, type); fill_(v); }
+  void fill_(const Scalar& v) {
+    if (v.val[0] == 0) { for (int y = 0; y < rows; y++) memset(ptr(y), 0, (size_t)cols * elemSize()); return; }
+    if (depth() != CV_8U) shim_unsupported("Mat(..., Scalar != 0) for a non-8-bit image");
+    for (int y = 0; y < rows; y++) memset(ptr(y), (int)v.val[0], (size_t)cols);
+  }
+  template <typename T> T& at(const Point_<int>& p) { return at<T>(p.y, p.x); }
   // user-owned memory (not freed)
   Mat(int r, int c, int type, void* d, size_t st = 0) : rows(r), cols(c), data((uchar*)d), type_(type), parent_(false) {
     step = st ? st : (size_t)c * elemSize();

@@ -20,6 +20,8 @@ typedef Point3_<double> Point3d;
 
 // display / drawing: no-ops (the constructor draws the detected lines into a clone of the image and shows it, Frame.cc:399-408)
 inline void line(Mat&, Point2f, Point2f, const Scalar&, int = 1, int = 8, int = 0) {}
+inline void line(Mat&, Point_<double>, Point_<double>, const Scalar&, int = 1, int = 8, int = 0) {}   // EDLines::getLineImage / drawOnImage (never called)
+enum { LINE_AA = 16, COLOR_GRAY2BGR = 8 };
 inline void imshow(const std::string&, const Mat&) {}
 inline int waitKey(int = 0) { return -1; }
 struct DrawMatchesFlags { enum { DEFAULT = 0 }; };
@@ -45,6 +47,7 @@ template <typename T> struct MatCommaInit {
   operator Mat_<T>() const { shim_unsupported("Mat_ comma initialiser"); }
 };
 template <typename T, typename U> inline MatCommaInit<T> operator<<(const Mat_<T>&, U) { return MatCommaInit<T>(); }
+inline void convertScaleAbs(const Mat&, Mat&, double = 1, double = 0) { shim_unsupported("convertScaleAbs"); }   // ED::getGradImage (never called)
 template <typename T, typename P> inline int partition(const std::vector<T>&, std::vector<int>&, P) { shim_unsupported("partition"); }
 }  // namespace cv
 #endif

@@ -17,6 +17,7 @@ void Mat::create(int r, int c, int type) {
   rows = r; cols = c;
   step = (size_t)c * elemSize();
   parent_ = false;
+  roi_x = roi_y = 0; whole_cols = whole_rows = 0;
   size_t bytes = step.p * (size_t)r;
   buf_ = std::shared_ptr<uchar>((uchar*)malloc(bytes ? bytes : 1), free);
   data = buf_.get();
@@ -28,7 +29,11 @@ Mat Mat::operator()(const Rect& r) const {
   Mat m(*this);
   m.data = data + step.p * r.y + (size_t)r.x * elemSize();
   m.rows = r.height; m.cols = r.width;
-  if (r.width != cols || r.height != rows) m.parent_ = true;
+  if (r.width != cols || r.height != rows) {
+    m.parent_ = true;
+    if (!parent_) { m.whole_cols = cols; m.whole_rows = rows; m.roi_x = 0; m.roi_y = 0; }
+    m.roi_x += r.x; m.roi_y += r.y;
+  }
   return m;
 }
 

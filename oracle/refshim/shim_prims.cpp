@@ -47,7 +47,21 @@ void GaussianBlur(InputArray _src, OutputArray _dst, Size ksize, double sigmaX, 
   if (ksize.width == 7 && ksize.height == 7 && sigmaX == 2 && sigmaY == 2) kind = 0;       // ORBextractor.cc:1084
   else if (ksize.width == 5 && ksize.height == 5 && sigmaX == 1 && sigmaY == 1) kind = 1;  // binary_descriptor_custom.cpp:358
   if (kind < 0 || (borderType & ~BORDER_ISOLATED) != BORDER_REFLECT_101) shim_unsupported("GaussianBlur kernel / border");
-  if (src.isSubmatrix() && !(borderType & BORDER_ISOLATED)) shim_unsupported("non-isolated GaussianBlur of a ROI");
+  if (src.isSubmatrix() && !(borderType & BORDER_ISOLATED)) {
+    // OpenCV reads the pixels around a ROI from the parent buffer (ED_Lib smooths LSDDetectorC's pyramid ROI, which sits inside a
+    // 19-pixel border): blur the ROI widened by the kernel radius, all of it real pixels, and keep the interior
+    const int r = kind == 0 ? 3 : 2;
+    if (src.roi_x < r || src.roi_y < r || src.roi_x + src.cols + r > src.whole_cols || src.roi_y + src.rows + r > src.whole_rows)
+      shim_unsupported("non-isolated GaussianBlur of a ROI closer to the parent's edge than the kernel radius");
+    const int W = src.cols + 2 * r, H = src.rows + 2 * r;
+    Mat wide(H, W, CV_8UC1), out(H, W, CV_8UC1);
+    for (int y = 0; y < H; y++) memcpy(wide.ptr(y), src.data + (ptrdiff_t)(y - r) * (ptrdiff_t)src.step.p - r, (size_t)W);
+    orc::gaussian_blur_u8(wide.data, W, H, (int)wide.step, out.data, (int)out.step, kind);
+    _dst.create(src.rows, src.cols, src.type());
+    Mat dst = _dst.getMat();
+    for (int y = 0; y < src.rows; y++) memcpy(dst.ptr(y), out.ptr(y + r) + r, (size_t)src.cols);
+    return;
+  }
   Mat in = (_dst.getMat().data == src.data) ? src.clone() : src;
   _dst.create(src.rows, src.cols, src.type());
   Mat dst = _dst.getMat();

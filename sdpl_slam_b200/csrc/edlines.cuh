@@ -1,0 +1,209 @@
+// sdpl_slam_b200/csrc/edlines.cuh -- the EDLines back-end of Lineextractor (extractor == 1; reference: LSDDetectorC::detectImpl_ED,
+// 3rdparty/line_descriptor/src/LSDDetector_custom.cpp:386-461 -> EDLines::EDLines(Mat), ED_Lib/EDLines.cpp:8-70, ED_Lib/ED.cpp:8-62).
+// Included by line.cu after LineDev / OctDev.  Per (frame, octave) task:
+//   k_ed_smooth   5x5 sigma 1 Gaussian of the pyramid level (OpenCV fixed point: Q8.8 rows, Q16.16 columns, round half up)   [pixel-parallel]
+//   k_ed_grad     Sobel-weighted |gx| + |gy| with threshold 36, vertical / horizontal direction map (ED.cpp:275-362)           [pixel-parallel]
+//   k_ed_anchor   anchors: gradient maxima by >= 8 across the edge direction (ED.cpp:364-398)                                  [pixel-parallel]
+//   k_ed_sort     anchors by descending gradient, row-major inside a value (ED.cpp:1000-1047 + the descending loop of :414)   [one warp per task]
+//   k_ed_serial   anchor linking, line fitting, joining, validation: include/sdpl_edlines_core.h                               [one thread per task]
+// The linking is sequential per image by definition (a walk stops at the pixels earlier walks have drawn), like LSD's region growing;
+// this first version runs the whole sequential tail in one thread per task, so a batch is as fast as its slowest image, and all tasks
+// of the batch run side by side.  Results go into the Pending slots of the LSD path (accepted = 1), so key-line construction, the top-N
+// filter and LBD are the kernels of the LSD back-end.
+#pragma once
+#include "../../include/sdpl_edlines_core.h"
+
+namespace sdpl {
+
+constexpr int kEdNfaN = 2048;            // validation look-up table: pixel counts below this (a 2-px-wide rectangle around a line of < 80 pixels)
+
+struct EdOct {
+  int w, h, npx;
+  unsigned long long img_off;            // bytes inside one frame's image block: smooth[npx] dir[npx] edge[npx] pad grad[npx] (s16)
+  unsigned long long work_off;           // bytes inside one frame's scratch block
+  int anchors_cap, pixels_cap, stack_cap, chains_cap, chain_nos_cap, seg_px_cap, seg_cap, lines_cap;
+  int min_line_len;
+};
+struct EdDev {
+  EdOct O[kMaxOct];
+  unsigned long long img_frame, work_frame;
+  uint8_t* img; uint8_t* work;
+  int* n_anchors;                        // per task
+  const double* atan_lut;                // [1025]
+  const int* nfa_min_k;                  // [nl][kEdNfaN]
+};
+
+__device__ __forceinline__ size_t ed_align(size_t v) { return (v + 15) & ~(size_t)15; }
+struct EdPtrs {
+  uint8_t *smooth, *dir, *edge; int16_t* grad;
+  int* anchors; int* pixels; sdpl_ed::Node* stack; sdpl_ed::Chain* chains; int* chain_nos; int* seg_px; int* seg_off; sdpl_ed::Line* lines;
+};
+__host__ __device__ inline size_t ed_img_bytes(int npx) { return (((size_t)3 * npx + 15) & ~(size_t)15) + (size_t)2 * npx; }
+__host__ __device__ inline size_t ed_work_bytes(const EdOct& O) {
+  size_t b = 0;
+  b += (((size_t)O.anchors_cap * 4 + 15) & ~(size_t)15);
+  b += (((size_t)O.pixels_cap * 4 + 15) & ~(size_t)15);
+  b += (size_t)O.stack_cap * sizeof(sdpl_ed::Node);
+  b += (((size_t)O.chains_cap * sizeof(sdpl_ed::Chain) + 15) & ~(size_t)15);
+  b += (((size_t)O.chain_nos_cap * 4 + 15) & ~(size_t)15);
+  b += (((size_t)O.seg_px_cap * 4 + 15) & ~(size_t)15);
+  b += (((size_t)O.seg_cap * 4 + 15) & ~(size_t)15);
+  b += (size_t)O.lines_cap * sizeof(sdpl_ed::Line);
+  return (b + 15) & ~(size_t)15;
+}
+__device__ __forceinline__ EdPtrs ed_ptrs(const EdDev& E, int f, int o) {
+  const EdOct& O = E.O[o];
+  EdPtrs P;
+  uint8_t* im = E.img + (size_t)f * E.img_frame + O.img_off;
+  P.smooth = im; P.dir = im + O.npx; P.edge = im + 2 * (size_t)O.npx;
+  P.grad = (int16_t*)(im + ed_align((size_t)3 * O.npx));
+  uint8_t* wk = E.work + (size_t)f * E.work_frame + O.work_off;
+  P.anchors = (int*)wk; wk += ed_align((size_t)O.anchors_cap * 4);
+  P.pixels = (int*)wk; wk += ed_align((size_t)O.pixels_cap * 4);
+  P.stack = (sdpl_ed::Node*)wk; wk += (size_t)O.stack_cap * sizeof(sdpl_ed::Node);
+  P.chains = (sdpl_ed::Chain*)wk; wk += ed_align((size_t)O.chains_cap * sizeof(sdpl_ed::Chain));
+  P.chain_nos = (int*)wk; wk += ed_align((size_t)O.chain_nos_cap * 4);
+  P.seg_px = (int*)wk; wk += ed_align((size_t)O.seg_px_cap * 4);
+  P.seg_off = (int*)wk; wk += ed_align((size_t)O.seg_cap * 4);
+  P.lines = (sdpl_ed::Line*)wk;
+  return P;
+}
+__device__ __forceinline__ void ed_level(const LineDev& D, int f, int o, const uint8_t*& src, int& stride) {
+  if (o == 0) { src = D.in + (size_t)f * D.in_frame; stride = D.in_stride; }
+  else { src = D.lvl + (size_t)f * D.lvl_frame + D.O[o].lvl_off; stride = D.O[o].w; }
+}
+__device__ __forceinline__ int ed_r101(int v, int n) { if (v < 0) v = -v; if (v >= n) v = 2 * n - 2 - v; return v; }
+
+__global__ void __launch_bounds__(256) k_ed_smooth(LineDev D, EdDev E, int o) {
+  const EdOct& O = E.O[o];
+  const int f = blockIdx.z;
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (x >= O.w || y >= O.h) return;
+  const uint8_t* src; int stride;
+  ed_level(D, f, o, src, stride);
+  const int k[5] = {14, 62, 104, 62, 14};
+  int xs[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) xs[j] = ed_r101(x + j - 2, O.w);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    const uint8_t* row = src + (size_t)ed_r101(y + i - 2, O.h) * stride;
+    uint32_t hsum = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) hsum += (uint32_t)k[j] * row[xs[j]];
+    acc += (uint32_t)k[i] * hsum;
+  }
+  ed_ptrs(E, f, o).smooth[(size_t)y * O.w + x] = (uint8_t)min(255u, (acc + (1u << 15)) >> 16);
+}
+
+__global__ void __launch_bounds__(256) k_ed_grad(EdDev E, int o) {
+  const EdOct& O = E.O[o];
+  const int f = blockIdx.z, w = O.w, h = O.h;
+  const int j = blockIdx.x * 64 + (threadIdx.x & 63), i = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (j >= w || i >= h) return;
+  const EdPtrs P = ed_ptrs(E, f, o);
+  const uint8_t* s = P.smooth;
+  int sum = sdpl_ed::kGradThresh - 1, d = 0;
+  if (i >= 1 && i < h - 1 && j >= 1 && j < w - 1) {
+    const int com1 = (int)s[(i + 1) * w + j + 1] - (int)s[(i - 1) * w + j - 1];
+    const int com2 = (int)s[(i - 1) * w + j + 1] - (int)s[(i + 1) * w + j - 1];
+    const int gx = abs(com1 + com2 + 2 * ((int)s[i * w + j + 1] - (int)s[i * w + j - 1]));
+    const int gy = abs(com1 - com2 + 2 * ((int)s[(i + 1) * w + j] - (int)s[(i - 1) * w + j]));
+    sum = gx + gy;
+    if (sum >= sdpl_ed::kGradThresh) d = gx >= gy ? sdpl_ed::kVertical : sdpl_ed::kHorizontal;
+  }
+  P.grad[i * w + j] = (int16_t)sum;
+  P.dir[i * w + j] = (uint8_t)d;
+}
+
+__global__ void __launch_bounds__(256) k_ed_anchor(EdDev E, int o) {
+  const EdOct& O = E.O[o];
+  const int f = blockIdx.z, w = O.w, h = O.h;
+  const int j = blockIdx.x * 64 + (threadIdx.x & 63), i = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (j >= w || i >= h) return;
+  const EdPtrs P = ed_ptrs(E, f, o);
+  int e = 0;
+  if (i >= 2 && i < h - 2 && j >= 2 && j < w - 2) {
+    const int g = P.grad[i * w + j];
+    if (g >= sdpl_ed::kGradThresh) {
+      int d1, d2;
+      if (P.dir[i * w + j] == sdpl_ed::kVertical) { d1 = g - P.grad[i * w + j - 1]; d2 = g - P.grad[i * w + j + 1]; }
+      else { d1 = g - P.grad[(i - 1) * w + j]; d2 = g - P.grad[(i + 1) * w + j]; }
+      if (d1 >= sdpl_ed::kAnchorThresh && d2 >= sdpl_ed::kAnchorThresh) e = sdpl_ed::kAnchor;
+    }
+  }
+  P.edge[i * w + j] = (uint8_t)e;
+}
+
+// one warp per task: counting sort of the anchors by gradient value (descending), row-major inside a value
+__global__ void __launch_bounds__(32) k_ed_sort(LineDev D, EdDev E) {
+  __shared__ int hist[2048];
+  const int task = blockIdx.x, f = task / D.nl, o = task % D.nl, lane = threadIdx.x;
+  const EdOct& O = E.O[o];
+  const EdPtrs P = ed_ptrs(E, f, o);
+  for (int i = lane; i < 2048; i += 32) hist[i] = 0;
+  __syncwarp();
+  for (int q = lane; q < O.npx; q += 32)
+    if (P.edge[q] == sdpl_ed::kAnchor) atomicAdd(&hist[min((int)P.grad[q], 2047)], 1);
+  __syncwarp();
+  // start of every value's run in descending order of the value: lane-strided exclusive scan (64 bins per lane), highest value first
+  int local = 0;
+  for (int b = 0; b < 64; b++) local += hist[2047 - (lane * 64 + b)];
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+  int run = incl - local;
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  for (int b = 0; b < 64; b++) { const int idx = 2047 - (lane * 64 + b); const int c = hist[idx]; hist[idx] = run; run += c; }
+  __syncwarp();
+  if (total > O.anchors_cap) { if (lane == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); E.n_anchors[task] = 0; } return; }
+  for (int q0 = 0; q0 < O.npx; q0 += 32) {
+    const int q = q0 + lane;
+    const bool a = q < O.npx && P.edge[q] == sdpl_ed::kAnchor;
+    uint32_t m = __ballot_sync(0xffffffffu, a);
+    while (m) {                                   // in pixel order: the position inside a value's run is the row-major rank
+      const int L = __ffs(m) - 1;
+      m &= m - 1;
+      if (lane == L) { const int g = min((int)P.grad[q], 2047); P.anchors[hist[g]] = q; hist[g]++; }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) E.n_anchors[task] = total;
+}
+
+__global__ void __launch_bounds__(32) k_ed_serial(LineDev D, EdDev E) {
+  const int task = blockIdx.x * blockDim.x + threadIdx.x;
+  if (task >= D.nl * D.B) return;
+  const int f = task / D.nl, o = task % D.nl;
+  const EdOct& O = E.O[o];
+  const EdPtrs P = ed_ptrs(E, f, o);
+  sdpl_ed::Work W;
+  W.w = O.w; W.h = O.h; W.grad = P.grad; W.dir = P.dir; W.edge = P.edge;
+  W.anchors = P.anchors; W.n_anchors = E.n_anchors[task];
+  W.pixels = P.pixels; W.pixels_cap = O.pixels_cap;
+  W.stack = P.stack; W.stack_cap = O.stack_cap;
+  W.chains = P.chains; W.chains_cap = O.chains_cap;
+  W.chain_nos = P.chain_nos; W.chain_nos_cap = O.chain_nos_cap;
+  W.seg_px = P.seg_px; W.seg_px_cap = O.seg_px_cap;
+  W.seg_off = P.seg_off; W.seg_cap = O.seg_cap; W.nseg = 0;
+  W.lines = P.lines; W.lines_cap = O.lines_cap; W.nlines = 0;
+  ed_level(D, f, o, W.src, W.src_stride);
+  W.atan_lut = E.atan_lut;
+  W.nfa_min_k = E.nfa_min_k + (size_t)o * kEdNfaN; W.nfa_n = kEdNfaN;
+  W.min_line_len = O.min_line_len;
+  W.err = 0;
+  sdpl_ed::run_task(W);
+  lsd::Pending* pend = D.pend + (size_t)task * D.pend_cap;
+  int n = W.nlines;
+  if (W.err || n > D.pend_cap) { atomicOr(D.err, SDPL_ERR_OVERFLOW); n = 0; }
+  for (int i = 0; i < n; i++) {
+    pend[i].accepted = 1;
+    pend[i].seg[0] = (float)W.lines[i].sx; pend[i].seg[1] = (float)W.lines[i].sy;
+    pend[i].seg[2] = (float)W.lines[i].ex; pend[i].seg[3] = (float)W.lines[i].ey;
+    pend[i].tag = 0; pend[i].seed = 0; pend[i].npix = W.lines[i].len;
+  }
+  D.npend[task] = n;
+}
+
+}  // namespace sdpl

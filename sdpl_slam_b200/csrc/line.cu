@@ -71,6 +71,9 @@ struct LineDev {
   float gaussL[21], gaussG[63];
 };
 
+}  // namespace sdpl
+#include "edlines.cuh"
+namespace sdpl {
 // ------------------------------------------------------------------------------------------------
 // Shared-memory staging of an u8 image window as aligned 32-bit words, for the word / dp4a stencils below (L2, L8).
 // Staged word m of a row holds the image columns xf + 4m - 4 .. xf + 4m - 1, whatever the alignment of the image rows in
@@ -873,6 +876,9 @@ struct sdpl_line {
   LineDev D;
   DevBuf lvl, scaled, px, ang, g2, order, hist, maxg2, ndef, torder, reg, pend, npend, g, sd, err, tables, tmpkl;
   DevBuf in_stage, out_kls, out_desc, out_n, prof, lgam, nbig, bigidx, ctx, nfatab;
+  DevBuf ed_img, ed_work, ed_nanch, ed_tab;    // EDLines back-end (extractor == 1): images, per-task scratch, anchor counts, host tables
+  EdDev E;
+  int ed_w = 0, ed_h = 0;
   int grow_warps = 0 /* auto */, sm_count = 148, grow_minb = 0 /* auto */;
   int grow_warps_small = 16, grow_ta_small = -1;  // small batches (tasks <= SMs): warps per task, phase-A cap (-1: grow_ta)
   int grow_forced = 0;   // SDPL_GROW given: use it for big batches only (single frames keep the 8-warp variant)
@@ -1085,10 +1091,51 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
 }
 
 // LSD detection + KeyLine construction for B frames resident on the device (asynchronous on o->stream)
+// EDLines back-end: buffers and host tables for B frames of the current geometry (after line_setup)
+static int ed_setup(sdpl_line* o, int B) {
+  LineDev& D = o->D;
+  EdDev& E = o->E;
+  const int nl = o->nlevels;
+  size_t img_off = 0, work_off = 0;
+  for (int l = 0; l < nl; l++) {
+    EdOct& O = E.O[l];
+    O.w = D.O[l].w; O.h = D.O[l].h; O.npx = O.w * O.h;
+    if (O.w < 8 || O.h < 8 || O.w > 32767 || O.h > 32767) { set_last_error("EDLines: image size out of range"); return SDPL_ERR_UNSUPPORTED; }
+    O.anchors_cap = O.npx / 4 + 1024; O.pixels_cap = O.npx / 4 + 1024; O.stack_cap = O.npx / 16 + 1024; O.chains_cap = O.npx / 16 + 1024;
+    O.chain_nos_cap = O.npx / 16 + 1024; O.seg_px_cap = O.npx / 2 + 1024; O.seg_cap = O.npx / 64 + 256; O.lines_cap = O.npx / 64 + 256;
+    O.min_line_len = sdpl_ed::host::min_line_len(O.w, O.h);
+    O.img_off = img_off; img_off += (ed_img_bytes(O.npx) + 255) & ~(size_t)255;
+    O.work_off = work_off; work_off += (ed_work_bytes(O) + 255) & ~(size_t)255;
+  }
+  E.img_frame = img_off; E.work_frame = work_off;
+  int rc;
+  if ((rc = o->ed_img.reserve(E.img_frame * B))) return rc;
+  if ((rc = o->ed_work.reserve(E.work_frame * B))) return rc;
+  if ((rc = o->ed_nanch.reserve(sizeof(int) * nl * B))) return rc;
+  if ((rc = o->ed_tab.reserve(sizeof(double) * (sdpl_ed::kAtanLut + 1) + sizeof(int) * (size_t)kEdNfaN * kMaxOct))) return rc;
+  E.img = o->ed_img.as<uint8_t>(); E.work = o->ed_work.as<uint8_t>(); E.n_anchors = o->ed_nanch.as<int>();
+  E.atan_lut = o->ed_tab.as<double>();
+  E.nfa_min_k = (const int*)(o->ed_tab.as<uint8_t>() + sizeof(double) * (sdpl_ed::kAtanLut + 1));
+  if (o->ed_w != D.in_w || o->ed_h != D.in_h) {
+    // the C library's atan / log / exp / pow of the validation tables are evaluated on the host (as in the oracle)
+    std::vector<double> lut(sdpl_ed::kAtanLut + 1);
+    sdpl_ed::host::atan_table(lut.data());
+    std::vector<int> mk((size_t)kEdNfaN * kMaxOct, 0);
+    for (int l = 0; l < nl; l++)
+      if (!sdpl_ed::host::nfa_table(E.O[l].w, E.O[l].h, kEdNfaN, mk.data() + (size_t)l * kEdNfaN)) { set_last_error("EDLines: NFA table is not monotone"); return SDPL_ERR_UNSUPPORTED; }
+    SDPL_CUDA(cudaMemcpyAsync((void*)E.atan_lut, lut.data(), sizeof(double) * lut.size(), cudaMemcpyHostToDevice, o->stream));
+    SDPL_CUDA(cudaMemcpyAsync((void*)E.nfa_min_k, mk.data(), sizeof(int) * mk.size(), cudaMemcpyHostToDevice, o->stream));
+    SDPL_CUDA(cudaStreamSynchronize(o->stream));
+    o->ed_w = D.in_w; o->ed_h = D.in_h;
+  }
+  return SDPL_OK;
+}
+
 static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, int h, int stride, size_t frame_stride,
                            sdpl_keyline* d_kls, int capacity, int* d_n_out) {
   int rc = line_setup(o, w, h, B);
   if (rc) return rc;
+  if (o->extractor == 1 && (rc = ed_setup(o, B))) return rc;
   LineDev& D = o->D;
   D.B = B; D.in = d_imgs; D.in_stride = stride; D.in_frame = frame_stride; D.serial_mode = o->serial_mode;
   D.prof_detail = o->prof_detail;
@@ -1101,6 +1148,31 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "lsd_pyramid");
+  if (o->extractor == 1) {
+    // EDLines back-end (edlines.cuh): the lines land in the Pending slots, key lines / top-N / LBD are shared with the LSD back-end
+    const EdDev& E = o->E;
+    for (int l = 0; l < nl; l++) {
+      const dim3 g(div_up(E.O[l].w, 64), div_up(E.O[l].h, 4), B);
+      k_ed_smooth<<<g, 256, 0, st>>>(D, E, l);
+      SDPL_LAUNCH_CHECK();
+      k_ed_grad<<<g, 256, 0, st>>>(E, l);
+      SDPL_LAUNCH_CHECK();
+      k_ed_anchor<<<g, 256, 0, st>>>(E, l);
+      SDPL_LAUNCH_CHECK();
+    }
+    o->timer.mark(st, "ed_gradient");
+    k_ed_sort<<<nl * B, 32, 0, st>>>(D, E);
+    SDPL_LAUNCH_CHECK();
+    o->timer.mark(st, "ed_sort");
+    k_ed_serial<<<div_up(nl * B, 32), 32, 0, st>>>(D, E);
+    SDPL_LAUNCH_CHECK();
+    o->timer.mark(st, "ed_link_fit_validate");
+    k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());
+    SDPL_LAUNCH_CHECK();
+    o->timer.mark(st, "keylines");
+    o->last_B = B;
+    return SDPL_OK;
+  }
   SDPL_CUDA(cudaMemsetAsync(D.maxg2, 0, sizeof(int) * nl * B, st));
   for (int l = 0; l < nl; l++) {
     k_lsd_scale<<<dim3(div_up(D.O[l].sw, kST_W), div_up(D.O[l].sh, kST_H), B), 256, 0, st>>>(D, l);
@@ -1250,7 +1322,7 @@ int sdpl_line_create(sdpl_line** out, int nfeatures, int refine, float lsd_scale
     set_last_error("sdpl_line_create: bad argument");
     return SDPL_ERR_ARG;
   }
-  if (extractor != 0) { set_last_error("sdpl_line_create: extractor==1 (EDLines) is out of scope; only LSD (0) is implemented"); return SDPL_ERR_UNSUPPORTED; }
+  if (extractor != 0 && extractor != 1) { set_last_error("sdpl_line_create: extractor must be 0 (LSD) or 1 (EDLines)"); return SDPL_ERR_UNSUPPORTED; }
   if (nlevels > kMaxOct) { set_last_error("sdpl_line_create: at most 4 octaves"); return SDPL_ERR_UNSUPPORTED; }
   {  // only the reference's pre-scaling kernel is implemented: sigma = 0.6/0.8 = 0.75 -> 7 taps [0,4,56,136,56,4,0]
     const double sigma = 0.6 / (double)lsd_scale;
@@ -1304,7 +1376,7 @@ void sdpl_line_destroy(sdpl_line* o) {
   if (!o) return;
   cudaSetDevice(o->device);
   cudaStreamSynchronize(o->stream);
-  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->order, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
+  for (DevBuf* b : {&o->lvl, &o->scaled, &o->px, &o->ang, &o->g2, &o->order, &o->ed_img, &o->ed_work, &o->ed_nanch, &o->ed_tab, &o->hist, &o->maxg2, &o->ndef, &o->torder, &o->reg, &o->pend, &o->npend,
                     &o->g, &o->sd, &o->err, &o->tables, &o->tmpkl, &o->in_stage, &o->out_kls, &o->out_desc, &o->out_n, &o->prof, &o->lgam, &o->nbig, &o->bigidx, &o->ctx, &o->nfatab})
     b->release();
   if (o->h_stage) cudaFreeHost(o->h_stage);

@@ -160,7 +160,7 @@ def test_line_golden_fixture(frontend):
 
 def test_line_unsupported_configurations(frontend):
     with pytest.raises(frontend.SdplError) as e:
-        frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 1)       # EDLines back-end: out of scope
+        frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 2)       # 0 = LSD, 1 = EDLines (tests/test_gpu_edlines.py); nothing else exists
     assert e.value.code == frontend.SDPL_ERR_UNSUPPORTED
     with pytest.raises(frontend.SdplError):
         frontend.Lineextractor(0, 2, 0.5, 2, 2.0, 0)       # only the reference's 0.8 pre-scaling is implemented

@@ -1,6 +1,6 @@
 """Pins the ORACLE (oracle/*.cpp) against the reference's OWN code: oracle/_ref/libsdpl_ref.so is
 /root/reference/src/{ORBextractor,Lineextractor,Frame}.cc and 3rdparty/line_descriptor/src/{LSDDetector_custom,
-binary_descriptor_custom,binary_descriptor_matcher}.cpp compiled UNMODIFIED against the OpenCV stand-in in
+binary_descriptor_custom,binary_descriptor_matcher}.cpp + src/ED_Lib/{ED,EDLines,NFA}.cpp compiled UNMODIFIED against the OpenCV stand-in in
 oracle/refshim/ (recipe: oracle/refshim/Makefile).  The OpenCV primitives under it are oracle/cvprim.cpp and
 oracle/lsd_oracle.cpp, themselves pinned bit-exact against cv2 in test_oracle_vs_cv2.py.
 
@@ -116,6 +116,42 @@ def test_line_extractor_equals_reference(ref, oracle, h, w, nf, refine, nl, seed
     rt, ot = r.tables(synth.frame(seeds[0], h, w)), o.tables()
     for a, b in zip(rt, (ot["scale"], ot["inv_scale"], ot["sigma2"], ot["inv_sigma2"])):
         assert (a == b).all()
+
+
+ED_CONFIGS = [  # (h, w, nfeatures, nlevels, seeds): Lineextractor with extractor == 1 (LSDDetectorC::detect_ED -> ED_Lib EDLines)
+    (375, 1242, 0, 2, (0, 1, 2, 3)),
+    (480, 640, 0, 2, (6, 7)),
+    (375, 1242, 60, 2, (4,)),          # top-N branch
+    (240, 416, 0, 1, (7,)),
+    (240, 416, 0, 3, (8,)),
+    (768, 1024, 0, 2, (9,)),
+    (96, 160, 0, 2, (5,)),
+]
+
+
+@pytest.mark.parametrize("h,w,nf,nl,seeds", ED_CONFIGS)
+def test_edlines_extractor_equals_reference(ref, oracle, h, w, nf, nl, seeds):
+    """The EDLines back-end: oracle/ed_oracle.cpp + include/sdpl_edlines_core.h (the source the CUDA kernel compiles as well) against
+    ED_Lib's ED.cpp / EDLines.cpp / NFA.cpp compiled unmodified.  The reference hands ED_Lib a ROI of its padded pyramid buffer and ED_Lib
+    indexes it as if it were contiguous (see the header of sdpl_edlines_core.h): the shim's Mat reproduces that memory layout, so the
+    comparison covers it."""
+    r = ref.RefLineextractor(nf, 2, 0.8, nl, 2.0, 1)
+    o = oracle.LineOracle(nf, 2, 0.8, nl, 2.0, 1)
+    total = 0
+    for s in seeds:
+        img = synth.frame(s, h, w)
+        rk, rd = r(img)
+        ok, od = o(img)
+        assert len(rk) == len(ok)
+        total += len(rk)
+        for f in rk.dtype.names:
+            if f == "angle":
+                continue
+            assert (rk[f] == ok[f]).all(), f
+        if len(rk):
+            assert np.abs(rk["angle"] - ok["angle"]).max() <= 4e-7
+        assert (rd == od).all(), "LBD descriptors differ"
+    assert total > 0 or h < 100
 
 
 def test_lbd_equals_reference_on_given_keylines(ref, oracle):
