@@ -166,23 +166,31 @@ SDPL_ED_HD inline void link_anchors(Work& W) {
       const int want = horiz ? kHorizontal : kVertical;
       const bool to_child0 = dir == kLeft || dir == kUp;
       bool stopped = false;
-      while (dirm[r * w + c] == want) {
+      int cur_dir = dirm[r * w + c];
+      while (cur_dir == want) {
+        // every value the step can need is loaded up front, independently of the decisions below (one memory round trip per step
+        // instead of a chain of them: the walk is latency-bound on a GPU thread)
+        const int br = r + fr, bc = c + fc;                               // straight ahead
+        const int oA = (br - lr) * w + bc - lc, oB = br * w + bc, oC = (br + lr) * w + bc + lc;
+        const int o1 = (r - lr) * w + (c - lc), o2 = (r + lr) * w + (c + lc);
+        const int eA = edge[oA], eB = edge[oB], eC = edge[oC], e1 = edge[o1], e2 = edge[o2];
+        const int gA = grad[oA], gB = grad[oB], gC = grad[oC];
+        const int dA = dirm[oA], dB = dirm[oB], dC = dirm[oC];
         edge[r * w + c] = kEdge;
         // clean up the anchors beside the path
-        { const int o1 = (r - lr) * w + (c - lc), o2 = (r + lr) * w + (c + lc);
-          if (edge[o1] == kAnchor) edge[o1] = 0;
-          if (edge[o2] == kAnchor) edge[o2] = 0; }
-        const int br = r + fr, bc = c + fc;                               // straight ahead
-        if (edge[br * w + bc] >= kAnchor) { r = br; c = bc; }
-        else if (edge[(br + first_lat * lr) * w + bc + first_lat * lc] >= kAnchor) { r = br + first_lat * lr; c = bc + first_lat * lc; }
-        else if (edge[(br - first_lat * lr) * w + bc - first_lat * lc] >= kAnchor) { r = br - first_lat * lr; c = bc - first_lat * lc; }
-        else {
-          const int A = grad[(br - lr) * w + bc - lc], B = grad[br * w + bc], C = grad[(br + lr) * w + bc + lc];
-          int lat = 0;
-          if (A > B) { lat = A > C ? -1 : 1; } else if (C > B) lat = 1;
-          r = br + lat * lr; c = bc + lat * lc;
-        }
-        if (edge[r * w + c] == kEdge || grad[r * w + c] < kGradThresh) {
+        if (e1 == kAnchor) edge[o1] = 0;
+        if (e2 == kAnchor) edge[o2] = 0;
+        // the neighbour ahead that is already an anchor / edge pixel, looked for in the reference's order; else the largest gradient
+        const int eF = first_lat < 0 ? eA : eC, eS = first_lat < 0 ? eC : eA;
+        int lat;
+        if (eB >= kAnchor) lat = 0;
+        else if (eF >= kAnchor) lat = first_lat;
+        else if (eS >= kAnchor) lat = -first_lat;
+        else { lat = 0; if (gA > gB) { lat = gA > gC ? -1 : 1; } else if (gC > gB) lat = 1; }
+        r = br + lat * lr; c = bc + lat * lc;
+        const int eN = lat == 0 ? eB : (lat < 0 ? eA : eC), gN = lat == 0 ? gB : (lat < 0 ? gA : gC);
+        cur_dir = lat == 0 ? dB : (lat < 0 ? dA : dC);
+        if (eN == kEdge || gN < kGradThresh) {
           ch[no_chains].len = chain_len;
           if (to_child0) ch[parent].child0 = no_chains; else ch[parent].child1 = no_chains;
           no_chains++;
@@ -368,8 +376,10 @@ SDPL_ED_HD inline void line_fit(const SegXY& s, int o, int count, double& a, dou
   }
 }
 
-// EDLines::SplitSegment2Lines (EDLines.cpp:270-358); line_error = 1.0
-SDPL_ED_HD inline void split_segment(Work& W, int seg_no) {
+// EDLines::SplitSegment2Lines (EDLines.cpp:270-358); line_error = 1.0.  The lines of segment seg_no go to out[0, cap) (out == null: they
+// are only counted); returns their number.  Segments are independent of each other, so a caller may work on many at once.
+SDPL_ED_HD inline int split_segment(Work& W, int seg_no, Line* out, int cap) {
+  int n_out = 0;
   SegXY s; s.p = W.seg_px + W.seg_off[seg_no];
   int no_pixels = W.seg_off[seg_no + 1] - W.seg_off[seg_no];
   const int mll = W.min_line_len;
@@ -385,7 +395,7 @@ SDPL_ED_HD inline void split_segment(Work& W, int seg_no) {
       if (error <= 0.5) { valid = true; break; }
       no_pixels -= 1; o += 1; first_pixel_index += 1;
     }
-    if (!valid) return;
+    if (!valid) return n_out;
     int index = mll, len = mll;
     while (index < no_pixels) {
       const int start_index = index;
@@ -410,16 +420,20 @@ SDPL_ED_HD inline void split_segment(Work& W, int seg_no) {
         idx = last_good;
         while (min_distance(s.x(o + idx), s.y(o + idx), lastA, lastB, lastInvert) > line_error) idx--;
         closest_point(s.x(o + idx), s.y(o + idx), lastA, lastB, lastInvert, ex, ey);
-        if (W.nlines >= W.lines_cap) { W.err |= kErrLines; return; }
-        Line& L = W.lines[W.nlines++];
-        L.a = lastA; L.b = lastB; L.invert = lastInvert; L.sx = sx; L.sy = sy; L.ex = ex; L.ey = ey;
-        L.segmentNo = seg_no; L.firstPixelIndex = first_pixel_index + skipped; L.len = idx - skipped + 1;
+        if (out) {
+          if (n_out >= cap) { W.err |= kErrLines; return n_out; }
+          Line& L = out[n_out];
+          L.a = lastA; L.b = lastB; L.invert = lastInvert; L.sx = sx; L.sy = sy; L.ex = ex; L.ey = ey;
+          L.segmentNo = seg_no; L.firstPixelIndex = first_pixel_index + skipped; L.len = idx - skipped + 1;
+        }
+        n_out++;
         len = idx + 1;
         break;
       }
     }
     no_pixels -= len; o += len; first_pixel_index += len;
   }
+  return n_out;
 }
 
 SDPL_ED_HD inline void update_line_parameters(Line& l) {               // EDLines.cpp:962-984
@@ -467,6 +481,21 @@ SDPL_ED_HD inline bool try_join(Line& l1, const Line& l2) {
   else if (l2.len > l1.len) { l1.firstPixelIndex = l2.firstPixelIndex; l1.len = l2.len; }
   update_line_parameters(l1);
   return true;
+}
+// the lines L[0, n) of ONE segment: JoinCollinearLines' inner loop (EDLines.cpp:375-396); returns how many remain, packed at L[0, ..)
+SDPL_ED_HD inline int join_segment(Line* L, int n) {
+  if (n <= 0) return 0;
+  int last = 0;
+  for (int j = 1; j < n; j++) {
+    if (!try_join(L[last], L[j])) {
+      last++;
+      if (last != j) L[last] = L[j];
+    }
+  }
+  if (last != 0) {
+    if (try_join(L[0], L[last])) last--;
+  }
+  return last + 1;
 }
 // EDLines::JoinCollinearLines (EDLines.cpp:362-400)
 SDPL_ED_HD inline void join_collinear(Work& W) {
@@ -611,39 +640,42 @@ SDPL_ED_HD inline bool validate_rect(Work& W, const Line& l, double prec) {
   }
   return nfa_ok(W, count, aligned);
 }
+// one line of ValidateLineSegments (EDLines.cpp:413-493)
+SDPL_ED_HD inline bool validate_one(Work& W, const Line& l) {
+  const double prec = (22.5 / 180) * kPi;
+  bool valid = false;
+  if (l.len >= 80) valid = true;
+  else if (l.len <= 25) valid = validate_rect(W, l, prec);
+  else {
+    const double line_angle = line_angle_of(l);
+    const int* pixels = W.seg_px + W.seg_off[l.segmentNo];      // the segment's pixel 0 (sic), x and y swapped (sic)
+    int aligned = 0, count = 0;
+    for (int j = 0; j < l.len; j++) {
+      const int r = px_x(pixels[j]), c = px_y(pixels[j]);
+      if (r <= 0 || r >= W.h - 1 || c <= 0 || c >= W.w - 1) continue;
+      count++;
+      if (pixel_aligned(W, r, c, line_angle, prec)) aligned++;
+    }
+    valid = nfa_ok(W, count, aligned);
+    if (!valid) valid = validate_rect(W, l, prec);
+  }
+  return valid;
+}
 // EDLines::ValidateLineSegments (EDLines.cpp:405-505)
 SDPL_ED_HD inline void validate_lines(Work& W) {
-  const double prec = (22.5 / 180) * kPi;
   int n_valid = 0;
   for (int i = 0; i < W.nlines; i++) {
-    const Line& l = W.lines[i];
-    bool valid = false;
-    if (l.len >= 80) valid = true;
-    else if (l.len <= 25) valid = validate_rect(W, l, prec);
-    else {
-      const double line_angle = line_angle_of(l);
-      const int* pixels = W.seg_px + W.seg_off[l.segmentNo];      // the segment's pixel 0 (sic), x and y swapped (sic)
-      int aligned = 0, count = 0;
-      for (int j = 0; j < l.len; j++) {
-        const int r = px_x(pixels[j]), c = px_y(pixels[j]);
-        if (r <= 0 || r >= W.h - 1 || c <= 0 || c >= W.w - 1) continue;
-        count++;
-        if (pixel_aligned(W, r, c, line_angle, prec)) aligned++;
-      }
-      valid = nfa_ok(W, count, aligned);
-      if (!valid) valid = validate_rect(W, l, prec);
-    }
+    const bool valid = validate_one(W, W.lines[i]);
     if (valid) { if (i != n_valid) W.lines[n_valid] = W.lines[i]; n_valid++; }
   }
   W.nlines = n_valid;
 }
-
 // everything after the anchors: the sequential part of one task
 SDPL_ED_HD inline void run_task(Work& W) {
   W.err = 0; W.nlines = 0; W.nseg = 0;
   link_anchors(W);
   if (W.err) return;
-  for (int s = 0; s < W.nseg && !W.err; s++) split_segment(W, s);
+  for (int s = 0; s < W.nseg && !W.err; s++) W.nlines += split_segment(W, s, W.lines + W.nlines, W.lines_cap - W.nlines);
   if (W.err) return;
   join_collinear(W);
   validate_lines(W);
@@ -715,14 +747,16 @@ inline bool nfa_table(int w, int h, int n_max, int* min_k) {
     if (found) lut = j;
     min_k[i] = lut > i ? i + 1 : lut;
   }
+  // direct branch: nfa(n, k) >= 0 is an up-set in k whose lower end does not fall as n grows, so the threshold is followed from n to
+  // n + 1 instead of scanning every k (a full scan of n_max^2 / 2 tail sums takes seconds); the two neighbours of the threshold are
+  // evaluated to confirm it
+  int k0 = 0;
   for (int n = lut_size > 0 ? lut_size : 0; n < n_max; n++) {
-    int first = n + 1;
-    for (int k = 0; k <= n; k++) {
-      const bool v = nfa(n, k, prob, logNT) >= 0.0;
-      if (v && first == n + 1) first = k;
-      if (!v && first != n + 1) ok = false;
-    }
-    min_k[n] = first;
+    while (k0 > 0 && nfa(n, k0 - 1, prob, logNT) >= 0.0) k0--;
+    while (k0 <= n && !(nfa(n, k0, prob, logNT) >= 0.0)) k0++;
+    min_k[n] = k0 <= n ? k0 : n + 1;
+    if (k0 < n && !(nfa(n, k0 + 1, prob, logNT) >= 0.0)) ok = false;
+    if (k0 > n) k0 = n + 1;
   }
   return ok;
 }

@@ -73,7 +73,7 @@ int ed_detect(const uint8_t* roi, int w, int h, int stride, std::vector<float>& 
   std::vector<double> lut(kAtanLut + 1);
   host::atan_table(lut.data());
   W.atan_lut = lut.data();
-  std::vector<int> min_k(2048);
+  std::vector<int> min_k(1024);
   if (!host::nfa_table(w, h, (int)min_k.size(), min_k.data())) return -2;
   W.nfa_min_k = min_k.data(); W.nfa_n = (int)min_k.size();
   W.min_line_len = host::min_line_len(w, h);

@@ -5,7 +5,8 @@
 //   k_ed_grad     Sobel-weighted |gx| + |gy| with threshold 36, vertical / horizontal direction map (ED.cpp:275-362)           [pixel-parallel]
 //   k_ed_anchor   anchors: gradient maxima by >= 8 across the edge direction (ED.cpp:364-398)                                  [pixel-parallel]
 //   k_ed_sort     anchors by descending gradient, row-major inside a value (ED.cpp:1000-1047 + the descending loop of :414)   [one warp per task]
-//   k_ed_serial   anchor linking, line fitting, joining, validation: include/sdpl_edlines_core.h                               [one thread per task]
+//   k_ed_link     anchor linking (include/sdpl_edlines_core.h)                                                                [one thread per task]
+//   k_ed_fit      line fitting, joining, validation (same header; lane per segment / per line)                                [one warp per task]
 // The linking is sequential per image by definition (a walk stops at the pixels earlier walks have drawn), like LSD's region growing;
 // this first version runs the whole sequential tail in one thread per task, so a batch is as fast as its slowest image, and all tasks
 // of the batch run side by side.  Results go into the Pending slots of the LSD path (accepted = 1), so key-line construction, the top-N
@@ -15,7 +16,7 @@
 
 namespace sdpl {
 
-constexpr int kEdNfaN = 2048;            // validation look-up table: pixel counts below this (a 2-px-wide rectangle around a line of < 80 pixels)
+constexpr int kEdNfaN = 1024;            // validation look-up table: pixel counts below this (a 2-px-wide rectangle around a line of < 80 pixels)
 
 struct EdOct {
   int w, h, npx;
@@ -28,7 +29,7 @@ struct EdDev {
   EdOct O[kMaxOct];
   unsigned long long img_frame, work_frame;
   uint8_t* img; uint8_t* work;
-  int* n_anchors;                        // per task
+  int* n_anchors; int* nseg;             // per task
   const double* atan_lut;                // [1025]
   const int* nfa_min_k;                  // [nl][kEdNfaN]
 };
@@ -172,13 +173,11 @@ __global__ void __launch_bounds__(32) k_ed_sort(LineDev D, EdDev E) {
   if (lane == 0) E.n_anchors[task] = total;
 }
 
-__global__ void __launch_bounds__(32) k_ed_serial(LineDev D, EdDev E) {
-  const int task = blockIdx.x * blockDim.x + threadIdx.x;
-  if (task >= D.nl * D.B) return;
+// one task per CTA, worked by its first lane: tasks must not share a warp (32 divergent tasks in a warp run one after the other)
+__device__ __forceinline__ void ed_work(const LineDev& D, const EdDev& E, int task, sdpl_ed::Work& W) {
   const int f = task / D.nl, o = task % D.nl;
   const EdOct& O = E.O[o];
   const EdPtrs P = ed_ptrs(E, f, o);
-  sdpl_ed::Work W;
   W.w = O.w; W.h = O.h; W.grad = P.grad; W.dir = P.dir; W.edge = P.edge;
   W.anchors = P.anchors; W.n_anchors = E.n_anchors[task];
   W.pixels = P.pixels; W.pixels_cap = O.pixels_cap;
@@ -193,17 +192,80 @@ __global__ void __launch_bounds__(32) k_ed_serial(LineDev D, EdDev E) {
   W.nfa_min_k = E.nfa_min_k + (size_t)o * kEdNfaN; W.nfa_n = kEdNfaN;
   W.min_line_len = O.min_line_len;
   W.err = 0;
-  sdpl_ed::run_task(W);
+}
+// anchor linking: the walks of one image are sequential by definition
+__global__ void __launch_bounds__(32) k_ed_link(LineDev D, EdDev E) {
+  const int task = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  sdpl_ed::Work W;
+  ed_work(D, E, task, W);
+  sdpl_ed::link_anchors(W);
+  E.nseg[task] = W.err ? -1 : W.nseg;
+  if (W.err) atomicOr(D.err, SDPL_ERR_OVERFLOW);
+}
+// line fitting, joining and validation of one task, by one warp: segments are independent of each other (fitting: lane per segment,
+// counted first, then written at the segment's offset, so the lines keep the reference's segment order; joining: lane per segment, in
+// place), and so are the lines in the validation (lane per line, ordered compaction into the Pending slots with ballots).  The arithmetic
+// is the shared header's, function by function.
+__global__ void __launch_bounds__(32) k_ed_fit(LineDev D, EdDev E) {
+  const uint32_t FULL = 0xffffffffu;
+  const int task = blockIdx.x, lane = threadIdx.x;
+  sdpl_ed::Work W;
+  ed_work(D, E, task, W);
+  const int nseg = E.nseg[task];
   lsd::Pending* pend = D.pend + (size_t)task * D.pend_cap;
-  int n = W.nlines;
-  if (W.err || n > D.pend_cap) { atomicOr(D.err, SDPL_ERR_OVERFLOW); n = 0; }
-  for (int i = 0; i < n; i++) {
-    pend[i].accepted = 1;
-    pend[i].seg[0] = (float)W.lines[i].sx; pend[i].seg[1] = (float)W.lines[i].sy;
-    pend[i].seg[2] = (float)W.lines[i].ex; pend[i].seg[3] = (float)W.lines[i].ey;
-    pend[i].tag = 0; pend[i].seed = 0; pend[i].npix = W.lines[i].len;
+  if (nseg < 0) { if (lane == 0) D.npend[task] = 0; return; }
+  const int o = task % D.nl;
+  const int seg_cap = E.O[o].seg_cap;
+  int* cnt = W.chain_nos;                  // [nseg]     lines per segment (after fitting, then after joining)
+  int* off = W.chain_nos + seg_cap;        // [nseg + 1] first line of a segment in W.lines
+  int* pre = W.chain_nos + 2 * seg_cap;    // [nseg + 1] prefix of the joined counts
+  // ---- fitting, pass 1: count ----
+  for (int s = lane; s < nseg; s += 32) cnt[s] = sdpl_ed::split_segment(W, s, nullptr, 0);
+  __syncwarp();
+  int total = 0;
+  if (lane == 0) { int run = 0; for (int s = 0; s < nseg; s++) { off[s] = run; run += cnt[s]; } off[nseg] = run; total = run; }
+  total = __shfl_sync(FULL, total, 0);
+  if (total > W.lines_cap) { if (lane == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); D.npend[task] = 0; } return; }
+  __syncwarp();
+  // ---- pass 2: write; then join the lines of each segment in place ----
+  for (int s = lane; s < nseg; s += 32) {
+    sdpl_ed::split_segment(W, s, W.lines + off[s], cnt[s]);
+    cnt[s] = sdpl_ed::join_segment(W.lines + off[s], cnt[s]);
   }
-  D.npend[task] = n;
+  __syncwarp();
+  int J = 0;
+  if (lane == 0) { int run = 0; for (int s = 0; s < nseg; s++) { pre[s] = run; run += cnt[s]; } pre[nseg] = run; J = run; }
+  J = __shfl_sync(FULL, J, 0);
+  __syncwarp();
+  // ---- validation: lane per line, in line order ----
+  int base = 0;
+  for (int t0 = 0; t0 < J; t0 += 32) {
+    const int t = t0 + lane;
+    bool valid = false;
+    const sdpl_ed::Line* l = nullptr;
+    if (t < J) {
+      int lo = 0, hi = nseg;               // the segment of line t: pre[lo] <= t < pre[lo + 1]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t) lo = mid; else hi = mid; }
+      l = W.lines + off[lo] + (t - pre[lo]);
+      valid = sdpl_ed::validate_one(W, *l);
+    }
+    const uint32_t m = __ballot_sync(FULL, valid);
+    if (valid) {
+      const int idx = base + __popc(m & ((1u << lane) - 1u));
+      if (idx < D.pend_cap) {
+        pend[idx].accepted = 1;
+        pend[idx].seg[0] = (float)l->sx; pend[idx].seg[1] = (float)l->sy; pend[idx].seg[2] = (float)l->ex; pend[idx].seg[3] = (float)l->ey;
+        pend[idx].tag = 0; pend[idx].seed = 0; pend[idx].npix = l->len;
+      }
+    }
+    base += __popc(m);
+  }
+  const bool bad = __any_sync(FULL, W.err != 0) || base > D.pend_cap;
+  if (lane == 0) {
+    if (bad) atomicOr(D.err, SDPL_ERR_OVERFLOW);
+    D.npend[task] = bad ? 0 : base;
+  }
 }
 
 }  // namespace sdpl

@@ -1111,9 +1111,9 @@ static int ed_setup(sdpl_line* o, int B) {
   int rc;
   if ((rc = o->ed_img.reserve(E.img_frame * B))) return rc;
   if ((rc = o->ed_work.reserve(E.work_frame * B))) return rc;
-  if ((rc = o->ed_nanch.reserve(sizeof(int) * nl * B))) return rc;
+  if ((rc = o->ed_nanch.reserve(sizeof(int) * 2 * nl * B))) return rc;
   if ((rc = o->ed_tab.reserve(sizeof(double) * (sdpl_ed::kAtanLut + 1) + sizeof(int) * (size_t)kEdNfaN * kMaxOct))) return rc;
-  E.img = o->ed_img.as<uint8_t>(); E.work = o->ed_work.as<uint8_t>(); E.n_anchors = o->ed_nanch.as<int>();
+  E.img = o->ed_img.as<uint8_t>(); E.work = o->ed_work.as<uint8_t>(); E.n_anchors = o->ed_nanch.as<int>(); E.nseg = E.n_anchors + (size_t)nl * B;
   E.atan_lut = o->ed_tab.as<double>();
   E.nfa_min_k = (const int*)(o->ed_tab.as<uint8_t>() + sizeof(double) * (sdpl_ed::kAtanLut + 1));
   if (o->ed_w != D.in_w || o->ed_h != D.in_h) {
@@ -1164,9 +1164,12 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     k_ed_sort<<<nl * B, 32, 0, st>>>(D, E);
     SDPL_LAUNCH_CHECK();
     o->timer.mark(st, "ed_sort");
-    k_ed_serial<<<div_up(nl * B, 32), 32, 0, st>>>(D, E);
+    k_ed_link<<<nl * B, 32, 0, st>>>(D, E);
     SDPL_LAUNCH_CHECK();
-    o->timer.mark(st, "ed_link_fit_validate");
+    o->timer.mark(st, "ed_link");
+    k_ed_fit<<<nl * B, 32, 0, st>>>(D, E);
+    SDPL_LAUNCH_CHECK();
+    o->timer.mark(st, "ed_fit_validate");
     k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());
     SDPL_LAUNCH_CHECK();
     o->timer.mark(st, "keylines");
