@@ -36,7 +36,7 @@ enum {
   SDPL_ERR_CUDA = 2,       /* CUDA runtime failure / no device (there is no CPU fallback) */
   SDPL_ERR_CAPACITY = 3,   /* caller-provided output capacity too small (n_out holds the needed count) */
   SDPL_ERR_OVERFLOW = 4,   /* an internal device buffer overflowed (reported, never silently truncated) */
-  SDPL_ERR_UNSUPPORTED = 5 /* configuration outside what the kernels implement (e.g. extractor==1 / EDLines) */
+  SDPL_ERR_UNSUPPORTED = 5 /* configuration outside what the kernels implement (e.g. lsd_scale other than 0.8, more than 4 octaves) */
 };
 const char* sdpl_strerror(int code);
 /* last CUDA / internal error text of the calling thread (empty string if none) */
@@ -89,7 +89,9 @@ int sdpl_orb_last_launches(const sdpl_orb* h);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct sdpl_line sdpl_line;
 /* Lineextractor(lsd_nfeatures, lsd_refine, lsd_scale, nlevels, scale, extractor), src/Lineextractor.cc:36-40.
- * extractor must be 0 (LSD); 1 (EDLines) returns SDPL_ERR_UNSUPPORTED. */
+ * extractor 0 = LSD (LSDDetectorC::detect, src/Lineextractor.cc:47-98), 1 = EDLines (LSDDetectorC::detect_ED, :100-135 ->
+ * LSDDetector_custom.cpp:372-461 -> 3rdparty/line_descriptor/src/ED_Lib/EDLines.cpp:8-70); anything else: SDPL_ERR_UNSUPPORTED.
+ * lsd_refine and lsd_scale are ignored by the EDLines back-end, as in the reference. */
 int sdpl_line_create(sdpl_line** h, int nfeatures, int refine, float lsd_scale, int nlevels, float scale, int extractor,
                      int device);
 void sdpl_line_destroy(sdpl_line* h);

@@ -4,7 +4,7 @@
  * The oracle is a single-threaded CPU restatement of the reference front-end
  * (argyrissm/SDPL-SLAM: src/ORBextractor.cc, src/Lineextractor.cc,
  * 3rdparty/line_descriptor/src/{LSDDetector_custom,binary_descriptor_custom}.cpp,
- * bitops_custom.hpp) with the OpenCV 3.4 primitives it calls restated from their
+ * bitops_custom.hpp, and for Lineextractor's EDLines back-end src/ED_Lib/{ED,EDLines,NFA}.cpp) with the OpenCV 3.4 primitives it calls restated from their
  * bit-exact integer/float formulas.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.
  *
