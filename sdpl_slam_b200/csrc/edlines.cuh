@@ -235,18 +235,19 @@ __global__ void __launch_bounds__(32) k_ed_fit(LineDev D, EdDev E) {
   int* cnt = W.chain_nos;                  // [nseg]     lines per segment (after fitting, then after joining)
   int* off = W.chain_nos + seg_cap;        // [nseg + 1] first line of a segment in W.lines
   int* pre = W.chain_nos + 2 * seg_cap;    // [nseg + 1] prefix of the joined counts
-  // ---- fitting, pass 1: count ----
-  for (int s = lane; s < nseg; s += 32) cnt[s] = sdpl_ed::split_segment(W, s, nullptr, 0);
+  // ---- fitting: every line uses up at least min_line_len pixels of its segment, so segment s can have at most len(s) / min_line_len
+  // lines and may write them at the prefix of those bounds -- one pass, no counting pass; then the lines of the segment are joined
+  // in place.  off[] keeps the (gappy) starts, cnt[] the numbers: the order of the lines is still (segment, position).
+  if (lane == 0) {
+    int run = 0;
+    for (int s = 0; s < nseg; s++) { off[s] = run; run += (W.seg_off[s + 1] - W.seg_off[s]) / W.min_line_len; }
+    off[nseg] = run;
+  }
   __syncwarp();
-  int total = 0;
-  if (lane == 0) { int run = 0; for (int s = 0; s < nseg; s++) { off[s] = run; run += cnt[s]; } off[nseg] = run; total = run; }
-  total = __shfl_sync(FULL, total, 0);
-  if (total > W.lines_cap) { if (lane == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); D.npend[task] = 0; } return; }
-  __syncwarp();
-  // ---- pass 2: write; then join the lines of each segment in place ----
+  if (off[nseg] > W.lines_cap) { if (lane == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); D.npend[task] = 0; } return; }
   for (int s = lane; s < nseg; s += 32) {
-    sdpl_ed::split_segment(W, s, W.lines + off[s], cnt[s]);
-    cnt[s] = sdpl_ed::join_segment(W.lines + off[s], cnt[s]);
+    const int n = sdpl_ed::split_segment(W, s, W.lines + off[s], off[s + 1] - off[s]);
+    cnt[s] = sdpl_ed::join_segment(W.lines + off[s], n);
   }
   __syncwarp();
   int J = 0;
