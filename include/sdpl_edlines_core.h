@@ -137,8 +137,13 @@ SDPL_ED_HD inline void link_anchors(Work& W) {
   if (W.seg_cap > 0) W.seg_off[0] = 0;
   for (int k = 0; k < W.n_anchors; k++) {
     const int off = W.anchors[k];
-    const int ai = off / w, aj = off % w;
+#ifdef __CUDA_ARCH__
+    // most anchors have been erased or drawn over by the time their turn comes: the byte that says so is a scattered read, asked for a
+    // few anchors ahead (a cache hint only; the value is read when the anchor's turn comes)
+    if (k + 8 < W.n_anchors) asm volatile("prefetch.global.L2 [%0];" :: "l"(edge + W.anchors[k + 8]));
+#endif
     if (edge[off] != kAnchor) continue;
+    const int ai = off / w, aj = off % w;
     ch[0].len = 0; ch[0].parent = -1; ch[0].dir = 0; ch[0].child0 = ch[0].child1 = -1; ch[0].pix = 0;
     int no_chains = 1, len = 0, dup = 0, top = -1;
     if (dirm[off] == kVertical) {
@@ -166,17 +171,18 @@ SDPL_ED_HD inline void link_anchors(Work& W) {
       const int want = horiz ? kHorizontal : kVertical;
       const bool to_child0 = dir == kLeft || dir == kUp;
       bool stopped = false;
-      int cur_dir = dirm[r * w + c];
+      // the walk in linear offsets: p = r * w + c, one step ahead = p + df, one pixel to either side = -+ dl (adds only: the walk is
+      // bound by the instruction count of its one thread on the device)
+      const int df = fr * w + fc, dl = lr * w + lc;
+      int p = r * w + c;
+      int cur_dir = dirm[p];
       while (cur_dir == want) {
-        // every value the step can need is loaded up front, independently of the decisions below (one memory round trip per step
-        // instead of a chain of them: the walk is latency-bound on a GPU thread)
-        const int br = r + fr, bc = c + fc;                               // straight ahead
-        const int oA = (br - lr) * w + bc - lc, oB = br * w + bc, oC = (br + lr) * w + bc + lc;
-        const int o1 = (r - lr) * w + (c - lc), o2 = (r + lr) * w + (c + lc);
+        // every value the step can need is loaded up front, independently of the decisions below (one memory round trip per step)
+        const int oB = p + df, oA = oB - dl, oC = oB + dl, o1 = p - dl, o2 = p + dl;
         const int eA = edge[oA], eB = edge[oB], eC = edge[oC], e1 = edge[o1], e2 = edge[o2];
         const int gA = grad[oA], gB = grad[oB], gC = grad[oC];
         const int dA = dirm[oA], dB = dirm[oB], dC = dirm[oC];
-        edge[r * w + c] = kEdge;
+        edge[p] = kEdge;
         // clean up the anchors beside the path
         if (e1 == kAnchor) edge[o1] = 0;
         if (e2 == kAnchor) edge[o2] = 0;
@@ -187,7 +193,8 @@ SDPL_ED_HD inline void link_anchors(Work& W) {
         else if (eF >= kAnchor) lat = first_lat;
         else if (eS >= kAnchor) lat = -first_lat;
         else { lat = 0; if (gA > gB) { lat = gA > gC ? -1 : 1; } else if (gC > gB) lat = 1; }
-        r = br + lat * lr; c = bc + lat * lc;
+        r += fr + lat * lr; c += fc + lat * lc;
+        p = lat == 0 ? oB : (lat < 0 ? oA : oC);
         const int eN = lat == 0 ? eB : (lat < 0 ? eA : eC), gN = lat == 0 ? gB : (lat < 0 ? gA : gC);
         cur_dir = lat == 0 ? dB : (lat < 0 ? dA : dC);
         if (eN == kEdge || gN < kGradThresh) {
