@@ -754,6 +754,8 @@ def run_gpu(args, stages, cfg):
         oc, lc = cfg["orb"], cfg["line"]
         front = fe.FrontEnd(oc["nfeatures"], oc["scale"], oc["nlevels"], oc["ini"], oc["mn"], lc["nfeatures"],
                             lc["refine"], lc["lsd_scale"], lc["nlevels"], lc["scale"], RATIO, MAX_DIST, device=local)
+        if lc["extractor"]:
+            front.set_line_extractor(lc["extractor"])
         himgs = pinned.numpy()[lead:]            # the F owned frames; frame 0 of a batch is matched against the previous batch's last
         e2e_steps = max(1, min(args.steps, 5))
         res = front.process(himgs)
@@ -893,9 +895,14 @@ def main():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-post", action="store_true", help="skip the Frame post-processing stage block (SURVEY 8f rows 1, 2)")
     ap.add_argument("--sweep", action="store_true", help="batch-size sweep {1, 8, 64, 512, 2048} through the host-buffer API (1 GPU)")
+    ap.add_argument("--extractor", type=int, default=0, choices=(0, 1),
+                    help="line back-end of Lineextractor: 0 = LSD (BASELINE.json's configuration), 1 = EDLines (SURVEY 8f row 3)")
     ap.add_argument("--verify", type=int, default=8, help="frames of the last end-to-end batch compared with the oracle (0 = off)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    if args.extractor and cfg.get("line"):
+        cfg = dict(cfg, line=dict(cfg["line"], extractor=args.extractor),
+                   workload=cfg["workload"] + " -- with the EDLines line back-end (extractor = 1) instead of LSD")
     stages = [s for s in args.stages.split(",") if s]
     if cfg["line"] is None:
         stages = [s for s in stages if s != "line"]

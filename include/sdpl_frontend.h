@@ -125,6 +125,8 @@ int sdpl_line_last_launches(const sdpl_line* h);
  * one CTA of several warps per (frame, octave) (default), 1 = strictly one seed at a time, 3 = single-warp waves of 32 seeds; all give
  * identical results; 2 is not a schedule any more (SDPL_ERR_ARG) */
 int sdpl_line_set_serial(sdpl_line* h, int on);
+/* Lineextractor::extractor (include/Lineextractor.h:60) of an existing object: 0 = LSD, 1 = EDLines; takes effect at the next call */
+int sdpl_line_set_extractor(sdpl_line* h, int extractor);
 
 /* ------------------------------------------------------------------------------------------------
  * Descriptor matcher -- 256-bit Hamming (cv::line_descriptor::match, bitops_custom.hpp:86-99) brute force;
@@ -205,6 +207,8 @@ void sdpl_frontend_destroy(sdpl_frontend* h);
 int sdpl_frontend_capacities(const sdpl_frontend* h, int* kp_capacity, int* kl_capacity);
 /* change kl_capacity (rows per frame of the key-line outputs); only while no batch is in flight */
 int sdpl_frontend_set_line_capacity(sdpl_frontend* h, int kl_capacity);
+/* the line back-end of the front-end's Lineextractor (0 = LSD, the default; 1 = EDLines); only while nothing is in flight */
+int sdpl_frontend_set_line_extractor(sdpl_frontend* h, int extractor);
 /* forget the previous frame (start of a new sequence) */
 int sdpl_frontend_reset(sdpl_frontend* h);
 /* imgs: HOST, n frames frame_stride bytes apart.  Outputs (HOST): frame f owns rows [f*cap, f*cap + count):

@@ -150,6 +150,12 @@ int sdpl_frontend_set_line_capacity(sdpl_frontend* f, int kl_capacity) {
   }
   return SDPL_OK;
 }
+int sdpl_frontend_set_line_extractor(sdpl_frontend* f, int extractor) {
+  if (!f || f->count > 0) { set_last_error("sdpl_frontend_set_line_extractor: bad argument or batches in flight"); return SDPL_ERR_ARG; }
+  const int rc = sdpl_line_set_extractor(f->line, extractor);
+  if (rc == SDPL_OK) f->have_prev = 0;
+  return rc;
+}
 int sdpl_frontend_last_launches(const sdpl_frontend* f) { return f ? f->launches : 0; }
 int sdpl_frontend_pending(const sdpl_frontend* f) { return f ? f->count : 0; }
 int sdpl_frontend_reset(sdpl_frontend* f) { if (!f) return SDPL_ERR_ARG; f->have_prev = 0; return SDPL_OK; }

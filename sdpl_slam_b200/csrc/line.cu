@@ -1438,6 +1438,12 @@ int sdpl_line_stage_times(sdpl_line* o, float* ms, const char** names, int* laun
 // 3 = single-warp waves of 32 seeds.  Bits 8-11 / 12-15: warps per task / CTAs per SM of mode 0; bits 3-7: CTAs per SM the second
 // NFA pass is compiled for; bits 24-30: phase-A expansion cap + 1.  All give identical results.  (Mode 2, a re-order-buffer schedule
 // of round 1, was measured 3x slower than the waves and has been removed.)
+int sdpl_line_set_extractor(sdpl_line* o, int extractor) {
+  if (!o || (extractor != 0 && extractor != 1)) { set_last_error("sdpl_line_set_extractor: extractor must be 0 (LSD) or 1 (EDLines)"); return SDPL_ERR_ARG; }
+  o->extractor = extractor;
+  return SDPL_OK;
+}
+
 int sdpl_line_set_serial(sdpl_line* o, int on) {
   if (!o || on < 0 || (on & 3) == 2) return SDPL_ERR_ARG;
   o->serial_mode = on & 3;

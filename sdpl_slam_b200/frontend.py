@@ -82,6 +82,7 @@ def load_library(path=None):
     L.sdpl_line_last_launches.argtypes = [vp]
     L.sdpl_line_set_stream.argtypes = [vp, vp]
     L.sdpl_line_set_serial.argtypes = [vp, i]
+    L.sdpl_line_set_extractor.argtypes = [vp, i]
     L.sdpl_line_debug_grow_profile.argtypes = [vp, i, i, vp]
     L.sdpl_line_debug_grow_detail.argtypes = [vp, i]
     L.sdpl_line_debug_pending.argtypes = [vp, i, i, vp, i, ip]
@@ -107,6 +108,7 @@ def load_library(path=None):
     L.sdpl_frontend_destroy.argtypes = [vp]; L.sdpl_frontend_destroy.restype = None
     L.sdpl_frontend_capacities.argtypes = [vp, ip, ip]
     L.sdpl_frontend_set_line_capacity.argtypes = [vp, i]
+    L.sdpl_frontend_set_line_extractor.argtypes = [vp, i]
     L.sdpl_frontend_reset.argtypes = [vp]
     L.sdpl_frontend_process.argtypes = [vp, vp, i, i, i, i, sz, vp, vp, vp, vp, vp, vp, vp]
     L.sdpl_frontend_last_launches.argtypes = [vp]
@@ -516,6 +518,10 @@ class FrontEnd:
         self._bufs = [None, None]
         self._flip = 0
         self._inflight = []
+
+    def set_line_extractor(self, extractor):
+        """0 = LSD (default), 1 = EDLines (Lineextractor's `extractor`, include/Lineextractor.h:60); only while nothing is in flight"""
+        _check(self._L.sdpl_frontend_set_line_extractor(self._h, int(extractor)))
 
     def set_line_capacity(self, kl_capacity):
         """rows per frame of the key-line outputs (default 2048 when lsd_nfeatures == 0); only while nothing is in flight"""
