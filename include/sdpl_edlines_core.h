@@ -56,12 +56,17 @@ struct Work {                      // one (frame, octave) task
   Line* lines; int lines_cap; int nlines;
   // validation
   const uint8_t* src; int src_stride;       // the level image the reference's ED object was given (ROI origin, real row stride)
+  unsigned long long src_magic;             // ceil(2^35 / (w + 38)) when w + 38 < 2^12, else 0 (src_flat)
   const double* atan_lut;          // atan(i / 1024), i = 0..1024
   const int* nfa_min_k; int nfa_n; // smallest k with NFALUT::checkValidationByNFA(n, k) for n < nfa_n (n + 1 = never)
   int min_line_len;
   int err;
 };
 
+SDPL_ED_HD inline unsigned long long src_magic_of(int w) {
+  const unsigned long long S = (unsigned long long)(w + 38);
+  return S < (1ull << 12) ? ((1ull << 35) + S - 1) / S : 0ull;
+}
 SDPL_ED_HD inline int px_pack(int x, int y) { return (y << 16) | x; }
 SDPL_ED_HD inline int px_x(int p) { return p & 0xffff; }
 SDPL_ED_HD inline int px_y(int p) { return (int)((unsigned)p >> 16); }
@@ -561,7 +566,10 @@ SDPL_ED_HD inline int reflect101(int v, int n) { if (v < 0) v = -v; if (v >= n) 
 SDPL_ED_HD inline int src_flat(const Work& W, int flat) {
   const int S = W.w + 38;
   const int P = 19 * S + 19 + flat;
-  const int y = reflect101(P / S - 19, W.h), x = reflect101(P % S - 19, W.w);
+  // P / S by multiplication: exact for P < 2^23 and S < 2^12 with a 35-bit reciprocal (sixteen of these per tested pixel)
+  int q;
+  if (W.src_magic && P < (1 << 23)) q = (int)(((unsigned long long)(unsigned)P * W.src_magic) >> 35); else q = P / S;
+  const int y = reflect101(q - 19, W.h), x = reflect101(P - q * S - 19, W.w);
   return (int)W.src[y * W.src_stride + x];
 }
 SDPL_ED_HD inline bool pixel_aligned(const Work& W, int r, int c, double line_angle, double prec) {

@@ -69,7 +69,7 @@ int ed_detect(const uint8_t* roi, int w, int h, int stride, std::vector<float>& 
   W.seg_px = seg_px.data(); W.seg_px_cap = (int)seg_px.size();
   W.seg_off = seg_off.data(); W.seg_cap = (int)seg_off.size();
   W.lines = lines.data(); W.lines_cap = (int)lines.size();
-  W.src = roi; W.src_stride = stride;
+  W.src = roi; W.src_stride = stride; W.src_magic = src_magic_of(w);
   std::vector<double> lut(kAtanLut + 1);
   host::atan_table(lut.data());
   W.atan_lut = lut.data();

@@ -137,33 +137,22 @@ __global__ void __launch_bounds__(256) k_ed_anchor(EdDev E, int o) {
   P.edge[i * w + j] = (uint8_t)e;
 }
 
-// one warp per task: counting sort of the anchors by gradient value (descending), row-major inside a value
+// one warp per task: counting sort of the anchors by gradient value (descending), row-major inside a value.  Pass 1 compacts the anchors
+// in pixel order (four pixels per lane and trip, warp scan of the counts) into the walk's pixel buffer, which is idle until the
+// linking, and counts the values; pass 2 places 32 listed anchors per trip: lanes with the same value are ranked with match_any, so
+// the position inside a value's run stays the row-major rank.
 __global__ void __launch_bounds__(32) k_ed_sort(LineDev D, EdDev E) {
   __shared__ int hist[2048];
+  const uint32_t FULL = 0xffffffffu;
   const int task = blockIdx.x, f = task / D.nl, o = task % D.nl, lane = threadIdx.x;
+  const uint32_t lt = (1u << lane) - 1u;
   const EdOct& O = E.O[o];
   const EdPtrs P = ed_ptrs(E, f, o);
+  int* list = P.pixels;
   for (int i = lane; i < 2048; i += 32) hist[i] = 0;
   __syncwarp();
-  for (int q0 = 0; q0 < O.npx; q0 += 128) {          // four consecutive pixels per lane: a quarter of the trips
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int q = q0 + 4 * lane + j;
-      if (q < O.npx && P.edge[q] == sdpl_ed::kAnchor) atomicAdd(&hist[min((int)P.grad[q], 2047)], 1);
-    }
-  }
-  __syncwarp();
-  // start of every value's run in descending order of the value: lane-strided exclusive scan (64 bins per lane), highest value first
-  int local = 0;
-  for (int b = 0; b < 64; b++) local += hist[2047 - (lane * 64 + b)];
-  int incl = local;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
-  int run = incl - local;
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  for (int b = 0; b < 64; b++) { const int idx = 2047 - (lane * 64 + b); const int c = hist[idx]; hist[idx] = run; run += c; }
-  __syncwarp();
-  if (total > O.anchors_cap) { if (lane == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); E.n_anchors[task] = 0; } return; }
+  int total = 0;
+  bool over = false;
   for (int q0 = 0; q0 < O.npx; q0 += 128) {
     uint32_t mine = 0;
 #pragma unroll
@@ -171,19 +160,44 @@ __global__ void __launch_bounds__(32) k_ed_sort(LineDev D, EdDev E) {
       const int q = q0 + 4 * lane + j;
       if (q < O.npx && P.edge[q] == sdpl_ed::kAnchor) mine |= 1u << j;
     }
-    uint32_t m = __ballot_sync(0xffffffffu, mine != 0);
-    while (m) {                                   // in pixel order (lane-major, then the lane's four pixels): the position inside a
-      const int L = __ffs(m) - 1;                 // value's run is the row-major rank
-      m &= m - 1;
-      if (lane == L) {
-        for (uint32_t b = mine; b; b &= b - 1) {
-          const int q = q0 + 4 * lane + (__ffs(b) - 1);
-          const int g = min((int)P.grad[q], 2047);
-          P.anchors[hist[g]] = q; hist[g]++;
-        }
-      }
-      __syncwarp();
+    const int c = __popc(mine);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+    const int chunk = __shfl_sync(FULL, incl, 31);
+    if (chunk == 0) continue;
+    if (total + chunk > O.anchors_cap || total + chunk > O.pixels_cap) { over = true; break; }
+    int pos = total + incl - c;
+    for (uint32_t b = mine; b; b &= b - 1) {
+      const int q = q0 + 4 * lane + (__ffs(b) - 1);
+      list[pos++] = q;
+      atomicAdd(&hist[min((int)P.grad[q], 2047)], 1);
     }
+    total += chunk;
+  }
+  if (over) { if (lane == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); E.n_anchors[task] = 0; } return; }
+  __syncwarp();
+  // start of every value's run in descending order of the value: lane-strided exclusive scan (64 values per lane), highest value first
+  int local = 0;
+  for (int b = 0; b < 64; b++) local += hist[2047 - (lane * 64 + b)];
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+  int run = incl - local;
+  for (int b = 0; b < 64; b++) { const int idx = 2047 - (lane * 64 + b); const int c = hist[idx]; hist[idx] = run; run += c; }
+  __syncwarp();
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    const bool have = i < total;
+    const int q = have ? list[i] : 0;
+    const int g = have ? min((int)P.grad[q], 2047) : -1 - lane;
+    const uint32_t grp = __match_any_sync(FULL, g);
+    int at = 0;
+    if (have) at = hist[g] + __popc(grp & lt);
+    __syncwarp();
+    if (have && (grp & lt) == 0) hist[g] += __popc(grp);      // the first lane of a value's group moves the run on
+    if (have) P.anchors[at] = q;
+    __syncwarp();
   }
   if (lane == 0) E.n_anchors[task] = total;
 }
@@ -203,6 +217,7 @@ __device__ __forceinline__ void ed_work(const LineDev& D, const EdDev& E, int ta
   W.seg_off = P.seg_off; W.seg_cap = O.seg_cap; W.nseg = 0;
   W.lines = P.lines; W.lines_cap = O.lines_cap; W.nlines = 0;
   ed_level(D, f, o, W.src, W.src_stride);
+  W.src_magic = sdpl_ed::src_magic_of(O.w);
   W.atan_lut = E.atan_lut;
   W.nfa_min_k = E.nfa_min_k + (size_t)o * kEdNfaN; W.nfa_n = kEdNfaN;
   W.min_line_len = O.min_line_len;
