@@ -233,66 +233,70 @@ __global__ void __launch_bounds__(32) k_ed_link(LineDev D, EdDev E) {
   E.nseg[task] = W.err ? -1 : W.nseg;
   if (W.err) atomicOr(D.err, SDPL_ERR_OVERFLOW);
 }
-// line fitting, joining and validation of one task, by one warp: segments are independent of each other (fitting: lane per segment,
-// counted first, then written at the segment's offset, so the lines keep the reference's segment order; joining: lane per segment, in
-// place), and so are the lines in the validation (lane per line, ordered compaction into the Pending slots with ballots).  The arithmetic
-// is the shared header's, function by function.
-__global__ void __launch_bounds__(32) k_ed_fit(LineDev D, EdDev E) {
+// line fitting, joining and validation of one task, by one CTA of kEdFitThreads threads: segments are independent of each other
+// (fitting + joining: thread per segment, the lines of segment s written at the prefix of the bounds len(s) / min_line_len -- every line
+// uses up at least min_line_len pixels -- so they keep the reference's (segment, position) order), and so are the lines in the
+// validation (thread per line, verdicts into a flag array, ordered compaction into the Pending slots by the first warp).  Threads of a
+// warp diverge in these loops (ncu: 4.8 of 32 threads per instruction), so the parallelism that counts is the number of warps.
+constexpr int kEdFitThreads = 256;
+__global__ void __launch_bounds__(kEdFitThreads) k_ed_fit(LineDev D, EdDev E) {
   const uint32_t FULL = 0xffffffffu;
-  const int task = blockIdx.x, lane = threadIdx.x;
+  const int task = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   sdpl_ed::Work W;
   ed_work(D, E, task, W);
   const int nseg = E.nseg[task];
   lsd::Pending* pend = D.pend + (size_t)task * D.pend_cap;
-  if (nseg < 0) { if (lane == 0) D.npend[task] = 0; return; }
+  if (nseg < 0) { if (tid == 0) D.npend[task] = 0; return; }
   const int o = task % D.nl;
   const int seg_cap = E.O[o].seg_cap;
-  int* cnt = W.chain_nos;                  // [nseg]     lines per segment (after fitting, then after joining)
-  int* off = W.chain_nos + seg_cap;        // [nseg + 1] first line of a segment in W.lines
-  int* pre = W.chain_nos + 2 * seg_cap;    // [nseg + 1] prefix of the joined counts
-  // ---- fitting: every line uses up at least min_line_len pixels of its segment, so segment s can have at most len(s) / min_line_len
-  // lines and may write them at the prefix of those bounds -- one pass, no counting pass; then the lines of the segment are joined
-  // in place.  off[] keeps the (gappy) starts, cnt[] the numbers: the order of the lines is still (segment, position).
-  if (lane == 0) {
+  int* cnt = W.chain_nos;                  // [nseg]     lines per segment after joining
+  int* off = W.chain_nos + seg_cap;        // [nseg + 1] first line slot of a segment in W.lines
+  int* pre = W.chain_nos + 2 * seg_cap;    // [nseg + 1] prefix of cnt
+  uint8_t* vflag = (uint8_t*)W.pixels;     // [J] verdicts (the walk's pixel buffer is idle here)
+  __shared__ int s_J, s_bad;
+  if (tid == 0) {
     int run = 0;
     for (int s = 0; s < nseg; s++) { off[s] = run; run += (W.seg_off[s + 1] - W.seg_off[s]) / W.min_line_len; }
     off[nseg] = run;
+    s_bad = run > W.lines_cap;
   }
-  __syncwarp();
-  if (off[nseg] > W.lines_cap) { if (lane == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); D.npend[task] = 0; } return; }
-  for (int s = lane; s < nseg; s += 32) {
+  __syncthreads();
+  if (s_bad) { if (tid == 0) { atomicOr(D.err, SDPL_ERR_OVERFLOW); D.npend[task] = 0; } return; }
+  for (int s = tid; s < nseg; s += kEdFitThreads) {
     const int n = sdpl_ed::split_segment(W, s, W.lines + off[s], off[s + 1] - off[s]);
     cnt[s] = sdpl_ed::join_segment(W.lines + off[s], n);
   }
-  __syncwarp();
-  int J = 0;
-  if (lane == 0) { int run = 0; for (int s = 0; s < nseg; s++) { pre[s] = run; run += cnt[s]; } pre[nseg] = run; J = run; }
-  J = __shfl_sync(FULL, J, 0);
-  __syncwarp();
-  // ---- validation: lane per line, in line order ----
+  __syncthreads();
+  if (tid == 0) { int run = 0; for (int s = 0; s < nseg; s++) { pre[s] = run; run += cnt[s]; } pre[nseg] = run; s_J = run; }
+  __syncthreads();
+  const int J = s_J;
+  for (int t = tid; t < J; t += kEdFitThreads) {
+    int lo = 0, hi = nseg;                 // the segment of line t: pre[lo] <= t < pre[lo + 1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t) lo = mid; else hi = mid; }
+    vflag[t] = sdpl_ed::validate_one(W, W.lines[off[lo] + (t - pre[lo])]) ? 1 : 0;
+  }
+  if (W.err) atomicOr(&s_bad, 1);
+  __syncthreads();
+  if (tid >= 32) return;
   int base = 0;
   for (int t0 = 0; t0 < J; t0 += 32) {
     const int t = t0 + lane;
-    bool valid = false;
-    const sdpl_ed::Line* l = nullptr;
-    if (t < J) {
-      int lo = 0, hi = nseg;               // the segment of line t: pre[lo] <= t < pre[lo + 1]
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t) lo = mid; else hi = mid; }
-      l = W.lines + off[lo] + (t - pre[lo]);
-      valid = sdpl_ed::validate_one(W, *l);
-    }
+    const bool valid = t < J && vflag[t];
     const uint32_t m = __ballot_sync(FULL, valid);
     if (valid) {
+      int lo = 0, hi = nseg;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pre[mid] <= t) lo = mid; else hi = mid; }
+      const sdpl_ed::Line& l = W.lines[off[lo] + (t - pre[lo])];
       const int idx = base + __popc(m & ((1u << lane) - 1u));
       if (idx < D.pend_cap) {
         pend[idx].accepted = 1;
-        pend[idx].seg[0] = (float)l->sx; pend[idx].seg[1] = (float)l->sy; pend[idx].seg[2] = (float)l->ex; pend[idx].seg[3] = (float)l->ey;
-        pend[idx].tag = 0; pend[idx].seed = 0; pend[idx].npix = l->len;
+        pend[idx].seg[0] = (float)l.sx; pend[idx].seg[1] = (float)l.sy; pend[idx].seg[2] = (float)l.ex; pend[idx].seg[3] = (float)l.ey;
+        pend[idx].tag = 0; pend[idx].seed = 0; pend[idx].npix = l.len;
       }
     }
     base += __popc(m);
   }
-  const bool bad = __any_sync(FULL, W.err != 0) || base > D.pend_cap;
+  const bool bad = s_bad != 0 || base > D.pend_cap;
   if (lane == 0) {
     if (bad) atomicOr(D.err, SDPL_ERR_OVERFLOW);
     D.npend[task] = bad ? 0 : base;

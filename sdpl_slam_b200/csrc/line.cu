@@ -1167,7 +1167,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
     k_ed_link<<<nl * B, 32, 0, st>>>(D, E);
     SDPL_LAUNCH_CHECK();
     o->timer.mark(st, "ed_link");
-    k_ed_fit<<<nl * B, 32, 0, st>>>(D, E);
+    k_ed_fit<<<nl * B, kEdFitThreads, 0, st>>>(D, E);
     SDPL_LAUNCH_CHECK();
     o->timer.mark(st, "ed_fit_validate");
     k_keylines<<<B, 256, 0, st>>>(D, d_kls, capacity, d_n_out, o->tmpkl.as<sdpl_keyline>());
