@@ -595,6 +595,10 @@ SDPL_ED_HD inline bool validate_rect(Work& W, const Line& l, double prec) {
   const double width = 2;
   double dx = x2 - x1, dy = y2 - y1;
   const double vlen = sqrt(dx * dx + dy * dy);
+  // A line whose two end points coincide (TryToJoinTwoLineSegments can produce one) has no rectangle: the reference divides by zero
+  // here, its enumeration never terminates and it writes past its point buffers (it crashes on frame 2822 of the synthetic sequence).
+  // Decision: such a line is not validated.
+  if (!(vlen > 0.0)) return false;
   dx = dx / vlen; dy = dy / vlen;
   double vxt[4], vyt[4], vx[4], vy[4];
   vxt[0] = x1 - dy * width / 2.0; vyt[0] = y1 + dx * width / 2.0;

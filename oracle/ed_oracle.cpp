@@ -8,6 +8,8 @@
 #include "oracle_internal.h"
 #include "../include/sdpl_edlines_core.h"
 #include <cstring>
+#include <map>
+#include <utility>
 #include <vector>
 
 namespace orc {
@@ -73,8 +75,14 @@ int ed_detect(const uint8_t* roi, int w, int h, int stride, std::vector<float>& 
   std::vector<double> lut(kAtanLut + 1);
   host::atan_table(lut.data());
   W.atan_lut = lut.data();
-  std::vector<int> min_k(1024);
-  if (!host::nfa_table(w, h, (int)min_k.size(), min_k.data())) return -2;
+  // validation thresholds for every pixel count a 2-pixel-wide rectangle inside the image can have (a joined line can be much longer
+  // than its pixel count says); cached per geometry
+  static std::map<std::pair<int, int>, std::vector<int>> cache;
+  std::vector<int>& min_k = cache[std::make_pair(w, h)];
+  if (min_k.empty()) {
+    min_k.resize(8192);
+    if (!host::nfa_table(w, h, (int)min_k.size(), min_k.data())) { min_k.clear(); return -2; }
+  }
   W.nfa_min_k = min_k.data(); W.nfa_n = (int)min_k.size();
   W.min_line_len = host::min_line_len(w, h);
   run_task(W);

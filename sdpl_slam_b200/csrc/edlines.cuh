@@ -16,7 +16,7 @@
 
 namespace sdpl {
 
-constexpr int kEdNfaN = 1024;            // validation look-up table: pixel counts below this (a 2-px-wide rectangle around a line of < 80 pixels)
+constexpr int kEdNfaN = 8192;            // validation look-up table: pixel counts below this (a 2-px-wide rectangle along a joined line: up to 3 x the image diagonal)
 
 struct EdOct {
   int w, h, npx;

@@ -1102,7 +1102,7 @@ static int ed_setup(sdpl_line* o, int B) {
     O.w = D.O[l].w; O.h = D.O[l].h; O.npx = O.w * O.h;
     if (O.w < 8 || O.h < 8 || O.w > 32767 || O.h > 32767) { set_last_error("EDLines: image size out of range"); return SDPL_ERR_UNSUPPORTED; }
     O.anchors_cap = O.npx / 4 + 1024; O.pixels_cap = O.npx / 4 + 1024; O.stack_cap = O.npx / 16 + 1024; O.chains_cap = O.npx / 16 + 1024;
-    O.chain_nos_cap = O.npx / 16 + 1024; O.seg_px_cap = O.npx / 2 + 1024; O.seg_cap = O.npx / 64 + 256; O.lines_cap = O.npx / 64 + 256;
+    O.chain_nos_cap = O.npx / 16 + 1024; O.seg_px_cap = O.npx / 2 + 1024; O.seg_cap = O.npx / 64 + 256; O.lines_cap = O.npx / 40 + 256;
     O.min_line_len = sdpl_ed::host::min_line_len(O.w, O.h);
     O.img_off = img_off; img_off += (ed_img_bytes(O.npx) + 255) & ~(size_t)255;
     O.work_off = work_off; work_off += (ed_work_bytes(O) + 255) & ~(size_t)255;

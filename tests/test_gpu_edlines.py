@@ -57,3 +57,13 @@ def test_edlines_flat_image_and_highres(frontend, oracle):
     kr, dr = oracle.LineOracle(0, 2, 0.8, 2, 2.0, 1)(img, cap=30000)
     _same(kg, dg, kr, dr)
     assert len(kg) > 100
+
+
+def test_edlines_degenerate_joined_line(frontend, oracle):
+    """Frame 2822 of the synthetic sequence: joining produces a line whose end points coincide on octave 1.  The reference divides by
+    zero in EnumerateRectPoints and crashes there (decision 10: the line is not validated); oracle and kernel agree."""
+    img = synth.sequence(2822, 2823, 375, 1242)[0]
+    kg, dg = frontend.Lineextractor(0, 2, 0.8, 2, 2.0, 1)(img)
+    kr, dr = oracle.LineOracle(0, 2, 0.8, 2, 2.0, 1)(img)
+    _same(kg, dg, kr, dr)
+    assert len(kg) == 293
