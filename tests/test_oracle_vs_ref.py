@@ -154,6 +154,28 @@ def test_edlines_extractor_equals_reference(ref, oracle, h, w, nf, nl, seeds):
     assert total > 0 or h < 100
 
 
+_ED_CRASH_SCRIPT = r"""
+import sys
+sys.path.insert(0, %r)
+from oracle import ref
+from sdpl_slam_b200 import synth
+img = synth.sequence(2822, 2823, 375, 1242)[0]
+k, d = ref.RefLineextractor(0, 2, 0.8, 2, 2.0, 1)(img)
+print("SURVIVED", len(k))
+"""
+
+
+def test_edlines_reference_crashes_on_a_zero_length_line(ref, oracle):
+    """Oracle decision 10: on frame 2822 of the synthetic sequence TryToJoinTwoLineSegments leaves a line whose end points
+    coincide (octave 1); EDLines::EnumerateRectPoints divides by its length, every comparison of its loop is then against NaN, the loop never
+    ends and writes past its two point buffers.  The compiled reference dies with a signal; the oracle rejects the line and goes on."""
+    out = subprocess.run([sys.executable, "-c", _ED_CRASH_SCRIPT % ROOT], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "SURVIVED" not in out.stdout
+    img = synth.sequence(2822, 2823, 375, 1242)[0]
+    k, d = oracle.LineOracle(0, 2, 0.8, 2, 2.0, 1)(img)
+    assert len(k) == 293 and (k["octave"] == 1).sum() == 94
+
+
 def test_lbd_equals_reference_on_given_keylines(ref, oracle):
     """BinaryDescriptor::compute -> computeImpl -> computeLBD -> binaryConversion on the oracle's keylines, incl. lines
     that touch the image border (clamped samples) and a one-octave set."""
