@@ -64,6 +64,7 @@ struct LineDev {
   const double* nfa_tab;               // [nl][kNfaTabLevels][kNfaTabTri] (lsd::nfa_lookup), filled by k_nfa_table at set-up
   int* nbig; int* bigidx;
   double rho, prec, p, density_th, log_eps, scale;
+  int g2_min;                          // smallest 4 * |gradient|^2 whose norm sqrt(g2 / 4.0) exceeds rho (host-computed, exact)
   int refine, serial_mode;
   double min_length;
   int nfeatures;
@@ -264,8 +265,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
       const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
       const int gx = DA + BC, gy = DA - BC;
       g2 = gx * gx + gy * gy;
-      const double norm = sqrt((double)g2 / 4.0);
-      if (norm > D.rho) {
+      if (g2 >= D.g2_min) {           // norm = sqrt(g2 / 4.0) > rho: sqrt is monotonic, the integer bound is found on the host
         a.deg = fast_atan2_deg((float)gx, (float)-gy);
         ang = (double)a.deg * lsd::kDegToRad;
         const double af = (double)(float)ang;
@@ -929,6 +929,11 @@ static int line_setup(sdpl_line* o, int w, int h, int B) {
   // LSD constants, Lineextractor.cc:54-70
   const double ang_th = 22.5, quant = 2.0;
   D.prec = lsd::kPI * ang_th / 180; D.p = ang_th / 180; D.rho = quant / sin(D.prec);
+  {
+    int g = std::max(0, (int)(4.0 * D.rho * D.rho) - 4);
+    while (!(sqrt((double)g / 4.0) > D.rho)) g++;
+    D.g2_min = g;
+  }
   D.density_th = 0.8; D.log_eps = 0.0; D.scale = (double)o->lsd_scale; D.refine = o->refine; D.serial_mode = o->serial_mode;
   D.min_length = 0.02 * (double)std::min(w, h);
   D.nfeatures = o->nfeatures;

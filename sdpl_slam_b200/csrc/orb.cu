@@ -205,11 +205,60 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
   // ring offsets (dx, dy), k = 0..15 (cv::FAST order)
   constexpr int RX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
   constexpr int RY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+  // Pass 1 -- quick reject (cv::FAST's own pre-test, generalised): every arc of 9 ring pixels holds two NEIGHBOURING compass
+  // points (k = 0, 4, 8, 12), so a pair of pixels neither of which has two neighbouring compass points brighter than
+  // centre + minThFAST, nor two darker than centre - minThFAST, scores below minThFAST: zeros are stored at once.  The
+  // surviving pairs (about a third on densely textured frames, far fewer on smooth ones) are compacted into a shared list
+  // and pass 2 runs the full 16-arc evaluation on the list with all lanes busy.
+  __shared__ unsigned short surv[(kFT_W / 2) * kFT_H];
+  __shared__ int n_surv;
+  if (threadIdx.x == 0) n_surv = 0;
+  __syncthreads();
+  {
+    const unsigned t2 = (unsigned)tmin * 0x00010001u, nt2 = __vneg2(t2);
 #pragma unroll 1
-  for (int i = threadIdx.x; i < (kFT_W / 2) * kFT_H; i += 256) {
+    for (int i = threadIdx.x; i < (kFT_W / 2) * kFT_H; i += 256) {
+      const int yy = i / (kFT_W / 2), xx = (i % (kFT_W / 2)) * 2;
+      const int gx = x0 + xx, gy = y0 + yy;
+      bool keep = false;
+      if (gx < xe && gy < ye) {
+        const int base = (yy + 3) * S + xx + 3 + kShift;
+        const unsigned c2 = expand2(*(const unsigned short*)(tileA + base));
+        unsigned b[4], k[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int off = base + RY[4 * j] * S + RX[4 * j];
+          const unsigned short v = (RX[4 * j] & 1) ? *(const unsigned short*)(tileB + off - 1) : *(const unsigned short*)(tileA + off);
+          const unsigned dj = __vsub2(expand2(v), c2);
+          b[j] = __vcmpgts2(dj, t2);       // 0xffff per lane where ring > centre + minTh
+          k[j] = __vcmplts2(dj, nt2);      //                       ring < centre - minTh
+        }
+        const unsigned any = (b[0] & b[1]) | (b[1] & b[2]) | (b[2] & b[3]) | (b[3] & b[0]) |
+                             (k[0] & k[1]) | (k[1] & k[2]) | (k[2] & k[3]) | (k[3] & k[0]);
+        keep = any != 0u;
+        if (!keep) {
+          uint8_t* o = sc + (size_t)gy * L.sstride + gx;
+          o[0] = 0;
+          if (gx + 1 < xe) o[1] = 0;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        const int lane = threadIdx.x & 31;
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&n_surv, __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (keep) surv[at + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+      }
+    }
+  }
+  __syncthreads();
+  const int ns = n_surv;
+#pragma unroll 1
+  for (int j = threadIdx.x; j < ns; j += 256) {
+    const int i = surv[j];
     const int yy = i / (kFT_W / 2), xx = (i % (kFT_W / 2)) * 2;   // even column inside the tile
     const int gx = x0 + xx, gy = y0 + yy;
-    if (gx >= xe || gy >= ye) continue;
     const int base = (yy + 3) * S + xx + 3 + kShift;               // even byte offset of the centre pair (tile column xx + 3)
     const unsigned c2 = expand2(*(const unsigned short*)(tileA + base));
     unsigned d[16];
