@@ -211,49 +211,59 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
   // surviving pairs (about a third on densely textured frames, far fewer on smooth ones) are compacted into a shared list
   // and pass 2 runs the full 16-arc evaluation on the list with all lanes busy.
   __shared__ unsigned short surv[(kFT_W / 2) * kFT_H];
-  __shared__ int n_surv;
-  if (threadIdx.x == 0) n_surv = 0;
-  __syncthreads();
+  __shared__ int warp_surv[8];
+  int ns;
   {
-    const unsigned t2 = (unsigned)tmin * 0x00010001u, nt2 = __vneg2(t2);
+    // thread -> fixed pair column, rows tid/32 + 8 it: offsets advance by constants, no division in the loop
+    const int lane = threadIdx.x & 31, xx = 2 * lane, gx = x0 + xx;
+    int yy = threadIdx.x >> 5;
+    int base = (yy + 3) * S + xx + 3 + kShift;
+    uint8_t* o = sc + (size_t)(y0 + yy) * L.sstride + gx;
+    const size_t ostep = (size_t)8 * L.sstride;
+    unsigned kept = 0;                                             // bit it: the pair of row tid / 32 + 8 it survives
 #pragma unroll 1
-    for (int i = threadIdx.x; i < (kFT_W / 2) * kFT_H; i += 256) {
-      const int yy = i / (kFT_W / 2), xx = (i % (kFT_W / 2)) * 2;
-      const int gx = x0 + xx, gy = y0 + yy;
+    for (int it = 0; it < kFT_H / 8; it++, yy += 8, base += 8 * S, o += ostep) {
       bool keep = false;
-      if (gx < xe && gy < ye) {
-        const int base = (yy + 3) * S + xx + 3 + kShift;
+      if (gx < xe && y0 + yy < ye) {
         const unsigned c2 = expand2(*(const unsigned short*)(tileA + base));
-        unsigned b[4], k[4];
+        unsigned d[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int off = base + RY[4 * j] * S + RX[4 * j];
           const unsigned short v = (RX[4 * j] & 1) ? *(const unsigned short*)(tileB + off - 1) : *(const unsigned short*)(tileA + off);
-          const unsigned dj = __vsub2(expand2(v), c2);
-          b[j] = __vcmpgts2(dj, t2);       // 0xffff per lane where ring > centre + minTh
-          k[j] = __vcmplts2(dj, nt2);      //                       ring < centre - minTh
+          d[j] = __vsub2(expand2(v), c2);
         }
-        const unsigned any = (b[0] & b[1]) | (b[1] & b[2]) | (b[2] & b[3]) | (b[3] & b[0]) |
-                             (k[0] & k[1]) | (k[1] & k[2]) | (k[2] & k[3]) | (k[3] & k[0]);
-        keep = any != 0u;
+        // upper bound of score + 1 from the four compass points: max over neighbouring pairs of their minimum (bright side),
+        // minus the min over neighbouring pairs of their maximum (dark side)
+        const unsigned br = __vimax3_s16x2(__vmins2(d[0], d[1]), __vmins2(d[1], d[2]), __vmaxs2(__vmins2(d[2], d[3]), __vmins2(d[3], d[0])));
+        const unsigned dk = __vimin3_s16x2(__vmaxs2(d[0], d[1]), __vmaxs2(d[1], d[2]), __vmins2(__vmaxs2(d[2], d[3]), __vmaxs2(d[3], d[0])));
+        const unsigned q = __vmaxs2(br, __vsub2(0u, dk));
+        keep = (int)(short)(q & 0xffffu) > tmin || (int)(short)(q >> 16) > tmin;
         if (!keep) {
-          uint8_t* o = sc + (size_t)gy * L.sstride + gx;
           o[0] = 0;
           if (gx + 1 < xe) o[1] = 0;
         }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      if (m) {
-        const int lane = threadIdx.x & 31;
-        int at = 0;
-        if (lane == 0) at = atomicAdd(&n_surv, __popc(m));
-        at = __shfl_sync(0xffffffffu, at, 0);
-        if (keep) surv[at + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
-      }
+      kept |= (unsigned)keep << it;
+    }
+    // ordered-by-warp compaction without atomics: per-warp counts, one barrier, every warp sums the counts before it
+    unsigned m[kFT_H / 8];
+    int cnt = 0;
+#pragma unroll
+    for (int it = 0; it < kFT_H / 8; it++) { m[it] = __ballot_sync(0xffffffffu, (kept >> it) & 1u); cnt += __popc(m[it]); }
+    if (lane == 0) warp_surv[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    int at = 0; ns = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const int c = warp_surv[w]; if (w < (int)(threadIdx.x >> 5)) at += c; ns += c; }
+    const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < kFT_H / 8; it++) {
+      if ((kept >> it) & 1u) surv[at + __popc(m[it] & below)] = (unsigned short)(((threadIdx.x >> 5) + 8 * it) * (kFT_W / 2) + lane);
+      at += __popc(m[it]);
     }
   }
   __syncthreads();
-  const int ns = n_surv;
 #pragma unroll 1
   for (int j = threadIdx.x; j < ns; j += 256) {
     const int i = surv[j];
