@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) k_pyr_base(const uint8_t* __restrict__ in
 // level l from level l-1: cv::resize INTER_LINEAR (Q11 fixed point) + reflect-101 border in one pass.  A thread owns four
 // output columns (one aligned word) and kPyrRows consecutive rows: the column part of the bilinear set-up (reflected
 // column, source offset, Q11 weights from the tables) is done once and reused down the rows.
-constexpr int kPyrRows = 4;
+constexpr int kPyrRows = 8;
 __global__ void __launch_bounds__(128) k_pyr_resize(OrbDev D, int l) {
   const LvlDev& Ld = D.L[l];
   const LvlDev& Ls = D.L[l - 1];
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(128) k_pyr_resize(OrbDev D, int l) {
     if (Ld.area_fast) { sx0[k] = 2 * ix; sx1[k] = 2 * ix + 1; aa[k] = make_short2(0, 0); }
     else { sx0[k] = Ld.xofs[ix]; sx1[k] = min(sx0[k] + 1, Ls.w - 1); aa[k] = Ld.xa[ix]; }
   }
+  int h0[4], h1[4] = {0, 0, 0, 0}, prev_sy1 = -1;
 #pragma unroll 1
   for (int r = 0; r < kPyrRows; r++) {
     const int y = y_first + r;
@@ -113,17 +114,24 @@ __global__ void __launch_bounds__(128) k_pyr_resize(OrbDev D, int l) {
       const int sy = (short)Ld.yofs[iy];
       const short2 bb = Ld.ya[iy];
       const int sy0 = min(max(sy, 0), Ls.h - 1), sy1 = min(max(sy + 1, 0), Ls.h - 1);
-      const uint8_t* s0 = src + (size_t)sy0 * Ls.pstride;
+      // the rows of a block are uniform across its threads: when this output row's upper source row is the previous output
+      // row's lower one (4 rows of 5 at scale 1.2) its horizontal pass is already in registers
+      if (sy0 == prev_sy1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) h0[k] = h1[k];
+      } else {
+        const uint8_t* s0 = src + (size_t)sy0 * Ls.pstride;
+#pragma unroll
+        for (int k = 0; k < 4; k++) h0[k] = s0[sx0[k]] * aa[k].x + s0[sx1[k]] * aa[k].y;
+      }
       const uint8_t* s1 = src + (size_t)sy1 * Ls.pstride;
 #pragma unroll
+      for (int k = 0; k < 4; k++) h1[k] = s1[sx0[k]] * aa[k].x + s1[sx1[k]] * aa[k].y;
+      prev_sy1 = sy1;
+#pragma unroll
       for (int k = 0; k < 4; k++) {
-        uint32_t b = 0;
-        if (in[k]) {
-          const int r0 = s0[sx0[k]] * aa[k].x + s0[sx1[k]] * aa[k].y;
-          const int r1 = s1[sx0[k]] * aa[k].x + s1[sx1[k]] * aa[k].y;
-          const int o = (((bb.x * (r0 >> 4)) >> 16) + ((bb.y * (r1 >> 4)) >> 16) + 2) >> 2;
-          b = (uint32_t)min(max(o, 0), 255);
-        }
+        const int o = (((bb.x * (h0[k] >> 4)) >> 16) + ((bb.y * (h1[k] >> 4)) >> 16) + 2) >> 2;
+        const uint32_t b = in[k] ? (uint32_t)min(max(o, 0), 255) : 0u;
         v |= b << (8 * k);
       }
     }
