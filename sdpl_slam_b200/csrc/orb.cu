@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
 //     Two launches: k_cell_nms evaluates the maxima once and keeps them as bit masks (32 pixels per word, one word for
 //     "local maximum", one for "local maximum with score >= iniThFAST"); k_cell_emit turns the masks of the threshold the
 //     cell ended up with into the ordered candidate list.
+constexpr int kNmsRows = 8;   // rows of a cell loaded ahead of the window (the loop is bound by the latency of these loads)
 __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int c = blockIdx.x * 8 + warp;
@@ -338,6 +339,50 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
   const int ss = L.sstride;
   int cnt_hi = 0, cnt_lo = 0;
   uint2* masks = D.cellmask + ((size_t)f * D.cells_per_frame + c) * D.mask_words;
+  if (iw <= 32) {
+    // lane == column of the cell interior: a row is one coalesced byte load, the horizontal neighbours come through two
+    // shuffles, the rows above and below from the sliding window (hm = max of left / right, h3 = max of all three), and the
+    // row's ballot is appended to the linear bit stream (pixel index = row * iw + column, 32 pixels per mask word) --
+    // about 25 instructions per row of up to 32 pixels, against 65 per 32 pixels for the pixel-per-lane loop below.
+    // Columns >= iw and rows outside the interior read as 0, as neighbours outside the interior do there.
+    const bool incol = lane < iw;
+    const uint8_t* col = sc + lane;
+    const int ini = D.ini_th;
+    auto horiz = [&](int v, int& hm, int& h3) {
+      int l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
+      if (lane == 0) l = 0;
+      if (lane == 31) r = 0;
+      hm = max(l, r); h3 = max(hm, v);
+    };
+    int v = incol ? (int)col[0] : 0, hm, h3, up3 = 0;
+    horiz(v, hm, h3);
+    unsigned long long lo_buf = 0, hi_buf = 0;
+    int pos = 0, widx = 0;
+    for (int y0 = 0; y0 < ih; y0 += kNmsRows) {
+      int nv[kNmsRows];
+#pragma unroll
+      for (int u = 0; u < kNmsRows; u++) nv[u] = (incol && y0 + 1 + u < ih) ? (int)col[(size_t)(y0 + 1 + u) * ss] : 0;
+#pragma unroll
+      for (int u = 0; u < kNmsRows; u++) {
+        if (y0 + u >= ih) break;
+        int nhm, nh3;
+        horiz(nv[u], nhm, nh3);
+        const bool ismax = v > max(hm, max(up3, nh3));
+        const uint32_t m_lo = __ballot_sync(0xffffffffu, ismax), m_hi = __ballot_sync(0xffffffffu, ismax && v >= ini);
+        cnt_lo += __popc(m_lo);
+        cnt_hi += __popc(m_hi);
+        lo_buf |= (unsigned long long)m_lo << pos;
+        hi_buf |= (unsigned long long)m_hi << pos;
+        pos += iw;
+        if (pos >= 32) {
+          if (lane == 0) masks[widx] = make_uint2((uint32_t)lo_buf, (uint32_t)hi_buf);
+          widx++; lo_buf >>= 32; hi_buf >>= 32; pos -= 32;
+        }
+        up3 = h3; v = nv[u]; hm = nhm; h3 = nh3;
+      }
+    }
+    if (pos > 0 && lane == 0) masks[widx] = make_uint2((uint32_t)lo_buf, (uint32_t)hi_buf);
+  } else {
   const int npx = iw * ih;
   int yy = lane / iw, xx = lane - yy * iw;
   for (int i0 = 0; i0 < npx; i0 += 32) {
@@ -370,6 +415,7 @@ __global__ void __launch_bounds__(256) k_cell_nms(OrbDev D) {
     if (lane == 0) masks[i0 >> 5] = make_uint2(m_lo, m_hi);
     xx += 32;
     while (xx >= iw) { xx -= iw; yy++; }
+  }
   }
   if (lane == 0) {
     int t = cnt_hi > 0 ? D.ini_th : D.min_th;
