@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) k_fast_score(OrbDev D, int total_tiles) {
     uint8_t* o = sc + (size_t)(y0 + yy) * L.sstride + gx;
     const size_t ostep = (size_t)8 * L.sstride;
     unsigned kept = 0;                                             // bit it: the pair of row tid / 32 + 8 it survives
-#pragma unroll 1
+#pragma unroll
     for (int it = 0; it < kFT_H / 8; it++, yy += 8, base += 8 * S, o += ostep) {
       bool keep = false;
       if (gx < xe && y0 + yy < ye) {
