@@ -249,10 +249,17 @@ __global__ void __launch_bounds__(256) k_lsd_scale(LineDev D, int o) {
 // ------------------------------------------------------------------------------------------------
 // L3: ll_angle: 2x2 gradient, level-line angle, per-pixel cos/sin, gradient-magnitude maximum.
 // ------------------------------------------------------------------------------------------------
+constexpr int kGradTiles = 4;
 __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
   const OctDev& O = D.O[o];
   const int f = blockIdx.z;
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+  int m = 0;
+  // kGradTiles 64 x 4 tiles per block, one below the other: a block of one tile lives a few thousand cycles, and its launch, the
+  // block maximum, the barrier and the atomic were a visible share of that
+#pragma unroll 1
+  for (int t = 0; t < kGradTiles; t++) {
+  const int y = (blockIdx.y * kGradTiles + t) * 4 + (threadIdx.x >> 6);
   int g2 = 0;
   if (x < O.sw && y < O.sh) {
     const uint8_t* img = D.scaled + (size_t)f * D.sc_frame + O.sc_off;
@@ -281,8 +288,9 @@ __global__ void __launch_bounds__(256) k_lsd_grad(LineDev D, int o) {
     D.ang[q] = ang;
     D.g2[q] = g2;
   }
+  m = max(m, g2);
+  }
   // block maximum of the defined gradient magnitudes
-  int m = g2;
 #pragma unroll
   for (int s = 16; s; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
   __shared__ int wm[8];
@@ -1188,7 +1196,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   }
   o->timer.mark(st, "lsd_scale");
   for (int l = 0; l < nl; l++) {
-    k_lsd_grad<<<dim3(div_up(D.O[l].sw, 64), div_up(D.O[l].sh, 4), B), 256, 0, st>>>(D, l);
+    k_lsd_grad<<<dim3(div_up(D.O[l].sw, 64), div_up(D.O[l].sh, 4 * kGradTiles), B), 256, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "lsd_gradient");
