@@ -54,20 +54,27 @@ struct OrbDev {
 // ------------------------------------------------------------------------------------------------
 // K1: pyramid.  ComputePyramid, src/ORBextractor.cc:1112-1137.
 // ------------------------------------------------------------------------------------------------
+constexpr int kBaseRows = 8;
 __global__ void __launch_bounds__(128) k_pyr_base(const uint8_t* __restrict__ in, int in_stride, size_t in_frame,
                                                    uint8_t* __restrict__ out, int w, int h, int pstride, size_t out_frame) {
   int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  int y = blockIdx.y;
   if (x4 >= pstride) return;
-  const uint8_t* src = in + (size_t)blockIdx.z * in_frame + (size_t)reflect101(y - kBorder, h) * in_stride;
-  uint32_t v = 0;
+  // kBaseRows rows per thread: the reflected source columns are computed once (and a one-row block was too short-lived)
+  int sx[4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    int x = x4 + k;
-    uint32_t b = x < w + 2 * kBorder ? src[reflect101(x - kBorder, w)] : 0;
-    v |= b << (8 * k);
+  for (int k = 0; k < 4; k++) sx[k] = x4 + k < w + 2 * kBorder ? reflect101(x4 + k - kBorder, w) : -1;
+  const int rows = h + 2 * kBorder;
+#pragma unroll 1
+  for (int y = blockIdx.y * kBaseRows; y < min(rows, (int)(blockIdx.y + 1) * kBaseRows); y++) {
+    const uint8_t* src = in + (size_t)blockIdx.z * in_frame + (size_t)reflect101(y - kBorder, h) * in_stride;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t b = sx[k] >= 0 ? src[sx[k]] : 0;
+      v |= b << (8 * k);
+    }
+    *(uint32_t*)(out + (size_t)blockIdx.z * out_frame + (size_t)y * pstride + x4) = v;
   }
-  *(uint32_t*)(out + (size_t)blockIdx.z * out_frame + (size_t)y * pstride + x4) = v;
 }
 
 // level l from level l-1: cv::resize INTER_LINEAR (Q11 fixed point) + reflect-101 border in one pass.  A thread owns four
@@ -1108,7 +1115,7 @@ static int orb_run_dev(sdpl_orb* o, const uint8_t* d_imgs, int B, int w, int h, 
   o->timer.begin(st);
   {
     const LvlDev& L = D.L[0];
-    dim3 g(div_up(L.pstride / 4, 128), L.h + 2 * kBorder, B);
+    dim3 g(div_up(L.pstride / 4, 128), div_up(L.h + 2 * kBorder, kBaseRows), B);
     k_pyr_base<<<g, 128, 0, st>>>(d_imgs, stride, frame_stride, D.pyr + L.pyr_off, L.w, L.h, L.pstride, D.pyr_frame);
     SDPL_LAUNCH_CHECK();
   }
