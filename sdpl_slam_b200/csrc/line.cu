@@ -141,15 +141,19 @@ __device__ __forceinline__ uint32_t vt5_word(const uint2 (*s_hz)[NWORDS], int gr
 //     The 19-px reflect-101 border of the reference buffers is never read by LSD beyond what reflect-101 of the
 //     interior gives (the LSD blur needs 3 px), so the octaves are stored un-padded.
 // ------------------------------------------------------------------------------------------------
+constexpr int kResizeRows = 8;
 __global__ void __launch_bounds__(128) k_line_resize(LineDev D, int o) {
   const OctDev& Od = D.O[o];
   const OctDev& Os = D.O[o - 1];
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= Od.w) return;
   const uint8_t* src; int sstride;
   if (o == 1) { src = D.in + (size_t)blockIdx.z * D.in_frame; sstride = D.in_stride; }
   else { src = D.lvl + (size_t)blockIdx.z * D.lvl_frame + Os.lvl_off; sstride = Os.w; }
   uint8_t* dst = D.lvl + (size_t)blockIdx.z * D.lvl_frame + Od.lvl_off;
+  // kResizeRows rows per thread (a one-row block is too short-lived to pay for its launch)
+#pragma unroll 1
+  for (int y = blockIdx.y * kResizeRows; y < min(Od.h, (int)(blockIdx.y + 1) * kResizeRows); y++) {
   int v;
   if (Od.area_fast) {
     const uint8_t* s0 = src + (size_t)(2 * y) * sstride;
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(128) k_line_resize(LineDev D, int o) {
     v = min(max(v, 0), 255);
   }
   dst[(size_t)y * Od.w + x] = (uint8_t)v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,16 +713,22 @@ __global__ void __launch_bounds__(256) k_lbd_blur_sobel(LineDev D) {
   }
 }
 
+constexpr int kLbdTiles = 4;
 __global__ void __launch_bounds__(256) k_lbd_pyrdown(LineDev D, int o) {
   const OctDev& Od = D.O[o];
   const OctDev& Os = D.O[o - 1];
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6), f = blockIdx.z;
-  if (x >= Od.lw || y >= Od.lh) return;
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), f = blockIdx.z;
+  if (x >= Od.lw) return;
   const uint8_t* src = D.g + (size_t)f * D.g_frame + Os.g_off;
   const int sw = Os.lw, sh = Os.lh, sp = Os.gstride;
   int cx[5];
 #pragma unroll
   for (int k = 0; k < 5; k++) cx[k] = reflect101(2 * x + k - 2, sw);
+  // kLbdTiles 64 x 4 tiles per block (one-tile blocks are too short-lived, see k_lsd_grad)
+#pragma unroll 1
+  for (int t = 0; t < kLbdTiles; t++) {
+  const int y = (blockIdx.y * kLbdTiles + t) * 4 + (threadIdx.x >> 6);
+  if (y >= Od.lh) break;
   int rows[5];
 #pragma unroll
   for (int k = 0; k < 5; k++) {
@@ -726,14 +737,19 @@ __global__ void __launch_bounds__(256) k_lbd_pyrdown(LineDev D, int o) {
   }
   const int v = rows[0] + rows[4] + 4 * (rows[1] + rows[3]) + 6 * rows[2];
   D.g[(size_t)f * D.g_frame + Od.g_off + (size_t)y * Od.gstride + x] = (uint8_t)((v + 128) >> 8);
+  }
 }
 
 __global__ void __launch_bounds__(256) k_lbd_sobel(LineDev D, int o) {
   const OctDev& O = D.O[o];
-  const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6), f = blockIdx.z;
-  if (x >= O.lw || y >= O.lh) return;
+  const int x = blockIdx.x * 64 + (threadIdx.x & 63), f = blockIdx.z;
+  if (x >= O.lw) return;
   const int w = O.lw, h = O.lh;
   const uint8_t* src = D.g + (size_t)f * D.g_frame + O.g_off;
+#pragma unroll 1
+  for (int t = 0; t < kLbdTiles; t++) {
+  const int y = (blockIdx.y * kLbdTiles + t) * 4 + (threadIdx.x >> 6);
+  if (y >= h) break;
   const uint8_t* r0 = src + (size_t)reflect101(y - 1, h) * O.gstride;
   const uint8_t* r1 = src + (size_t)y * O.gstride;
   const uint8_t* r2 = src + (size_t)reflect101(y + 1, h) * O.gstride;
@@ -742,6 +758,7 @@ __global__ void __launch_bounds__(256) k_lbd_sobel(LineDev D, int o) {
   const int gy = ((int)r2[xm] + 2 * r2[x] + r2[xp]) - ((int)r0[xm] + 2 * r0[x] + r0[xp]);
   const size_t q = (size_t)f * D.lbd_frame + O.lbd_off + (size_t)y * w + x;
   D.sd[q] = make_short2((short)gx, (short)gy);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1157,7 +1174,7 @@ static int line_detect_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, in
   const int nl = o->nlevels;
   o->timer.begin(st);
   for (int l = 1; l < nl; l++) {
-    k_line_resize<<<dim3(div_up(D.O[l].w, 128), D.O[l].h, B), 128, 0, st>>>(D, l);
+    k_line_resize<<<dim3(div_up(D.O[l].w, 128), div_up(D.O[l].h, kResizeRows), B), 128, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "lsd_pyramid");
@@ -1298,11 +1315,11 @@ static int line_lbd_dev(sdpl_line* o, const uint8_t* d_imgs, int B, int w, int h
   k_lbd_blur_sobel<<<dim3(div_up(w, kLT_W), div_up(h, kLT_H), B), 256, 0, st>>>(D);
   SDPL_LAUNCH_CHECK();
   for (int l = 1; l < nl; l++) {
-    k_lbd_pyrdown<<<dim3(div_up(D.O[l].lw, 64), div_up(D.O[l].lh, 4), B), 256, 0, st>>>(D, l);
+    k_lbd_pyrdown<<<dim3(div_up(D.O[l].lw, 64), div_up(D.O[l].lh, 4 * kLbdTiles), B), 256, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
   for (int l = 1; l < nl; l++) {
-    k_lbd_sobel<<<dim3(div_up(D.O[l].lw, 64), div_up(D.O[l].lh, 4), B), 256, 0, st>>>(D, l);
+    k_lbd_sobel<<<dim3(div_up(D.O[l].lw, 64), div_up(D.O[l].lh, 4 * kLbdTiles), B), 256, 0, st>>>(D, l);
     SDPL_LAUNCH_CHECK();
   }
   o->timer.mark(st, "lbd_sobel");
